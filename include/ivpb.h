@@ -1,0 +1,150 @@
+/* ivpb.h -- C ABI of libivpb (ivp-b200): batched IVP solves on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of the Rust crate `ivp` (Ryan-D-Gast/ivp
+ * v0.5.1).  The reference has no FFI of its own; its boundary is the generic function
+ *     solve_ivp<F: IVP>(f, x0, xend, y0, options) -> Result<Solution, Error>
+ *                                              (reference src/solve/solve_ivp.rs:99-108)
+ * and the `IVP` trait (src/ivp.rs:27-121).  `ivpb_solve_batch` is the batched form of that
+ * call: N independent trajectories of one problem, each with its own y0 row and parameter
+ * row, integrated by the per-trajectory step loops of
+ *     DOP853::solve  src/methods/dop853.rs:114-656      DOPRI5::solve src/methods/dopri5.rs:122-464
+ *     RK23::solve    src/methods/rk23.rs:81-310         RK4::solve    src/methods/rk4.rs:64-226
+ *     RADAU::solve   src/methods/radau.rs:114-796       BDF::solve    src/methods/bdf.rs:86-615
+ * with the output handler DefaultSolOut::solout (src/solve/solout.rs:128-431) running on the
+ * device.  A Rust `ivp-batch` crate binds these symbols (rust/).
+ *
+ * Conventions: plain pointers and sizes only; all arrays row-major; return 0 on success,
+ * non-zero for configuration / CUDA / NVRTC errors (== reference `Error::Config`,
+ * src/error.rs:18-60; message via ivpb_last_error).  Numerical failures are NOT errors: they are
+ * reported per trajectory in `status[]` (reference src/status.rs:4-19, declaration order).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails loudly.
+ */
+#ifndef IVPB_H
+#define IVPB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/solve/options.rs:14-27 (enum Method, declaration order) */
+typedef enum {
+  IVPB_RK23 = 0, IVPB_DOPRI5 = 1, IVPB_DOP853 = 2, IVPB_RK4 = 3, IVPB_RADAU = 4, IVPB_BDF = 5
+} ivpb_method;
+
+/* reference src/status.rs:4-19 (enum Status, declaration order) */
+typedef enum {
+  IVPB_SUCCESS = 0, IVPB_USER_INTERRUPT = 1, IVPB_NEED_LARGER_NMAX = 2, IVPB_STEP_SIZE_TOO_SMALL = 3,
+  IVPB_PROBABLY_STIFF = 4, IVPB_SINGULAR_MATRIX = 5, IVPB_POOR_CONVERGENCE = 6
+} ivpb_status;
+
+/* Built-in problems: the RHS / events / Jacobian are __device__ functions compiled with the solver.
+ * n = state size, p = parameters per trajectory. */
+typedef enum {
+  IVPB_P_DECAY = 0,      /* y' = -k y                    n=1 p=1 (k)        reference examples/exponential_decay.rs:10-12 */
+  IVPB_P_VDP_EPS = 1,    /* y1' = ((1-y0^2) y1 - y0)/eps n=2 p=1 (eps)      reference examples/van_der_pol.rs:10-13 */
+  IVPB_P_VDP_MU = 2,     /* y1' = mu (1-y0^2) y1 - y0    n=2 p=1 (mu)       reference benches/benchmark.py:22-27 */
+  IVPB_P_LORENZ = 3,     /* n=3 p=3 (sigma, rho, beta)                      reference benches/benchmark.py:30-37 */
+  IVPB_P_CR3BP = 4,      /* n=6 p=1 (mu)                                    reference examples/cr3bp.rs:24-35 */
+  IVPB_P_BALL = 5,       /* n=2 p=2 (g, drag); event y[0], terminal, negative  examples/bouncing_ball.rs:11-31 */
+  IVPB_P_ROBERTSON = 6,  /* n=3 p=3 (0.04, 1e4, 3e7)                        reference tests/test_stiff.py:104-110 */
+  IVPB_P_SHO = 7,        /* y0'=y1, y1'=-y0  n=2 p=0; event y[0] (All, non-terminal)  reference tests/common.rs:3-9, tests/ivp.rs:151-220 */
+  IVPB_P_ZERO3 = 8,      /* y' = 0          n=3 p=0                         reference tests/ivp.rs:11-18 */
+  IVPB_P_EXP2 = 9,       /* y' = y          n=2 p=0                         reference tests/ivp.rs:291-297 */
+  IVPB_P_RATIONAL = 10,  /* n=2 p=0                                         reference tests/test_helpers.py:23-25 */
+  IVPB_P_CANNON = 11,    /* y' = [y1, -9.80665] n=2 p=0; event y[0], terminal, negative  reference tests/test_ivp.py:153-160 */
+  IVPB_P_BUILTIN_COUNT = 12
+} ivpb_builtin;
+
+/* Mirrors `Options` (reference src/solve/options.rs:75-123) plus the per-event `EventConfig`
+ * (src/solve/event.rs:5-27) that the reference takes from `IVP::event_config`. */
+typedef struct {
+  int32_t method;              /* ivpb_method; reference default DOPRI5 */
+  int32_t n_rtol, n_atol;      /* 1 = Tolerance::Scalar, n = Tolerance::Vector (src/methods/mod.rs:104-107) */
+  const double* rtol;          /* reference default 1e-3 */
+  const double* atol;          /* reference default 1e-6 */
+  int32_t has_first_step, has_max_step, has_min_step, has_max_steps;   /* Option<..> discriminants */
+  double first_step, max_step, min_step;
+  uint64_t max_steps;          /* None => usize::MAX (src/solve/solve_ivp.rs:187-273) */
+  int32_t has_t_eval;          /* Option<Vec<Float>>: Some(empty) is legal */
+  int32_t n_t_eval;
+  const double* t_eval;        /* shared by all trajectories; ascending (descending for tf < t0) */
+  int32_t dense_output;        /* reserved: per-trajectory segment log; does not change t/y */
+  int32_t n_event_cfg;         /* 0 => problem defaults; else must equal the problem's n_events */
+  const int32_t* ev_direction;        /* >0 Positive, <0 Negative, 0 All (src/solve/event.rs:68-77) */
+  const int64_t* ev_terminal_count;   /* <0 => None */
+  int32_t max_events;          /* capacity of ev_t / ev_y per event function per trajectory (>=1 if events) */
+  int32_t max_out;             /* step-mode (no t_eval) capacity of t_out / y_out per trajectory; 0 => samples not stored */
+  int32_t jac_mode;            /* 0 finite differences (src/ivp.rs:67-107), 1 analytic ivp_jac */
+  int32_t flags;               /* IVPB_FLAG_* */
+} ivpb_options;
+
+#define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
+                                  the reference's rounding, no FMA contraction) */
+#define IVPB_FLAG_NO_REFILL 2u /* static one-trajectory-per-thread schedule (debug / A-B measurements) */
+
+/* Per-trajectory outputs.  Any pointer may be NULL (= not wanted).  In ivpb_solve_batch they are
+ * HOST pointers, in ivpb_solve_batch_device DEVICE pointers.
+ * out_cap = has_t_eval ? n_t_eval + 1 : max_out   (+1: a terminal event appends its point,
+ * reference src/solve/solout.rs:315-324). */
+typedef struct {
+  int32_t* status;      /* [N]      ivpb_status                                         */
+  uint32_t* counters;   /* [N][6]   nfev, njev, nlu, nstep, naccpt, nrejct (src/solve/solution.rs:12-17) */
+  double* t_final;      /* [N]      last accepted x, or the event time if a terminal event fired */
+  double* y_final;      /* [N][n]   state at t_final                                    */
+  double* h_next;       /* [N]      IntegrationResult.h (src/methods/mod.rs:31-32)      */
+  int32_t* n_out;       /* [N]      samples the reference would hold in Solution.t (may exceed out_cap => truncated) */
+  double* t_out;        /* [N][out_cap]                                                 */
+  double* y_out;        /* [N][out_cap][n]                                              */
+  int32_t* ev_count;    /* [N][n_events]   hits per event function (may exceed max_events => truncated) */
+  double* ev_t;         /* [N][n_events][max_events]                                    */
+  double* ev_y;         /* [N][n_events][max_events][n]                                 */
+} ivpb_outputs;
+
+typedef struct ivpb_ctx ivpb_ctx;
+
+/* Context: owns the device set, one stream + work queue per device, compiled NVRTC modules.
+ * device_ids == NULL => the current device only. */
+int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices);
+void ivpb_destroy(ivpb_ctx* ctx);
+const char* ivpb_last_error(const ivpb_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
+int ivpb_device_count(const ivpb_ctx* ctx);
+
+/* Problem handles.  Built-ins: handle == ivpb_builtin id.  *n, *p, *n_events receive the sizes. */
+int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_events);
+/* User problem in CUDA C, compiled with NVRTC together with the solver templates.  `cuda_src` must define
+ *   __device__ void ivp_ode(double t, const double* y, const double* p, double* dydt);
+ * and, if n_events > 0 / has_jac,
+ *   __device__ void ivp_events(double t, const double* y, const double* p, double* g);
+ *   __device__ void ivp_jac(double t, const double* y, const double* p, double* J);  // row-major n x n
+ * (the IVP trait, reference src/ivp.rs:27-121, with the parameter row made explicit). */
+int ivpb_nvrtc_problem(ivpb_ctx* ctx, const char* cuda_src, int n, int p, int n_events, int has_jac,
+                       int* handle);
+
+/* Batched solve_ivp with HOST buffers (the call a Rust/C++/Python user makes): copies y0/params to the
+ * devices of the context (static contiguous split of [0,N)), solves, copies the requested outputs back.
+ * y0 [N][n], params [N][p] (NULL if p == 0). */
+int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0, double tf,
+                     const double* y0, const double* params, const ivpb_outputs* out);
+
+/* Same solve with DEVICE buffers resident on the context's first device, enqueued on `stream`
+ * (a cudaStream_t, may be NULL = default stream); returns after enqueueing. rtol/atol/t_eval/event
+ * config in `opt` stay host pointers (small, copied to constant-like device storage). */
+int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0,
+                            double tf, const double* d_y0, const double* d_params,
+                            const ivpb_outputs* d_out, void* stream);
+
+/* Kernels launched by this context so far (for bench.py's gpu_launches). */
+uint64_t ivpb_launch_count(const ivpb_ctx* ctx);
+
+/* FP64 FMA-pipe peak of the first device measured with a dependent-chain DFMA microbenchmark
+ * (TFLOP/s, FMA = 2 flop).  Used as the roofline denominator (MEASURED_PEAKS.json has no fp64 entry). */
+int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops);
+
+const char* ivpb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVPB_H */

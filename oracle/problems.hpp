@@ -1,0 +1,123 @@
+// problems.hpp -- the built-in problems as CPU functors for the oracle.  TEST INFRASTRUCTURE ONLY.
+// Each functor is the `IVP` trait impl (reference src/ivp.rs:27-121) of the cited reference program,
+// with the struct fields read from the trajectory's parameter row `p`.
+#pragma once
+#include "ivp_oracle.hpp"
+
+namespace oracle {
+
+template <class D, int N_, int P_, int NEV_>
+struct ProblemBase {
+  static constexpr int N = N_, P = P_, NEV = NEV_;
+  const double* p = nullptr;               // parameter row of this trajectory
+  const EventConfig* ev_cfg = nullptr;     // override of event_config (from ivpb_options), or null
+  int n_events() const { return NEV; }
+  void events(double, const double*, double*) const {}
+  EventConfig default_event_config(int) const { return EventConfig(); }
+  EventConfig event_config(int i) const {
+    return ev_cfg ? ev_cfg[i] : static_cast<const D*>(this)->default_event_config(i);
+  }
+  static constexpr bool HAS_JAC = false;
+  void jac(double, const double*, double*) const {}
+};
+
+struct Decay : ProblemBase<Decay, 1, 1, 0> {          // examples/exponential_decay.rs:10-12
+  void ode(double, const double* y, double* d) const { d[0] = -p[0] * y[0]; }
+};
+struct VdpEps : ProblemBase<VdpEps, 2, 1, 0> {        // examples/van_der_pol.rs:10-13
+  void ode(double, const double* y, double* d) const {
+    d[0] = y[1];
+    d[1] = ((1.0 - y[0] * y[0]) * y[1] - y[0]) / p[0];
+  }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* y, double* J) const {
+    J[0] = 0.0; J[1] = 1.0;
+    J[2] = (-2.0 * y[0] * y[1] - 1.0) / p[0];
+    J[3] = (1.0 - y[0] * y[0]) / p[0];
+  }
+};
+struct VdpMu : ProblemBase<VdpMu, 2, 1, 0> {          // benches/benchmark.py:22-27
+  void ode(double, const double* y, double* d) const {
+    d[0] = y[1];
+    d[1] = p[0] * (1.0 - y[0] * y[0]) * y[1] - y[0];
+  }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* y, double* J) const {
+    J[0] = 0.0; J[1] = 1.0;
+    J[2] = -2.0 * p[0] * y[0] * y[1] - 1.0;
+    J[3] = p[0] * (1.0 - y[0] * y[0]);
+  }
+};
+struct Lorenz : ProblemBase<Lorenz, 3, 3, 0> {        // benches/benchmark.py:30-37
+  void ode(double, const double* y, double* d) const {
+    d[0] = p[0] * (y[1] - y[0]);
+    d[1] = y[0] * (p[1] - y[2]) - y[1];
+    d[2] = y[0] * y[1] - p[2] * y[2];
+  }
+};
+struct Cr3bp : ProblemBase<Cr3bp, 6, 1, 0> {          // examples/cr3bp.rs:24-35
+  void ode(double, const double* s, double* d) const {
+    const double mu = p[0];
+    const double x = s[0], y = s[1], z = s[2], vx = s[3], vy = s[4], vz = s[5];
+    const double r1 = std::sqrt(sq(x + mu) + sq(y) + sq(z));
+    const double r2 = std::sqrt(sq(x - 1.0 + mu) + sq(y) + sq(z));
+    auto cube = [](double r) { return (r * r) * r; };   // powi(3)
+    d[0] = vx; d[1] = vy; d[2] = vz;
+    d[3] = x + 2.0 * vy - (1.0 - mu) * (x + mu) / cube(r1) - mu * (x - 1.0 + mu) / cube(r2);
+    d[4] = y - 2.0 * vx - (1.0 - mu) * y / cube(r1) - mu * y / cube(r2);
+    d[5] = -(1.0 - mu) * z / cube(r1) - mu * z / cube(r2);
+  }
+};
+struct Ball : ProblemBase<Ball, 2, 2, 1> {            // examples/bouncing_ball.rs:11-31
+  void ode(double, const double* s, double* d) const {
+    const double vy = s[1];
+    d[0] = vy;
+    d[1] = -p[0] - p[1] * vy * std::fabs(vy);
+  }
+  void events(double, const double* s, double* g) const { g[0] = s[0]; }
+  EventConfig default_event_config(int) const { EventConfig c; c.terminal_count = 1; c.direction = Direction::Negative; return c; }
+};
+struct Robertson : ProblemBase<Robertson, 3, 3, 0> {  // tests/test_stiff.py:104-110
+  void ode(double, const double* s, double* d) const {
+    const double x = s[0], y = s[1], z = s[2];
+    d[0] = -p[0] * x + p[1] * y * z;
+    d[1] = p[0] * x - p[1] * y * z - p[2] * y * y;
+    d[2] = p[2] * y * y;
+  }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* s, double* J) const {
+    const double y = s[1], z = s[2];
+    J[0] = -p[0];  J[1] = p[1] * z;                       J[2] = p[1] * y;
+    J[3] = p[0];   J[4] = -p[1] * z - 2.0 * p[2] * y;     J[5] = -p[1] * y;
+    J[6] = 0.0;    J[7] = 2.0 * p[2] * y;                 J[8] = 0.0;
+  }
+};
+struct Sho : ProblemBase<Sho, 2, 0, 1> {              // tests/common.rs:3-9; events tests/ivp.rs:151-220
+  void ode(double, const double* y, double* d) const { d[0] = y[1]; d[1] = -y[0]; }
+  void events(double, const double* y, double* g) const { g[0] = y[0]; }
+};
+struct Zero3 : ProblemBase<Zero3, 3, 0, 0> {          // tests/ivp.rs:11-18
+  void ode(double, const double*, double* d) const { d[0] = 0.0; d[1] = 0.0; d[2] = 0.0; }
+};
+struct Exp2 : ProblemBase<Exp2, 2, 0, 0> {            // tests/ivp.rs:291-297
+  void ode(double, const double* y, double* d) const { d[0] = y[0]; d[1] = y[1]; }
+};
+struct Rational : ProblemBase<Rational, 2, 0, 0> {    // tests/test_helpers.py:23-25
+  void ode(double t, const double* y, double* d) const {
+    d[0] = y[1] / t;
+    d[1] = y[1] * (y[0] + 2.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+  static constexpr bool HAS_JAC = true;                // tests/test_helpers.py:34-40
+  void jac(double t, const double* y, double* J) const {
+    J[0] = 0.0; J[1] = 1.0 / t;
+    J[2] = -2.0 * y[1] * y[1] / (t * (y[0] - 1.0) * (y[0] - 1.0));
+    J[3] = (y[0] + 4.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+};
+struct Cannon : ProblemBase<Cannon, 2, 0, 1> {        // tests/test_ivp.py:153-160
+  void ode(double, const double* y, double* d) const { d[0] = y[1]; d[1] = -9.80665; }
+  void events(double, const double* y, double* g) const { g[0] = y[0]; }
+  EventConfig default_event_config(int) const { EventConfig c; c.terminal_count = 1; c.direction = Direction::Negative; return c; }
+};
+
+}  // namespace oracle
