@@ -104,6 +104,13 @@ typedef struct {
 
 typedef struct ivpb_ctx ivpb_ctx;
 
+/* Return codes (0 = ok).  Non-zero mirrors the reference's `Err(Error::Config(..))` -- raised before any
+ * stepping -- or reports a CUDA / NVRTC failure. */
+#define IVPB_OK 0
+#define IVPB_ERR_CONFIG 1
+#define IVPB_ERR_CUDA 2
+#define IVPB_ERR_NVRTC 3
+
 /* Context: owns the device set, one stream + work queue per device, compiled NVRTC modules.
  * device_ids == NULL => the current device only. */
 int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices);
@@ -134,6 +141,11 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
 int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0,
                             double tf, const double* d_y0, const double* d_params,
                             const ivpb_outputs* d_out, void* stream);
+
+/* Pinned host memory for y0 / params / outputs, so the H2D / D2H copies of ivpb_solve_batch run at full
+ * PCIe rate and asynchronously (pageable buffers work too, but are staged by the driver). */
+void* ivpb_host_alloc(size_t bytes);
+void ivpb_host_free(void* p);
 
 /* Kernels launched by this context so far (for bench.py's gpu_launches). */
 uint64_t ivpb_launch_count(const ivpb_ctx* ctx);

@@ -1,0 +1,60 @@
+// ivpb_common.cuh -- shared device-side types for the sm_100a IVP kernels.
+// This header (and everything it is combined with) is compiled twice: ahead of time by nvcc for the
+// built-in problems, and at run time by NVRTC together with user CUDA C (`ivp_ode`, ...).  It therefore
+// uses no standard headers -- only CUDA built-ins.
+#pragma once
+
+namespace ivpb {
+
+typedef unsigned int u32;
+typedef long long i64;
+typedef unsigned long long u64;
+
+// Method codes == reference enum Method (src/solve/options.rs:14-27)
+enum { M_RK23 = 0, M_DOPRI5 = 1, M_DOP853 = 2, M_RK4 = 3, M_RADAU = 4, M_BDF = 5 };
+// Status codes == reference enum Status (src/status.rs:4-19)
+enum { ST_SUCCESS = 0, ST_INTERRUPT = 1, ST_NMAX = 2, ST_SMALL = 3, ST_STIFF = 4, ST_SINGULAR = 5, ST_POOR = 6 };
+// Output-handler features a kernel instance is specialised for (what DefaultSolOut has to do,
+// reference src/solve/solout.rs:128-431).  FEAT == 0: final state + counters only, and the dense-output
+// coefficients nobody would read are not computed.
+enum { F_TEVAL = 1, F_STEPOUT = 2, F_EVENTS = 4 };
+
+constexpr int MAX_N = 32;       // thread-per-trajectory kernels: state size limit
+constexpr int MAX_EVENTS_FN = 8;  // event functions per problem
+
+// Kernel arguments (one struct by value; ~1 KB of the 4 KB parameter space).  Host layout must match:
+// the runtime fills this struct for nvcc-built kernels and memcpy's the same bytes for NVRTC kernels.
+struct KArgs {
+  i64 N;                 // trajectories in this launch (this device's shard)
+  double t0, tf;
+  const double* y0;      // [N][n] row-major
+  const double* params;  // [N][p] row-major (may be null when p == 0)
+  u64* queue;            // work-queue head (atomicAdd), zeroed before launch
+  double rtol[MAX_N], atol[MAX_N];   // scalar tolerances are broadcast by the host
+  double first_step, max_step, min_step;
+  int has_first_step, has_max_step, has_min_step, static_sched;
+  u64 max_steps;         // usize::MAX when Options.max_steps is None
+  const double* t_eval;  // device copy, [n_t_eval]
+  int n_t_eval, out_cap;
+  int max_events, jac_mode;
+  int ev_dir[MAX_EVENTS_FN];
+  i64 ev_term[MAX_EVENTS_FN];   // < 0: not terminal
+  // outputs (any may be null)
+  int* status;
+  u32* counters;
+  double* t_final;
+  double* y_final;
+  double* h_next;
+  int* n_out;
+  double* t_out;
+  double* y_out;
+  int* ev_count;
+  double* ev_t;
+  double* ev_y;
+};
+
+__device__ __forceinline__ double signum(double x) {   // f64::signum: +-1 by sign bit, NaN -> NaN
+  return (x != x) ? x : copysign(1.0, x);
+}
+
+}  // namespace ivpb

@@ -1,0 +1,814 @@
+// ivpb_erk.cuh -- persistent explicit Runge-Kutta ensemble kernel for sm_100a (fp64).
+//
+// One trajectory per thread.  All stage vectors live in registers (fully unrolled, table-driven
+// stage sums whose slot indices fold at compile time), the Butcher coefficients become constant-bank
+// operands of DFMA, and every thread runs the reference's own controller:
+//   DOP853  reference src/methods/dop853.rs:114-670      DOPRI5  src/methods/dopri5.rs:122-478
+//   RK23    reference src/methods/rk23.rs:81-321         RK4     src/methods/rk4.rs:64-244
+//   hinit   reference src/methods/mod.rs:217-281
+// followed, when outputs are requested, by the device form of DefaultSolOut::solout
+// (reference src/solve/solout.rs:128-431): t_eval sampling, step-mode capture, the first_step rule,
+// event sign tests + Brent root finding on the step interpolant, terminal counts.
+//
+// Scheduling: a persistent grid; lanes whose trajectory finished pull the next index from a global
+// atomic work queue (warp-aggregated), so step-count divergence between trajectories does not idle
+// the SM.  `static_sched` keeps the plain one-thread-one-trajectory mapping for A/B measurements.
+#pragma once
+#include "ivpb_common.cuh"
+#include "dop853_tableau.cuh"
+
+namespace ivpb {
+
+enum { K_OUT = 1, K_EVENTS = 2 };   // kernel feature bits (template parameter FEAT)
+
+template <int METHOD> struct MethodTraits;
+template <> struct MethodTraits<M_RK23>   { static constexpr int NC = 4, IORD = 3; };
+template <> struct MethodTraits<M_DOPRI5> { static constexpr int NC = 5, IORD = 5; };
+template <> struct MethodTraits<M_DOP853> { static constexpr int NC = 8, IORD = 8; };
+template <> struct MethodTraits<M_RK4>    { static constexpr int NC = 4, IORD = 4; };
+
+// ---------------------------------------------------------------------------------------------
+// Step interpolants (Method::interpolate).  cont is coefficient-major: c[coef][state].
+template <int METHOD, int N>
+__device__ __forceinline__ void erk_interp(double xi, double* yi, const double (&c)[MethodTraits<METHOD>::NC][N],
+                                           double xold, double h) {
+  if constexpr (METHOD == M_DOP853) {          // dop853.rs:659-670
+    const double s = (xi - xold) / h, s1 = 1.0 - s;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double conpar = c[4][i] + s * (c[5][i] + s1 * (c[6][i] + s * c[7][i]));
+      yi[i] = c[0][i] + s * (c[1][i] + s1 * (c[2][i] + s * (c[3][i] + s1 * conpar)));
+    }
+  } else if constexpr (METHOD == M_DOPRI5) {   // dopri5.rs:467-478
+    const double th = (xi - xold) / h, th1 = 1.0 - th;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      yi[i] = c[0][i] + th * (c[1][i] + th1 * (c[2][i] + th * (c[3][i] + th1 * c[4][i])));
+  } else if constexpr (METHOD == M_RK23) {     // rk23.rs:313-321
+    const double xc = (xi - xold) / h, x2 = xc * xc, x3 = x2 * xc;
+#pragma unroll
+    for (int i = 0; i < N; ++i) yi[i] = c[0][i] + h * (c[1][i] * xc + c[2][i] * x2 + c[3][i] * x3);
+  } else {                                      // rk4.rs:229-244 (cubic Hermite, cont = [y_old, k4 stage, f_new, y_new])
+    const double t = (xi - xold) / h, t2 = t * t, t3 = t2 * t;
+    const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
+    const double h01 = -2.0 * t3 + 3.0 * t2, h11 = t3 - t2;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      yi[i] = h00 * c[0][i] + h10 * h * c[1][i] + h01 * c[3][i] + h11 * h * c[2][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device DefaultSolOut (reference src/solve/solout.rs:15-432), state kept per thread.
+template <class Prob, int METHOD, int FEAT>
+struct SolOutDev {
+  static constexpr int N = Prob::N;
+  static constexpr int NEV = (FEAT & K_EVENTS) ? Prob::NEV : 0;
+  static constexpr int NEVS = NEV > 0 ? NEV : 1;
+  static constexpr int NC = MethodTraits<METHOD>::NC;
+  static constexpr double TOL = 1e-12;      // solout.rs:86
+
+  int next_idx, n_out;
+  double last_t;                 // self.t.last()
+  bool first_output_done, have_prev;
+  double prev_g[NEVS];
+  int hits[NEVS];
+  double yold[(NEV > 0) ? N : 1];
+
+  __device__ __forceinline__ void reset() {
+    next_idx = 0; n_out = 0; last_t = 0.0; first_output_done = false; have_prev = false;
+#pragma unroll
+    for (int e = 0; e < NEVS; ++e) { prev_g[e] = 0.0; hits[e] = 0; }
+  }
+
+  __device__ __forceinline__ void push(const KArgs& a, i64 idx, double t, const double* yv) {
+    if (n_out < a.out_cap) {
+      const i64 o = idx * (i64)a.out_cap + n_out;
+      if (a.t_out) a.t_out[o] = t;
+      if (a.y_out) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.y_out[o * N + i] = yv[i];
+      }
+    }
+    last_t = t;
+    ++n_out;
+  }
+
+  static __device__ __forceinline__ bool crossed(double l, double r, int dir) {   // solout.rs:168-176
+    if (dir == 0) return (l <= 0.0 && r >= 0.0) || (l >= 0.0 && r <= 0.0);
+    if (dir > 0) return l < 0.0 && r >= 0.0;
+    return l > 0.0 && r <= 0.0;
+  }
+
+  // Returns true for ControlFlag::Interrupt; then (tev, yev) hold the terminal event point.
+  // `first` marks the initial callback (interpolant == None, xold == x).
+  __device__ __forceinline__ bool solout(const KArgs& a, i64 idx, const double* p, bool first, double xold, double x,
+                                         const double* y, const double (&cont)[NC][N], double hstep,
+                                         double& tev, double* yev) {
+    if constexpr (NEV > 0) {
+      double g[NEV];
+      Prob::events(x, y, p, g);
+      if (!have_prev) {            // solout.rs:163-164 (yold.is_empty())
+#pragma unroll
+        for (int e = 0; e < NEV; ++e) prev_g[e] = g[e];
+      } else {
+        double det_t[NEV], det_y[NEV][N];
+        int det_i[NEV], ndet = 0;
+#pragma unroll
+        for (int e = 0; e < NEV; ++e) {
+          const double g_prev = prev_g[e], g_c = g[e];
+          if (!crossed(g_prev, g_c, a.ev_dir[e])) continue;
+          const double XTOL = 2e-12, RTOL = 2.220446049250313e-16;
+          double aa = xold, b = x, fa = g_prev, fb = g_c;
+          double et, ey[N];
+          if (fabs(fa) <= XTOL) {
+            et = aa;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ey[i] = yold[i];
+          } else if (fabs(fb) <= XTOL) {
+            et = b;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ey[i] = y[i];
+          } else {                 // Brent, solout.rs:204-291
+            double c = aa, fc = fa, d = b - aa, ee = d;
+            double gm[NEV];
+            for (int it = 0; it < 100; ++it) {
+              if (fb * fc > 0.0) { c = aa; fc = fa; d = b - aa; ee = d; }
+              if (fabs(fc) < fabs(fb)) { aa = b; b = c; c = aa; fa = fb; fb = fc; fc = fa; }
+              const double tol1 = 2.0 * RTOL * fabs(b) + 0.5 * XTOL;
+              const double xm = 0.5 * (c - b);
+              if (fabs(xm) <= tol1 || fb == 0.0) break;
+              if (fabs(ee) >= tol1 && fabs(fa) > fabs(fb)) {
+                double s, pp, q;
+                if (aa == c) {
+                  s = fb / fa; pp = 2.0 * xm * s; q = 1.0 - s;
+                } else {
+                  const double qv = fa / fc, r = fb / fc;
+                  s = fb / fa;
+                  pp = s * (2.0 * xm * qv * (qv - r) - (b - aa) * (r - 1.0));
+                  q = (qv - 1.0) * (r - 1.0) * (s - 1.0);
+                }
+                if (q > 0.0) pp = -pp; else q = -q;
+                if (2.0 * pp < fmin(3.0 * xm * q - fabs(tol1 * q), fabs(ee * q))) { ee = d; d = pp / q; }
+                else { d = xm; ee = d; }
+              } else { d = xm; ee = d; }
+              aa = b; fa = fb;
+              if (fabs(d) > tol1) b += d;
+              else b += (xm > 0.0 ? tol1 : -tol1);
+              erk_interp<METHOD, N>(b, ey, cont, xold, hstep);
+              Prob::events(b, ey, p, gm);
+              fb = gm[e];
+            }
+            erk_interp<METHOD, N>(b, ey, cont, xold, hstep);
+            et = b;
+          }
+          // append at position ndet (compile-time slot selected by predicate)
+#pragma unroll
+          for (int j = 0; j < NEV; ++j)
+            if (j == ndet) {
+              det_t[j] = et; det_i[j] = e;
+#pragma unroll
+              for (int i = 0; i < N; ++i) det_y[j][i] = ey[i];
+            }
+          ++ndet;
+        }
+        {  // stable sort by time, descending for backward integration (solout.rs:297-303)
+          const bool forward = x > xold;
+#pragma unroll
+          for (int u = 1; u < NEV; ++u) {
+#pragma unroll
+            for (int v = u; v > 0; --v) {
+              const bool sw = v < ndet && (forward ? (det_t[v] < det_t[v - 1]) : (det_t[v] > det_t[v - 1]));
+              if (sw) {
+                double tt = det_t[v]; det_t[v] = det_t[v - 1]; det_t[v - 1] = tt;
+                int ti = det_i[v]; det_i[v] = det_i[v - 1]; det_i[v - 1] = ti;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { double ty = det_y[v][i]; det_y[v][i] = det_y[v - 1][i]; det_y[v - 1][i] = ty; }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NEV; ++j) {
+          if (j >= ndet) break;
+          // det_i[j] is a run-time value: select the matching compile-time slot
+#pragma unroll
+          for (int e = 0; e < NEV; ++e) {
+            if (det_i[j] != e) continue;
+            if (hits[e] < a.max_events) {
+              const i64 o = (idx * NEV + e) * (i64)a.max_events + hits[e];
+              if (a.ev_t) a.ev_t[o] = det_t[j];
+              if (a.ev_y) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.ev_y[o * N + i] = det_y[j][i];
+              }
+            }
+            hits[e] += 1;
+            if (a.ev_term[e] >= 0 && (i64)hits[e] >= a.ev_term[e]) {
+              push(a, idx, det_t[j], det_y[j]);        // solout.rs:315-324
+              tev = det_t[j];
+#pragma unroll
+              for (int i = 0; i < N; ++i) yev[i] = det_y[j][i];
+#pragma unroll
+              for (int q = 0; q < NEV; ++q) prev_g[q] = g[q];
+              return true;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < NEV; ++e) prev_g[e] = g[e];
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) yold[i] = y[i];
+      have_prev = true;
+    }
+
+    if constexpr ((FEAT & K_OUT) != 0) {
+      if (a.n_t_eval >= 0) {       // Mode 1: t_eval (n_t_eval == -1 encodes Option::None)
+        int i = next_idx;
+        if (fabs(xold - x) <= TOL) {
+          while (i < a.n_t_eval && fabs(a.t_eval[i] - x) <= TOL) { push(a, idx, a.t_eval[i], y); ++i; }
+        } else {
+          double yi[N];
+          if (x > xold) {
+            while (i < a.n_t_eval) {
+              const double te = a.t_eval[i];
+              if (!(te <= x + TOL)) break;
+              if (te >= xold - TOL) { erk_interp<METHOD, N>(te, yi, cont, xold, hstep); push(a, idx, te, yi); }
+              ++i;
+            }
+          } else {
+            while (i < a.n_t_eval) {
+              const double te = a.t_eval[i];
+              if (!(te >= x - TOL)) break;
+              if (te <= xold + TOL) { erk_interp<METHOD, N>(te, yi, cont, xold, hstep); push(a, idx, te, yi); }
+              ++i;
+            }
+          }
+        }
+        next_idx = i;
+      } else if (a.out_cap > 0) {  // Mode 2: accepted step endpoints
+        if (a.has_first_step && !first_output_done && fabs(xold - x) > TOL) {   // solout.rs:392-421
+          const double direction = signum(x - xold);
+          const double target = a.t0 + direction * a.first_step;
+          if (direction * (x - target) >= -TOL) {
+            if (!first) {
+              double yi[N];
+              erk_interp<METHOD, N>(target, yi, cont, xold, hstep);
+              push(a, idx, target, yi);
+              first_output_done = true;
+            }
+            if (fabs(x - target) > TOL) push(a, idx, x, y);
+          }
+          return false;
+        }
+        if (n_out == 0 || fabs(last_t - x) > TOL) push(a, idx, x, y);
+      }
+    }
+    return false;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread trajectory state + the step loops.
+template <class Prob, int METHOD, int FEAT>
+struct ErkTraj {
+  static constexpr int N = Prob::N, P = Prob::P;
+  static constexpr int PS = P > 0 ? P : 1;
+  static constexpr bool DENSE = FEAT != 0;
+  static constexpr int NC = MethodTraits<METHOD>::NC;
+  using Out = SolOutDev<Prob, METHOD, FEAT>;
+
+  i64 idx;
+  double x, h;
+  double y[N], k1[N], p[PS];
+  double facold, hlamb;
+  u32 nfev, nstep, naccpt, nrejct;
+  int iasti, nonstiff, status;
+  bool last, reject;
+  Out so;
+
+  __device__ __forceinline__ double rt(const KArgs& a, int i) const { return a.rtol[i]; }
+  __device__ __forceinline__ double at(const KArgs& a, int i) const { return a.atol[i]; }
+
+  // hinit -- reference src/methods/mod.rs:217-281 (f0 == k1)
+  __device__ __forceinline__ double hinit(const KArgs& a, double posneg, double hmax) {
+    double dnf = 0.0, dny = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double sk = at(a, i) + rt(a, i) * fabs(y[i]);
+      dnf += (k1[i] / sk) * (k1[i] / sk);
+      dny += (y[i] / sk) * (y[i] / sk);
+    }
+    double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
+    if (hh > fabs(hmax)) hh = fabs(hmax);
+    hh = fabs(hh) * signum(posneg);
+    double y1[N], f1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y1[i] = y[i] + hh * k1[i];
+    Prob::ode(x + hh, y1, p, f1);
+    double der2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double sk = at(a, i) + rt(a, i) * fabs(y[i]);
+      const double df = (f1[i] - k1[i]) / sk;
+      der2 += df * df;
+    }
+    der2 = sqrt(der2) / fabs(hh);
+    const double der12 = fmax(fabs(der2), sqrt(dnf));
+    const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3)
+                                         : pow(0.01 / der12, 1.0 / (double)MethodTraits<METHOD>::IORD);
+    const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));   // mod.rs:279 quirk kept
+    return fabs(hf) * signum(posneg);
+  }
+
+  __device__ __forceinline__ double hmax_of(const KArgs& a) const {
+    if (!a.has_max_step) return fabs(a.tf - a.t0);
+    if constexpr (METHOD == M_DOPRI5) return a.max_step;      // dopri5.rs:180 (no abs)
+    return fabs(a.max_step);                                   // dop853.rs:172-175, rk23.rs:135
+  }
+
+  // Everything the reference does before its main loop; returns true if the trajectory is already done.
+  __device__ __forceinline__ bool init(const KArgs& a, i64 index) {
+    idx = index;
+    x = a.t0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = a.y0[index * N + i];
+    if constexpr (P > 0) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) p[i] = a.params[index * P + i];
+    }
+    facold = 1e-4; hlamb = 0.0;
+    nfev = 0; nstep = 0; naccpt = 0; nrejct = 0;
+    iasti = 0; nonstiff = 0; status = ST_SUCCESS;
+    last = false; reject = false;
+    so.reset();
+    const double posneg = signum(a.tf - a.t0);
+    Prob::ode(x, y, p, k1);
+    if constexpr (METHOD == M_RK4) {
+      h = a.has_first_step ? a.first_step : (a.tf - a.t0) / 100.0;    // solve_ivp.rs:185; rk4.rs:116 (not counted)
+    } else {
+      nfev = 1;
+      if (a.has_first_step) h = fabs(a.first_step) * posneg;
+      else { nfev = 2; h = hinit(a, posneg, hmax_of(a)); }
+    }
+    if constexpr (FEAT != 0) {
+      double cont[NC][N];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
+      double tev, yev[N];
+      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, tev, yev)) { status = ST_INTERRUPT; return true; }
+    }
+    return false;
+  }
+
+  __device__ __forceinline__ void finish(const KArgs& a, bool term, double tev, const double* yev) {
+    if (a.status) a.status[idx] = status;
+    if (a.counters) {
+      u32* c = a.counters + idx * 6;
+      c[0] = nfev; c[1] = 0u; c[2] = 0u; c[3] = nstep; c[4] = naccpt; c[5] = nrejct;
+    }
+    if (a.t_final) a.t_final[idx] = term ? tev : x;
+    if (a.y_final) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) a.y_final[idx * N + i] = term ? yev[i] : y[i];
+    }
+    if (a.h_next) a.h_next[idx] = h;
+    if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
+    if constexpr (Out::NEV > 0) {
+      if (a.ev_count) {
+#pragma unroll
+        for (int e = 0; e < Out::NEV; ++e) a.ev_count[idx * Out::NEV + e] = so.hits[e];
+      }
+    }
+  }
+
+  // One attempted step.  Returns true when the trajectory has ended (status set, results written).
+  __device__ __forceinline__ bool step(const KArgs& a);
+};
+
+// Table-driven linear combination: acc = sum_j COEF[j] * k[SLOT[j]][i], left to right.
+#define IVPB_LINCOMB(acc, LEN, SLOT, COEF, KARR, i)                               \
+  double acc = (COEF)[0] * (KARR)[(SLOT)[0]][i];                                  \
+  _Pragma("unroll") for (int j_ = 1; j_ < 9; ++j_) if (j_ < (LEN)) acc += (COEF)[j_] * (KARR)[(SLOT)[j_]][i];
+
+template <class Prob, int METHOD, int FEAT>
+__device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a) {
+  const double xend = a.tf;
+  const double posneg = signum(a.tf - a.t0);
+  double tev = 0.0, yev[N];
+  bool term = false;
+
+  if constexpr (METHOD == M_DOP853) {
+    // ---- reference src/methods/dop853.rs:272-653 ----
+    IVPB_DOP853_TABLES
+    const double uround = 2.3e-16, safe = 0.9;
+    const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0;      // beta = 0 => facold^beta == 1 exactly
+    const double h_max = hmax_of(a);
+    if ((u64)nstep > a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; finish(a, false, 0.0, y); return true; }
+    if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+    nstep += 1;
+
+    double k[10][N], y1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) k[0][i] = k1[i];
+#pragma unroll
+    for (int s = 0; s < 11; ++s) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (STG_LEN[s] == 1) {
+          y1[i] = y[i] + h * STG_COEF[s][0] * k[STG_SLOT[s][0]][i];        // (h*a21)*k1, dop853.rs:296
+        } else {
+          IVPB_LINCOMB(acc, STG_LEN[s], STG_SLOT[s], STG_COEF[s], k, i)
+          y1[i] = y[i] + h * acc;
+        }
+      }
+      const double ts = (s == 10) ? (x + h) : (x + STG_C[s] * h);
+      Prob::ode(ts, y1, p, k[STG_OUT[s]]);
+    }
+    const double xph = x + h;
+    nfev += 11;
+    // k4 = sum b_j k_j ; k5 = y + h k4      (slots 3 and 4)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      IVPB_LINCOMB(acc, LIN_LEN[0], LIN_SLOT[0], LIN_COEF[0], k, i)
+      k[3][i] = acc;
+      k[4][i] = y[i] + h * acc;
+    }
+    double err = 0.0, err2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(k[4][i]));
+      double erri = k[3][i] - BHH[0] * k[0][i] - BHH[1] * k[8][i] - BHH[2] * k[2][i];
+      const double q2 = erri / sk;
+      err2 += q2 * q2;
+      IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], LIN_COEF[1], k, i)
+      const double q1 = e8 / sk;
+      err += q1 * q1;
+    }
+    double deno = err + 0.01 * err2;
+    if (deno <= 0.0) deno = 1.0;
+    err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
+    const double fac11 = pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
+    double fac = fmax(facc2, fmin(facc1, fac11 / safe));
+    double hnew = h / fac;
+
+    if (err <= 1.0) {
+      facold = fmax(err, 1.0e-4);
+      naccpt += 1;
+      Prob::ode(xph, k[4], p, k[3]);
+      nfev += 1;
+      if ((naccpt % 1000u == 0u) || (iasti > 0)) {            // stiffness detection, dop853.rs:447-472
+        double stnum = 0.0, stden = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double d1 = k[3][i] - k[2][i], d2 = k[4][i] - y1[i];
+          stnum += d1 * d1; stden += d2 * d2;
+        }
+        if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
+        if (hlamb > 6.1) {
+          nonstiff = 0; iasti += 1;
+          if (iasti == 15) { status = ST_STIFF; finish(a, false, 0.0, y); return true; }
+        } else {
+          nonstiff += 1;
+          if (nonstiff == 6) iasti = 0;
+        }
+      }
+      // The reference always builds the dense coefficients (3 extra RHS calls).  They cannot influence
+      // y, h or err, so FEAT == 0 skips the arithmetic but still counts the evaluations (dop853.rs:560).
+      nfev += 3;
+      double cont[NC][N];
+      if constexpr (DENSE) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          cont[0][i] = y[i];
+          const double ydiff = k[4][i] - y[i];
+          cont[1][i] = ydiff;
+          const double bspl = h * k[0][i] - ydiff;
+          cont[2][i] = bspl;
+          cont[3][i] = ydiff - h * k[3][i] - bspl;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            IVPB_LINCOMB(acc, DF_LEN[r], DF_SLOT[r], DF_COEF[r], k, i)
+            cont[4 + r][i] = acc;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            IVPB_LINCOMB(acc, DSTG_LEN[s], DSTG_SLOT[s], DSTG_COEF[s], k, i)
+            y1[i] = y[i] + h * acc;
+          }
+          Prob::ode(x + DSTG_C[s] * h, y1, p, k[DSTG_OUT[s]]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            double acc = cont[4 + r][i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += DS_COEF[r][j] * k[DS_SLOT[r][j]][i];
+            cont[4 + r][i] = h * acc;
+          }
+        }
+      }
+      const double xold = x;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { k1[i] = k[3][i]; y[i] = k[4][i]; }
+      x = xph;
+      if constexpr (FEAT != 0) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+        }
+      }
+      if (last) { h = hnew; status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+      if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
+      if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
+    } else {
+      hnew = h / fmin(facc1, fac11 / safe);
+      reject = true;
+      if (naccpt > 1u) nrejct += 1;
+      last = false;
+    }
+    h = hnew;
+    (void)term;
+    return false;
+
+  } else if constexpr (METHOD == M_DOPRI5) {
+    // ---- reference src/methods/dopri5.rs:266-461 ----
+    constexpr double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
+    constexpr int S_LEN[6] = {1, 2, 3, 4, 5, 5};
+    constexpr int S_SLOT[6][5] = {{0, 0, 0, 0, 0}, {0, 1, 0, 0, 0}, {0, 1, 2, 0, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 4}, {0, 2, 3, 4, 5}};
+    constexpr double S_COEF[6][5] = {
+        {0.2, 0, 0, 0, 0},
+        {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0},
+        {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0},
+        {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0},
+        {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},
+        {35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+    constexpr int S_OUT[6] = {1, 2, 3, 4, 5, 1};
+    constexpr double S_C[6] = {c2, c3, c4, c5, 1.0, 1.0};
+    // e / d rows over slots {k1,k3,k4,k5,k6,k2(new)}
+    constexpr int ED_SLOT[6] = {0, 2, 3, 4, 5, 1};
+    constexpr double E_COEF[6] = {71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0};
+    constexpr double D_COEF[6] = {-12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
+                                  701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
+    const double uround = 2.3e-16, safe = 0.9, beta = 0.04;
+    const double facc1 = 1.0 / 0.2, facc2 = 1.0 / 10.0;
+    const double expo1 = 0.2 - beta * 0.75;
+    const double h_max = hmax_of(a);
+    if ((u64)nstep > a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; finish(a, false, 0.0, y); return true; }
+    if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+    nstep += 1;
+
+    double k[6][N], y1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) k[0][i] = k1[i];
+    const double xph = x + h;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (S_LEN[s] == 1) {
+          y1[i] = y[i] + h * S_COEF[s][0] * k[S_SLOT[s][0]][i];
+        } else {
+          double acc = S_COEF[s][0] * k[S_SLOT[s][0]][i];
+#pragma unroll
+          for (int j = 1; j < 5; ++j) if (j < S_LEN[s]) acc += S_COEF[s][j] * k[S_SLOT[s][j]][i];
+          y1[i] = y[i] + h * acc;
+        }
+      }
+      const double ts = (s >= 4) ? xph : (x + S_C[s] * h);
+      Prob::ode(ts, y1, p, k[S_OUT[s]]);
+    }
+    nfev += 6;
+    double cont[NC][N];
+    if constexpr (DENSE) {                                       // dopri5.rs:328-334
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = D_COEF[0] * k[ED_SLOT[0]][i];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) acc += D_COEF[j] * k[ED_SLOT[j]][i];
+        cont[4][i] = h * acc;
+      }
+    }
+    double err = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {                                // k4 <- scaled error vector, dopri5.rs:337-340
+      double acc = E_COEF[0] * k[ED_SLOT[0]][i];
+#pragma unroll
+      for (int j = 1; j < 6; ++j) acc += E_COEF[j] * k[ED_SLOT[j]][i];
+      k[3][i] = acc * h;
+      const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
+      err += (k[3][i] / sk) * (k[3][i] / sk);
+    }
+    err = sqrt(err / (double)N);
+    const double fac11 = pow(err, expo1);
+    double fac = fac11 / pow(facold, beta);
+    fac = fmax(facc2, fmin(facc1, fac / safe));
+    double hnew = h / fac;
+
+    if (err <= 1.0) {
+      facold = fmax(err, 1.0e-4);
+      naccpt += 1;
+      if ((naccpt % 1000u == 0u) || (iasti > 0)) {              // dopri5.rs:364-391 (uses overwritten k4: quirk kept)
+        double stnum = 0.0, stden = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double d1 = k[1][i] - k[5][i];
+          const double ysti = y[i] + h * (S_COEF[4][0] * k[0][i] + S_COEF[4][1] * k[1][i] + S_COEF[4][2] * k[2][i] +
+                                          S_COEF[4][3] * k[3][i] + S_COEF[4][4] * k[4][i]);
+          const double d2 = y1[i] - ysti;
+          stnum += d1 * d1; stden += d2 * d2;
+        }
+        if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
+        if (hlamb > 3.25) {
+          nonstiff = 0; iasti += 1;
+          if (iasti == 15) { status = ST_STIFF; finish(a, false, 0.0, y); return true; }
+        } else {
+          nonstiff += 1;
+          if (nonstiff == 6) iasti = 0;
+        }
+      }
+      if constexpr (DENSE) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double ydiff = y1[i] - y[i];
+          const double bspl = h * k[0][i] - ydiff;
+          cont[0][i] = y[i];
+          cont[1][i] = ydiff;
+          cont[2][i] = bspl;
+          cont[3][i] = -h * k[1][i] + ydiff - bspl;
+        }
+      }
+      const double xold = x;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { k1[i] = k[1][i]; y[i] = y1[i]; }
+      x = xph;
+      if constexpr (FEAT != 0) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+        }
+      }
+      if (last) { h = hnew; status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+      if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
+      if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
+    } else {
+      hnew = h / fmin(facc1, fac11 / safe);
+      reject = true;
+      if (naccpt > 1u) nrejct += 1;
+      last = false;
+    }
+    h = hnew;
+    return false;
+
+  } else if constexpr (METHOD == M_RK23) {
+    // ---- reference src/methods/rk23.rs:189-307 ----
+    constexpr double b1 = 2.0 / 9.0, b2 = 1.0 / 3.0, b3 = 4.0 / 9.0;
+    constexpr double e1 = 5.0 / 72.0, e2 = -1.0 / 12.0, e3 = -1.0 / 9.0, e4 = 1.0 / 8.0;
+    constexpr double d21 = -4.0 / 3.0, d22 = 1.0, d23 = 4.0 / 3.0, d24 = -1.0;
+    constexpr double d31 = 5.0 / 9.0, d32 = -2.0 / 3.0, d33 = -8.0 / 9.0, d34 = 1.0;
+    const double safe = 0.9, scale_min = 0.2, scale_max = 10.0, expo = -1.0 / 3.0;
+    const double hmax = hmax_of(a);
+    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    if ((x + h - xend) * posneg > 0.0) h = xend - x;
+    double k2[N], k3[N], k4[N], yt[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k1[i];
+    Prob::ode(x + 0.5 * h, yt, p, k2);
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.75 * k2[i];
+    Prob::ode(x + 0.75 * h, yt, p, k3);
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * (b1 * k1[i] + b2 * k2[i] + b3 * k3[i]);
+    Prob::ode(x + h, yt, p, k4);
+    nfev += 3;
+    double err = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double ye = h * (e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i]);
+      const double tol = at(a, i) + rt(a, i) * fmax(fabs(yt[i]), fabs(y[i]));
+      const double q = ye / tol;
+      err += q * q;
+    }
+    err = sqrt(err / (double)N);
+    if (err <= 1.0) {
+      nstep += 1; naccpt += 1;
+      const double xold = x;
+      double cont[NC][N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if constexpr (DENSE) {
+          cont[0][i] = y[i];
+          cont[1][i] = k1[i];
+          cont[2][i] = d21 * k1[i] + d22 * k2[i] + d23 * k3[i] + d24 * k4[i];
+          cont[3][i] = d31 * k1[i] + d32 * k2[i] + d33 * k3[i] + d34 * k4[i];
+        }
+        y[i] = yt[i];
+      }
+      x += h;
+      if constexpr (FEAT != 0) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) k1[i] = k4[i];
+      h *= fmax(fmin(safe * pow(err, expo), scale_max), scale_min);
+      if (fabs(h) > hmax) h = hmax * posneg;
+      if (x == xend) { status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+    } else {
+      nrejct += 1;
+      h *= fmax(fmin(safe * pow(err, expo), 1.0), scale_min);
+    }
+    return false;
+
+  } else {
+    // ---- RK4: reference src/methods/rk4.rs:141-222 ----
+    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    const bool lst = (x + 1.01 * h - xend) * signum(h) > 0.0;
+    double k2[N], k3[N], k4[N], yt[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k1[i];
+    Prob::ode(x + 0.5 * h, yt, p, k2);
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k2[i];
+    Prob::ode(x + 0.5 * h, yt, p, k3);
+#pragma unroll
+    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 1.0 * k3[i];
+    Prob::ode(x + 1.0 * h, yt, p, k4);
+    const double xold = x;
+    double cont[NC][N];
+    x += h;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if constexpr (DENSE) { cont[0][i] = y[i]; cont[1][i] = k4[i]; }
+      y[i] += h * ((1.0 / 6.0) * k1[i] + (1.0 / 3.0) * k2[i] + (1.0 / 3.0) * k3[i] + (1.0 / 6.0) * k4[i]);
+    }
+    Prob::ode(x, y, p, k1);
+    nfev += 4;
+    nstep += 1;
+    if constexpr (DENSE) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { cont[2][i] = k1[i]; cont[3][i] = y[i]; }
+    }
+    if constexpr (FEAT != 0) {
+      if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+        status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+      }
+    }
+    if (lst) { status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+    return false;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+#ifndef IVPB_BLOCK
+#define IVPB_BLOCK 128
+#endif
+
+template <class Prob, int METHOD, int FEAT>
+__device__ __forceinline__ void erk_body(const KArgs& a) {
+  ErkTraj<Prob, METHOD, FEAT> T;
+  if (a.static_sched) {
+    const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.N) return;
+    if (T.init(a, idx)) { double z[Prob::N] = {}; T.finish(a, false, 0.0, z); return; }
+    while (!T.step(a)) {}
+    return;
+  }
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  bool active = false, exhausted = false;
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL, !active);
+    if (need && !exhausted) {
+      const int leader = __ffs(need) - 1;
+      u64 base = 0;
+      if (lane == leader) base = atomicAdd(a.queue, (u64)__popc(need));
+      base = __shfl_sync(FULL, base, leader);
+      if (!active) {
+        const i64 idx = (i64)base + __popc(need & ((1u << lane) - 1u));
+        if (idx < a.N) {
+          active = true;
+          if (T.init(a, idx)) { T.finish(a, true, T.x, T.y); active = false; }
+        }
+      }
+      if ((i64)base + __popc(need) >= a.N) exhausted = true;
+    }
+    if (__ballot_sync(FULL, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    if (active) {
+      if (T.step(a)) active = false;
+    }
+  }
+}
+
+}  // namespace ivpb

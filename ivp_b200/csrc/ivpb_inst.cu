@@ -1,0 +1,34 @@
+// ivpb_inst.cu -- instantiates every kernel of ONE built-in problem.  Built once per problem and per
+// floating-point mode:
+//   nvcc -DIVPB_PROBLEM=PVdpMu -DIVPB_TAG=vdp_mu                      (FMA contraction on: the fast path)
+//   nvcc -DIVPB_PROBLEM=PVdpMu -DIVPB_TAG=vdp_mu -DIVPB_STRICT -fmad=false
+// The strict build renames the namespace so the two sets of template instantiations cannot be merged
+// by the linker.
+#ifdef IVPB_STRICT
+#define ivpb ivpb_strict
+#endif
+#include "ivpb_problems.cuh"
+#include "ivpb_kernels.cuh"
+
+#define IVPB_CAT2(a, b) a##b
+#define IVPB_CAT(a, b) IVPB_CAT2(a, b)
+#ifdef IVPB_STRICT
+#define IVPB_SYM(tag) IVPB_CAT(ivpb_lookup_strict_, tag)
+#else
+#define IVPB_SYM(tag) IVPB_CAT(ivpb_lookup_, tag)
+#endif
+
+#include "ivpb_runtime.h"
+
+extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, ivpb_pinfo* info) {
+  using P = ivpb::IVPB_PROBLEM;
+  if (info) {
+    info->n = P::N; info->p = P::P; info->nev = P::NEV; info->has_jac = P::HAS_JAC ? 1 : 0;
+    for (int e = 0; e < 8; ++e) {
+      info->ev_dir[e] = e < P::NEV ? P::default_dir(e) : 0;
+      info->ev_term[e] = e < P::NEV ? (long long)P::default_term(e) : -1;
+    }
+  }
+  if (method < 0) return nullptr;
+  return ivpb::erk_lookup<P>(method, feat);
+}

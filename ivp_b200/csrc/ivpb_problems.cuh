@@ -1,0 +1,146 @@
+// ivpb_problems.cuh -- built-in problems as __device__ code compiled together with the solvers.
+// A problem is the device form of the reference's `IVP` trait (src/ivp.rs:27-121): ode / events /
+// jac, with the struct fields of the reference programs read from the trajectory's parameter row `p`.
+#pragma once
+#include "ivpb_common.cuh"
+
+namespace ivpb {
+
+#define IVPB_DEV static __device__ __forceinline__
+#define IVPB_HD static __host__ __device__ __forceinline__
+
+// Defaults shared by all problems: no events, no analytic Jacobian.
+template <int N_, int P_, int NEV_>
+struct ProblemDefaults {
+  static constexpr int N = N_, P = P_, NEV = NEV_;
+  static constexpr bool HAS_JAC = false;
+  IVPB_DEV void events(double, const double*, const double*, double*) {}
+  IVPB_DEV void jac(double, const double*, const double*, double*) {}
+  // IVP::event_config default (src/ivp.rs:51-53 -> EventConfig::new: All, non-terminal)
+  IVPB_HD int default_dir(int) { return 0; }
+  IVPB_HD i64 default_term(int) { return -1; }
+};
+
+struct PDecay : ProblemDefaults<1, 1, 0> {      // reference examples/exponential_decay.rs:10-12
+  IVPB_DEV void ode(double, const double* y, const double* p, double* d) { d[0] = -p[0] * y[0]; }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double*, const double* p, double* J) { J[0] = -p[0]; }
+};
+
+struct PVdpEps : ProblemDefaults<2, 1, 0> {     // reference examples/van_der_pol.rs:10-13
+  IVPB_DEV void ode(double, const double* y, const double* p, double* d) {
+    d[0] = y[1];
+    d[1] = ((1.0 - y[0] * y[0]) * y[1] - y[0]) / p[0];
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* y, const double* p, double* J) {
+    J[0] = 0.0; J[1] = 1.0;
+    J[2] = (-2.0 * y[0] * y[1] - 1.0) / p[0];
+    J[3] = (1.0 - y[0] * y[0]) / p[0];
+  }
+};
+
+struct PVdpMu : ProblemDefaults<2, 1, 0> {      // reference benches/benchmark.py:22-27
+  IVPB_DEV void ode(double, const double* y, const double* p, double* d) {
+    d[0] = y[1];
+    d[1] = p[0] * (1.0 - y[0] * y[0]) * y[1] - y[0];
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* y, const double* p, double* J) {
+    J[0] = 0.0; J[1] = 1.0;
+    J[2] = -2.0 * p[0] * y[0] * y[1] - 1.0;
+    J[3] = p[0] * (1.0 - y[0] * y[0]);
+  }
+};
+
+struct PLorenz : ProblemDefaults<3, 3, 0> {     // reference benches/benchmark.py:30-37
+  IVPB_DEV void ode(double, const double* y, const double* p, double* d) {
+    d[0] = p[0] * (y[1] - y[0]);
+    d[1] = y[0] * (p[1] - y[2]) - y[1];
+    d[2] = y[0] * y[1] - p[2] * y[2];
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* y, const double* p, double* J) {
+    J[0] = -p[0];        J[1] = p[0];   J[2] = 0.0;
+    J[3] = p[1] - y[2];  J[4] = -1.0;   J[5] = -y[0];
+    J[6] = y[1];         J[7] = y[0];   J[8] = -p[2];
+  }
+};
+
+struct PCr3bp : ProblemDefaults<6, 1, 0> {      // reference examples/cr3bp.rs:24-35
+  IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
+    const double mu = p[0];
+    const double x = s[0], y = s[1], z = s[2];
+    const double r1 = sqrt((x + mu) * (x + mu) + y * y + z * z);
+    const double r2 = sqrt((x - 1.0 + mu) * (x - 1.0 + mu) + y * y + z * z);
+    const double r13 = (r1 * r1) * r1, r23 = (r2 * r2) * r2;   // powi(3)
+    d[0] = s[3]; d[1] = s[4]; d[2] = s[5];
+    d[3] = x + 2.0 * s[4] - (1.0 - mu) * (x + mu) / r13 - mu * (x - 1.0 + mu) / r23;
+    d[4] = y - 2.0 * s[3] - (1.0 - mu) * y / r13 - mu * y / r23;
+    d[5] = -(1.0 - mu) * z / r13 - mu * z / r23;
+  }
+};
+
+struct PBall : ProblemDefaults<2, 2, 1> {       // reference examples/bouncing_ball.rs:11-31
+  IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
+    const double vy = s[1];
+    d[0] = vy;
+    d[1] = -p[0] - p[1] * vy * fabs(vy);
+  }
+  IVPB_DEV void events(double, const double* s, const double*, double* g) { g[0] = s[0]; }
+  IVPB_HD int default_dir(int) { return -1; }       // config.negative()
+  IVPB_HD i64 default_term(int) { return 1; }       // config.terminal()
+};
+
+struct PRobertson : ProblemDefaults<3, 3, 0> {  // reference tests/test_stiff.py:104-110
+  IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
+    const double x = s[0], y = s[1], z = s[2];
+    d[0] = -p[0] * x + p[1] * y * z;
+    d[1] = p[0] * x - p[1] * y * z - p[2] * y * y;
+    d[2] = p[2] * y * y;
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* s, const double* p, double* J) {
+    const double y = s[1], z = s[2];
+    J[0] = -p[0]; J[1] = p[1] * z;                     J[2] = p[1] * y;
+    J[3] = p[0];  J[4] = -p[1] * z - 2.0 * p[2] * y;   J[5] = -p[1] * y;
+    J[6] = 0.0;   J[7] = 2.0 * p[2] * y;               J[8] = 0.0;
+  }
+};
+
+struct PSho : ProblemDefaults<2, 0, 1> {        // reference tests/common.rs:3-9, tests/ivp.rs:151-220
+  IVPB_DEV void ode(double, const double* y, const double*, double* d) { d[0] = y[1]; d[1] = -y[0]; }
+  IVPB_DEV void events(double, const double* y, const double*, double* g) { g[0] = y[0]; }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double*, const double*, double* J) { J[0] = 0.0; J[1] = 1.0; J[2] = -1.0; J[3] = 0.0; }
+};
+
+struct PZero3 : ProblemDefaults<3, 0, 0> {      // reference tests/ivp.rs:11-18
+  IVPB_DEV void ode(double, const double*, const double*, double* d) { d[0] = 0.0; d[1] = 0.0; d[2] = 0.0; }
+};
+
+struct PExp2 : ProblemDefaults<2, 0, 0> {       // reference tests/ivp.rs:291-297
+  IVPB_DEV void ode(double, const double* y, const double*, double* d) { d[0] = y[0]; d[1] = y[1]; }
+};
+
+struct PRational : ProblemDefaults<2, 0, 0> {   // reference tests/test_helpers.py:23-25, 34-40
+  IVPB_DEV void ode(double t, const double* y, const double*, double* d) {
+    d[0] = y[1] / t;
+    d[1] = y[1] * (y[0] + 2.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double t, const double* y, const double*, double* J) {
+    J[0] = 0.0; J[1] = 1.0 / t;
+    J[2] = -2.0 * y[1] * y[1] / (t * (y[0] - 1.0) * (y[0] - 1.0));
+    J[3] = (y[0] + 4.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+};
+
+struct PCannon : ProblemDefaults<2, 0, 1> {     // reference tests/test_ivp.py:153-160
+  IVPB_DEV void ode(double, const double* y, const double*, double* d) { d[0] = y[1]; d[1] = -9.80665; }
+  IVPB_DEV void events(double, const double* y, const double*, double* g) { g[0] = y[0]; }
+  IVPB_HD int default_dir(int) { return -1; }
+  IVPB_HD i64 default_term(int) { return 1; }
+};
+
+}  // namespace ivpb

@@ -1,0 +1,481 @@
+// ivpb_runtime.cu -- host runtime behind the C ABI of include/ivpb.h.
+//
+// Owns the device set (one stream + work-queue counter + grow-only staging buffers per device),
+// validates options the way the reference's solvers do before stepping (Error::Config), picks the
+// kernel specialisation, and launches the persistent kernels.  No numerics live here, and there is no
+// CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ivpb.h"
+#include "ivpb_common.cuh"
+#include "ivpb_runtime.h"
+
+using ivpb::KArgs;
+using ivpb::u64;
+
+// ------------------------------------------------------------------------------------------------
+// Built-in kernel tables (one lookup function per problem and floating-point mode; ivpb_inst.cu)
+typedef const void* (*lookup_fn)(int method, int feat, ivpb_pinfo* info);
+#define DECL(tag)                                                                  \
+  extern "C" const void* ivpb_lookup_##tag(int, int, ivpb_pinfo*);                 \
+  extern "C" const void* ivpb_lookup_strict_##tag(int, int, ivpb_pinfo*);
+DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
+DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon)
+#undef DECL
+#define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag}
+static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
+    ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
+#undef ROW
+
+// implicit-method kernels (ivpb_inst_implicit.cu); null until that path is built for a problem
+extern "C" const void* ivpb_lookup_implicit(int problem, int method, int feat, int strict) __attribute__((weak));
+
+namespace {
+
+std::string g_create_err;
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { OUT_STATUS, OUT_COUNTERS, OUT_TFINAL, OUT_YFINAL, OUT_HNEXT, OUT_NOUT, OUT_TOUT, OUT_YOUT, OUT_EVCOUNT,
+       OUT_EVT, OUT_EVY, OUT_FIELDS };
+
+struct Device {
+  int id = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  u64* queue = nullptr;
+  Buf y0, params, t_eval, out[OUT_FIELDS];
+};
+
+}  // namespace
+
+struct ivpb_ctx {
+  std::vector<Device> devs;
+  std::string err;
+  uint64_t launches = 0;
+  std::vector<ivpb_user_problem> user;   // NVRTC problems (ivpb_nvrtc.cpp)
+};
+
+namespace {
+
+}  // namespace
+void ivpb_set_error(ivpb_ctx* ctx, const std::string& msg) { if (ctx) ctx->err = msg; }
+namespace {
+int fail(ivpb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(ctx, IVPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+struct ProblemInfo {
+  int n = 0, p = 0, nev = 0, has_jac = 0;
+  bool user = false; int uidx = -1;
+  int ev_dir[8] = {0}; long long ev_term[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+};
+
+int problem_info(ivpb_ctx* ctx, int problem, ProblemInfo* pi) {
+  if (problem >= 0 && problem < IVPB_P_BUILTIN_COUNT) {
+    ivpb_pinfo info;
+    BUILTIN[problem][0](-1, 0, &info);
+    pi->n = info.n; pi->p = info.p; pi->nev = info.nev; pi->has_jac = info.has_jac;
+    for (int e = 0; e < 8; ++e) { pi->ev_dir[e] = info.ev_dir[e]; pi->ev_term[e] = info.ev_term[e]; }
+    return 0;
+  }
+  int u = problem - IVPB_USER_HANDLE_BASE;
+  if (u >= 0 && u < (int)ctx->user.size()) {
+    const ivpb_user_problem& up = ctx->user[u];
+    pi->n = up.n; pi->p = up.p; pi->nev = up.n_events; pi->has_jac = up.has_jac; pi->user = true; pi->uidx = u;
+    return 0;
+  }
+  return fail(ctx, IVPB_ERR_CONFIG, "unknown problem handle");
+}
+
+// Error::Config checks the reference performs before stepping, plus ABI sanity.
+int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_t N, double t0, double tf) {
+  if (!o) return fail(ctx, IVPB_ERR_CONFIG, "options is null");
+  if (N < 0) return fail(ctx, IVPB_ERR_CONFIG, "N must be >= 0");
+  if (o->method < IVPB_RK23 || o->method > IVPB_BDF) return fail(ctx, IVPB_ERR_CONFIG, "unknown method");
+  if (pi.n > ivpb::MAX_N) return fail(ctx, IVPB_ERR_CONFIG, "state size exceeds the thread-per-trajectory limit (32)");
+  if (!o->rtol || !o->atol) return fail(ctx, IVPB_ERR_CONFIG, "rtol/atol must be given");
+  // Tolerance::Vector length mismatch panics in the reference (src/methods/mod.rs:156-161)
+  if (!(o->n_rtol == 1 || o->n_rtol == pi.n)) return fail(ctx, IVPB_ERR_CONFIG, "rtol length must be 1 or n");
+  if (!(o->n_atol == 1 || o->n_atol == pi.n)) return fail(ctx, IVPB_ERR_CONFIG, "atol length must be 1 or n");
+  // ConfigError::MustBePositive { max_steps } (e.g. src/methods/dop853.rs:178-184)
+  if (o->has_max_steps && o->max_steps == 0) return fail(ctx, IVPB_ERR_CONFIG, "max_steps must be positive");
+  if (o->has_t_eval && o->n_t_eval > 0 && !o->t_eval) return fail(ctx, IVPB_ERR_CONFIG, "t_eval is null");
+  if (o->has_t_eval && o->n_t_eval < 0) return fail(ctx, IVPB_ERR_CONFIG, "n_t_eval < 0");
+  if (!o->has_t_eval && o->max_out < 0) return fail(ctx, IVPB_ERR_CONFIG, "max_out < 0");
+  if (pi.nev > ivpb::MAX_EVENTS_FN) return fail(ctx, IVPB_ERR_CONFIG, "too many event functions");
+  if (pi.nev > 0 && o->max_events < 1) return fail(ctx, IVPB_ERR_CONFIG, "max_events must be >= 1 for a problem with events");
+  if (o->n_event_cfg != 0 && o->n_event_cfg != pi.nev)
+    return fail(ctx, IVPB_ERR_CONFIG, "n_event_cfg must be 0 or the problem's n_events");
+  if (o->n_event_cfg != 0 && (!o->ev_direction || !o->ev_terminal_count))
+    return fail(ctx, IVPB_ERR_CONFIG, "event config arrays are null");
+  if (o->method == IVPB_RK4 && std::fabs(tf - t0) >= 1e-15) {
+    // ConfigError::InvalidStepSize (src/methods/rk4.rs:84-90); h as chosen by solve_ivp.rs:185
+    const double h = o->has_first_step ? o->first_step : (tf - t0) / 100.0;
+    const double posneg = std::signbit(tf - t0) ? -1.0 : 1.0;
+    const double sg = std::signbit(h) ? -1.0 : 1.0;
+    if (h == 0.0 || sg != posneg || std::isnan(h))
+      return fail(ctx, IVPB_ERR_CONFIG, "RK4: step size is zero or its sign does not match tf - t0");
+  }
+  if (o->jac_mode == 1 && !pi.has_jac && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
+    return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
+  return 0;
+}
+
+__global__ void zero_interval_kernel(KArgs a, int n, int nev) {
+  // reference src/solve/solve_ivp.rs:110-145: |xend - x0| < 1e-15 => Success, nothing evaluated.
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  if (a.status) a.status[i] = ivpb::ST_SUCCESS;
+  if (a.counters) for (int c = 0; c < 6; ++c) a.counters[i * 6 + c] = 0u;
+  if (a.t_final) a.t_final[i] = a.t0;
+  if (a.y_final) for (int c = 0; c < n; ++c) a.y_final[i * n + c] = a.y0[i * n + c];
+  if (a.h_next) a.h_next[i] = 0.0;
+  int m = 0;
+  if (a.n_t_eval >= 0) {
+    for (int j = 0; j < a.n_t_eval; ++j) {
+      if (fabs(a.t_eval[j] - a.t0) < 1e-12) {
+        if (m < a.out_cap) {
+          if (a.t_out) a.t_out[i * a.out_cap + m] = a.t_eval[j];
+          if (a.y_out) for (int c = 0; c < n; ++c) a.y_out[(i * a.out_cap + m) * n + c] = a.y0[i * n + c];
+        }
+        ++m;
+      }
+    }
+  } else if (a.out_cap > 0) {
+    if (a.t_out) a.t_out[i * a.out_cap] = a.t0;
+    if (a.y_out) for (int c = 0; c < n; ++c) a.y_out[i * a.out_cap * n + c] = a.y0[i * n + c];
+    m = 1;
+  }
+  if (a.n_out) a.n_out[i] = m;
+  if (a.ev_count) for (int e = 0; e < nev; ++e) a.ev_count[i * nev + e] = 0;
+}
+
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+    c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+}
+
+// Fill KArgs from options (host side of the by-value kernel parameter).
+void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N, double t0, double tf) {
+  std::memset(&a, 0, sizeof(a));
+  a.N = N; a.t0 = t0; a.tf = tf;
+  for (int i = 0; i < ivpb::MAX_N; ++i) {
+    a.rtol[i] = o->rtol[o->n_rtol == 1 ? 0 : (i < pi.n ? i : 0)];
+    a.atol[i] = o->atol[o->n_atol == 1 ? 0 : (i < pi.n ? i : 0)];
+  }
+  a.first_step = o->first_step; a.max_step = o->max_step; a.min_step = o->min_step;
+  a.has_first_step = o->has_first_step; a.has_max_step = o->has_max_step; a.has_min_step = o->has_min_step;
+  a.static_sched = (o->flags & IVPB_FLAG_NO_REFILL) ? 1 : 0;
+  a.max_steps = o->has_max_steps ? o->max_steps : std::numeric_limits<u64>::max();   // usize::MAX
+  a.n_t_eval = o->has_t_eval ? o->n_t_eval : -1;
+  a.out_cap = o->has_t_eval ? o->n_t_eval + 1 : o->max_out;
+  a.max_events = o->max_events;
+  a.jac_mode = o->jac_mode;
+  for (int e = 0; e < ivpb::MAX_EVENTS_FN; ++e) { a.ev_dir[e] = 0; a.ev_term[e] = -1; }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Enqueue one shard on one device.  All pointers in `d` are device pointers on dev.
+static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemInfo& pi, const ivpb_options* o,
+                        int64_t N, double t0, double tf, const double* d_y0, const double* d_params,
+                        const ivpb_outputs* d, cudaStream_t stream) {
+  if (N == 0) return 0;
+  KArgs a;
+  fill_args(a, pi, o, N, t0, tf);
+  a.y0 = d_y0; a.params = d_params; a.queue = dev.queue;
+  a.status = d->status; a.counters = d->counters; a.t_final = d->t_final; a.y_final = d->y_final;
+  a.h_next = d->h_next; a.n_out = d->n_out; a.t_out = d->t_out; a.y_out = d->y_out;
+  a.ev_count = d->ev_count; a.ev_t = d->ev_t; a.ev_y = d->ev_y;
+  if (a.out_cap == 0 || (!a.t_out && !a.y_out && !a.n_out)) {
+    if (!o->has_t_eval) a.out_cap = 0;    // nothing to store in step mode
+  }
+  if (o->has_t_eval && o->n_t_eval > 0) {
+    CK(dev.t_eval.ensure(sizeof(double) * o->n_t_eval));
+    CK(cudaMemcpyAsync(dev.t_eval.p, o->t_eval, sizeof(double) * o->n_t_eval, cudaMemcpyHostToDevice, stream));
+    a.t_eval = (const double*)dev.t_eval.p;
+  }
+  const int strict = (o->flags & IVPB_FLAG_STRICT_FP) ? 1 : 0;
+  const int block = 128;
+
+  if (std::fabs(tf - t0) < 1e-15) {
+    const int grid = (int)((N + block - 1) / block);
+    zero_interval_kernel<<<grid, block, 0, stream>>>(a, pi.n, pi.nev);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+  }
+
+  // event configuration: options override, else the problem's IVP::event_config defaults
+  if (pi.nev > 0) {
+    if (o->n_event_cfg > 0) {
+      for (int e = 0; e < pi.nev; ++e) {
+        a.ev_dir[e] = o->ev_direction[e] > 0 ? 1 : (o->ev_direction[e] < 0 ? -1 : 0);
+        a.ev_term[e] = o->ev_terminal_count[e];
+      }
+    } else {
+      for (int e = 0; e < pi.nev; ++e) { a.ev_dir[e] = pi.ev_dir[e]; a.ev_term[e] = pi.ev_term[e]; }
+    }
+  }
+  const bool want_out = o->has_t_eval || a.out_cap > 0;
+  int feat = 0;
+  if (pi.nev > 0) feat = 3;            // K_OUT | K_EVENTS: events always run (they can terminate)
+  else if (want_out) feat = 1;         // K_OUT
+
+  CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
+
+  if (pi.user) {
+    int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, &a, sizeof(a), stream);
+    if (rc) return rc;
+    ctx->launches += 1;
+    return 0;
+  }
+
+  const void* kern = nullptr;
+  if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
+    if (ivpb_lookup_implicit) kern = ivpb_lookup_implicit(problem, o->method, feat, strict);
+    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods are not built for this problem");
+  } else {
+    kern = BUILTIN[problem][strict](o->method, feat, nullptr);
+    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
+  }
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)dev.sms * occ;
+  const int64_t need = (N + block - 1) / block;
+  if (a.static_sched || need < grid) grid = need;
+  void* kargs[] = {&a};
+  CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return IVPB_ERR_CONFIG;
+  *out = nullptr;
+  ivpb_ctx* ctx = nullptr;   // for CK(): errors before the context exists go to g_create_err
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, IVPB_ERR_CUDA, std::string("no CUDA device available (libivpb has no CPU fallback): ") +
+                                            cudaGetErrorString(e));
+  std::vector<int> ids;
+  if (device_ids && n_devices > 0) ids.assign(device_ids, device_ids + n_devices);
+  else { int cur = 0; CK(cudaGetDevice(&cur)); ids.push_back(cur); }
+  ivpb_ctx* c = new ivpb_ctx();
+  for (int id : ids) {
+    if (id < 0 || id >= count) { delete c; return fail(nullptr, IVPB_ERR_CONFIG, "device id out of range"); }
+    Device d;
+    d.id = id;
+    cudaError_t err = cudaSetDevice(id);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, id);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&d.queue, sizeof(u64));
+    if (err != cudaSuccess) { delete c; return fail(nullptr, IVPB_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(err)); }
+    c->devs.push_back(d);
+  }
+  // peer access for the multi-device device-resident path (results gathered to device 0 over NVLink)
+  for (size_t i = 1; i < c->devs.size(); ++i) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->devs[0].id, c->devs[i].id);
+    if (can) {
+      cudaSetDevice(c->devs[0].id); cudaDeviceEnablePeerAccess(c->devs[i].id, 0);
+      cudaSetDevice(c->devs[i].id); cudaDeviceEnablePeerAccess(c->devs[0].id, 0);
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(c->devs[0].id);
+  *out = c;
+  return 0;
+}
+
+void ivpb_destroy(ivpb_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& d : ctx->devs) {
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    d.y0.release(); d.params.release(); d.t_eval.release();
+    for (auto& b : d.out) b.release();
+    cudaFree(d.queue);
+    cudaStreamDestroy(d.stream);
+  }
+  for (auto& u : ctx->user) ivpb_nvrtc_release(u);
+  delete ctx;
+}
+
+const char* ivpb_last_error(const ivpb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int ivpb_device_count(const ivpb_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+uint64_t ivpb_launch_count(const ivpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* ivpb_version(void) { return "ivp-b200 0.1.0 (sm_100a)"; }
+
+int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_events) {
+  if (builtin_id < 0 || builtin_id >= IVPB_P_BUILTIN_COUNT) return fail(ctx, IVPB_ERR_CONFIG, "unknown built-in problem id");
+  ivpb_pinfo info;
+  BUILTIN[builtin_id][0](-1, 0, &info);
+  if (n) *n = info.n;
+  if (p) *p = info.p;
+  if (n_events) *n_events = info.nev;
+  return 0;
+}
+
+int ivpb_nvrtc_problem(ivpb_ctx* ctx, const char* cuda_src, int n, int p, int n_events, int has_jac, int* handle) {
+  if (!ctx || !cuda_src || !handle) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
+  if (n < 1 || n > ivpb::MAX_N) return fail(ctx, IVPB_ERR_CONFIG, "n must be in 1..32");
+  if (p < 0 || n_events < 0 || n_events > ivpb::MAX_EVENTS_FN) return fail(ctx, IVPB_ERR_CONFIG, "bad p / n_events");
+  ivpb_user_problem up;
+  up.n = n; up.p = p; up.n_events = n_events; up.has_jac = has_jac; up.src = cuda_src;
+  ctx->user.push_back(up);
+  *handle = IVPB_USER_HANDLE_BASE + (int)ctx->user.size() - 1;
+  return 0;
+}
+
+void* ivpb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void ivpb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0, double tf,
+                            const double* d_y0, const double* d_params, const ivpb_outputs* d_out, void* stream) {
+  if (!ctx) return IVPB_ERR_CONFIG;
+  ProblemInfo pi;
+  if (int rc = problem_info(ctx, problem, &pi)) return rc;
+  if (int rc = validate(ctx, pi, opt, N, t0, tf)) return rc;
+  if (!d_y0 || !d_out) return fail(ctx, IVPB_ERR_CONFIG, "null device buffer");
+  if (pi.p > 0 && !d_params) return fail(ctx, IVPB_ERR_CONFIG, "params is null but the problem has parameters");
+  Device& dev = ctx->devs[0];
+  CK(cudaSetDevice(dev.id));
+  return launch_shard(ctx, dev, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, (cudaStream_t)stream);
+}
+
+int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0, double tf,
+                     const double* y0, const double* params, const ivpb_outputs* out) {
+  if (!ctx) return IVPB_ERR_CONFIG;
+  ProblemInfo pi;
+  if (int rc = problem_info(ctx, problem, &pi)) return rc;
+  if (int rc = validate(ctx, pi, opt, N, t0, tf)) return rc;
+  if (!y0 || !out) return fail(ctx, IVPB_ERR_CONFIG, "null host buffer");
+  if (pi.p > 0 && !params) return fail(ctx, IVPB_ERR_CONFIG, "params is null but the problem has parameters");
+  const int G = (int)ctx->devs.size();
+  const int64_t cap = opt->has_t_eval ? (int64_t)opt->n_t_eval + 1 : (int64_t)opt->max_out;
+  const int n = pi.n, nev = pi.nev, me = opt->max_events;
+  // bytes per trajectory of each output field, and the host base pointers
+  const size_t per[OUT_FIELDS] = {4, 24, 8, 8u * n, 8, 4, 8u * (size_t)cap, 8u * (size_t)cap * n,
+                                  4u * nev, 8u * (size_t)nev * me, 8u * (size_t)nev * me * n};
+  void* host[OUT_FIELDS] = {out->status, out->counters, out->t_final, out->y_final, out->h_next, out->n_out,
+                            out->t_out, out->y_out, out->ev_count, out->ev_t, out->ev_y};
+  // static contiguous split [g*N/G, (g+1)*N/G) -- trajectories are independent, no exchange step
+  for (int g = 0; g < G; ++g) {
+    Device& dev = ctx->devs[g];
+    const int64_t lo = N * g / G, hi = N * (g + 1) / G, Ng = hi - lo;
+    if (Ng == 0) continue;
+    CK(cudaSetDevice(dev.id));
+    CK(dev.y0.ensure(sizeof(double) * n * Ng));
+    CK(cudaMemcpyAsync(dev.y0.p, y0 + lo * n, sizeof(double) * n * Ng, cudaMemcpyHostToDevice, dev.stream));
+    if (pi.p > 0) {
+      CK(dev.params.ensure(sizeof(double) * pi.p * Ng));
+      CK(cudaMemcpyAsync(dev.params.p, params + lo * pi.p, sizeof(double) * pi.p * Ng, cudaMemcpyHostToDevice, dev.stream));
+    }
+    void* dptr[OUT_FIELDS];
+    for (int f = 0; f < OUT_FIELDS; ++f) {
+      dptr[f] = nullptr;
+      if (!host[f] || per[f] == 0) continue;
+      CK(dev.out[f].ensure(per[f] * Ng));
+      dptr[f] = dev.out[f].p;
+    }
+    ivpb_outputs d;
+    d.status = (int32_t*)dptr[OUT_STATUS]; d.counters = (uint32_t*)dptr[OUT_COUNTERS];
+    d.t_final = (double*)dptr[OUT_TFINAL]; d.y_final = (double*)dptr[OUT_YFINAL]; d.h_next = (double*)dptr[OUT_HNEXT];
+    d.n_out = (int32_t*)dptr[OUT_NOUT]; d.t_out = (double*)dptr[OUT_TOUT]; d.y_out = (double*)dptr[OUT_YOUT];
+    d.ev_count = (int32_t*)dptr[OUT_EVCOUNT]; d.ev_t = (double*)dptr[OUT_EVT]; d.ev_y = (double*)dptr[OUT_EVY];
+    // sample / event slots the kernel does not touch must read as zero on the host
+    if (d.t_out) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
+    if (d.y_out) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
+    if (d.ev_t) CK(cudaMemsetAsync(d.ev_t, 0, per[OUT_EVT] * Ng, dev.stream));
+    if (d.ev_y) CK(cudaMemsetAsync(d.ev_y, 0, per[OUT_EVY] * Ng, dev.stream));
+    if (d.ev_count) CK(cudaMemsetAsync(d.ev_count, 0, per[OUT_EVCOUNT] * Ng, dev.stream));
+    if (d.n_out) CK(cudaMemsetAsync(d.n_out, 0, per[OUT_NOUT] * Ng, dev.stream));
+    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, (const double*)dev.y0.p,
+                              pi.p > 0 ? (const double*)dev.params.p : nullptr, &d, dev.stream))
+      return rc;
+    for (int f = 0; f < OUT_FIELDS; ++f) {
+      if (!dptr[f]) continue;
+      CK(cudaMemcpyAsync((char*)host[f] + per[f] * lo, dptr[f], per[f] * Ng, cudaMemcpyDeviceToHost, dev.stream));
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    CK(cudaSetDevice(ctx->devs[g].id));
+    CK(cudaStreamSynchronize(ctx->devs[g].stream));
+  }
+  CK(cudaSetDevice(ctx->devs[0].id));
+  return 0;
+}
+
+int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return IVPB_ERR_CONFIG;
+  Device& dev = ctx->devs[0];
+  CK(cudaSetDevice(dev.id));
+  const int block = 256, grid = dev.sms * 8, iters = 1 << 16;
+  double* buf = nullptr;
+  CK(cudaMalloc((void**)&buf, sizeof(double) * (size_t)block * grid));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, dev.stream));
+    dfma_peak_kernel<<<grid, block, 0, dev.stream>>>(buf, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1, dev.stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * (double)block * (double)grid;
+    if (rep > 0) best = std::fmax(best, fl / (ms * 1e-3) / 1e12);
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

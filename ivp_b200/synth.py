@@ -1,0 +1,66 @@
+"""Synthetic ensembles for the BASELINE.json configurations.
+
+Counter-based generator so host, C++ and CUDA can produce identical bits:
+    u(i, j) = (splitmix64(seed + i * n_fields + j) >> 11) * 2**-53,  seed = 0x5EED1234
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SEED = 0x5EED1234
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def uniform(N: int, n_fields: int, seed: int = SEED, offset: int = 0) -> np.ndarray:
+    """[N, n_fields] doubles in [0, 1); `offset` = global index of row 0 (for sharding across ranks)."""
+    i = (np.arange(N, dtype=np.uint64) + np.uint64(offset))[:, None]
+    j = np.arange(n_fields, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        ctr = np.uint64(seed) + i * np.uint64(n_fields) + j
+    return (splitmix64(ctr) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def ensemble(name: str, N: int, offset: int = 0):
+    """Return (problem_name, y0[N,n], params[N,p] or None, t0, tf) for a named workload."""
+    if name == "vdp":            # north star: VdP mu=1, y0 ~ U(-3,3)^2
+        u = uniform(N, 2, offset=offset)
+        return "vdp_mu", -3.0 + 6.0 * u, np.ones((N, 1)), 0.0, 100.0
+    if name == "decay":          # cfg 2: y0 ~ U(1,10), k ~ U(0.1,1)
+        u = uniform(N, 2, offset=offset)
+        return "decay", 1.0 + 9.0 * u[:, :1], 0.1 + 0.9 * u[:, 1:2], 0.0, 10.0
+    if name == "lorenz":         # cfg 2: y0 = 1 + U(-.5,.5)^3, sigma=10, rho ~ U(20,35), beta=8/3
+        u = uniform(N, 4, offset=offset)
+        par = np.stack([np.full(N, 10.0), 20.0 + 15.0 * u[:, 3], np.full(N, 8.0 / 3.0)], axis=1)
+        return "lorenz", 1.0 + (u[:, :3] - 0.5), par, 0.0, 10.0
+    if name == "cr3bp":          # cfg 3: perturbed Arenstorf orbit
+        u = uniform(N, 4, offset=offset)
+        y0 = np.zeros((N, 6))
+        y0[:, 0] = 0.994 * (1.0 + 1e-3 * (2.0 * u[:, 0] - 1.0))
+        y0[:, 4] = -2.00158510637908252240537862224 * (1.0 + 1e-3 * (2.0 * u[:, 1] - 1.0))
+        y0[:, 2] = 1e-3 * (2.0 * u[:, 2] - 1.0)
+        y0[:, 5] = 1e-3 * (2.0 * u[:, 3] - 1.0)
+        return "cr3bp", y0, np.full((N, 1), 0.012277471), 0.0, 17.0652165601579625588917206249
+    if name == "ball":           # cfg 4: h0 ~ U(1,20), v0 ~ U(-5,10), g=9.81, drag ~ U(0,0.05)
+        u = uniform(N, 3, offset=offset)
+        y0 = np.stack([1.0 + 19.0 * u[:, 0], -5.0 + 15.0 * u[:, 1]], axis=1)
+        par = np.stack([np.full(N, 9.81), 0.05 * u[:, 2]], axis=1)
+        return "bouncing_ball", y0, par, 0.0, 10.0
+    if name == "robertson":      # cfg 5
+        u = uniform(N, 1, offset=offset)
+        y0 = np.zeros((N, 3))
+        y0[:, 0] = 1e4 * (1.0 + 0.1 * (2.0 * u[:, 0] - 1.0))
+        par = np.tile(np.array([[0.04, 1e4, 3e7]]), (N, 1))
+        return "robertson", y0, par, 0.0, 1e8
+    if name == "vdp_stiff":      # cfg 5: mu = 1000
+        u = uniform(N, 2, offset=offset)
+        y0 = np.stack([2.0 + (u[:, 0] - 0.5), u[:, 1] - 0.5], axis=1)
+        return "vdp_mu", y0, np.full((N, 1), 1000.0), 0.0, 3000.0
+    raise KeyError(name)

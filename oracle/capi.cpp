@@ -53,7 +53,7 @@ void scatter(const Solution& S, const P&, const ivpb_options* o, const ivpb_outp
   }
   if (out->h_next) out->h_next[i] = S.h_next;
   const int64_t cap = o->has_t_eval ? (int64_t)o->n_t_eval + 1 : (int64_t)o->max_out;
-  if (out->n_out) out->n_out[i] = (int32_t)S.t.size();
+  if (out->n_out) out->n_out[i] = cap > 0 ? (int32_t)S.t.size() : 0;   // only meaningful when samples are stored
   const int64_t m = std::min<int64_t>((int64_t)S.t.size(), cap);
   if (out->t_out && m > 0) std::memcpy(out->t_out + cap * i, S.t.data(), sizeof(double) * m);
   if (out->y_out && m > 0) std::memcpy(out->y_out + cap * n * i, S.y.data(), sizeof(double) * m * n);

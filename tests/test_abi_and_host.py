@@ -1,0 +1,120 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ivpb.h declares (no compute
+calls without a GPU), the ctypes structs match the header, and the host mirror behaves like the reference's
+types (names, defaults, conversions)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ivp_b200 as ib
+from ivp_b200 import _abi, api, synth
+from ivp_b200.types import Method, Options, Status
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ivpb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ivpb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    syms = header_symbols()
+    assert set(syms) == set(api.ABI_SYMBOLS)
+    for s in syms:
+        assert hasattr(lib, s), f"libivpb.so does not export {s}"
+    assert b"sm_100a" in lib.ivpb_version()
+
+
+def test_struct_layout_matches_header():
+    # field order of the ctypes mirrors == field order in include/ivpb.h
+    src = open(os.path.join(ROOT, "include", "ivpb.h")).read()
+    body = src[src.index("typedef struct {", src.index("Per-trajectory outputs")):]
+    body = body[: body.index("} ivpb_outputs;")]
+    names = re.findall(r"\*\s*(\w+);", body)
+    assert names == _abi.OUTPUT_FIELDS
+    assert ctypes.sizeof(_abi.IvpbOutputs) == 8 * len(names)
+    obody = src[src.index("typedef struct {", src.index("Mirrors `Options`")):]
+    obody = re.sub(r"/\*.*?\*/", "", obody[: obody.index("} ivpb_options;")], flags=re.S)
+    onames = []
+    for decl in obody.split(";"):
+        decl = decl.replace("typedef struct {", "").strip()
+        if not decl:
+            continue
+        parts = decl.split(",")
+        first = parts[0].split()[-1].lstrip("*")
+        onames.append(first)
+        onames += [p.strip().lstrip("*") for p in parts[1:]]
+    assert onames == [f for f, _ in _abi.IvpbOptions._fields_]
+
+
+def test_builtin_problem_dims_without_gpu(oracle):
+    for name, pid in api.PROBLEMS.items():
+        p = api.Problem.builtin(name)
+        assert (p.n, p.p, p.n_events) == oracle.dims(pid), name
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        api.Context()
+    with pytest.raises(RuntimeError):
+        ib.solve_ivp_batch("sho", 0.0, 1.0, np.array([[1.0, 0.0]]), None, Options())
+
+
+def test_method_and_status_mirror_reference_enums():
+    # reference src/solve/options.rs:14-27,61-73 and src/status.rs:4-19
+    assert [m.name for m in Method] == ["RK23", "DOPRI5", "DOP853", "RK4", "RADAU", "BDF"]
+    assert Method.from_str("rk45") == Method.DOPRI5 and Method.from_str("Radau5") == Method.RADAU
+    assert Method.from_str("BDF15") == Method.BDF and Method.from_str("nonsense") == Method.DOPRI5
+    assert [s.name for s in Status] == ["Success", "UserInterrupt", "NeedLargerNMax", "StepSizeTooSmall",
+                                       "ProbablyStiff", "SingularMatrix", "PoorConvergence"]
+    assert Status.UserInterrupt.is_success() and not Status.ProbablyStiff.is_success()
+    assert [Method(m).coeffs_per_state() for m in range(6)] == [4, 5, 8, 4, 4, 7]
+
+
+def test_options_defaults_and_builder():
+    # reference src/solve/options.rs:75-123
+    o = Options()
+    assert o.method == Method.DOPRI5 and o.rtol == 1e-3 and o.atol == 1e-6 and o.dense_output is False
+    assert o.max_steps is None and o.t_eval is None and o.first_step is None and o.max_step is None
+    b = Options.builder().method("DOP853").rtol(1e-9).atol([1e-9, 1e-8]).t_eval([0.0, 1.0]).build()
+    assert b.method == Method.DOP853 and b.t_eval == [0.0, 1.0]
+    mo = _abi.MarshalledOptions(b, 2, 0)
+    assert mo.struct.n_rtol == 1 and mo.struct.n_atol == 2 and mo.struct.has_t_eval == 1 and mo.cap == 3
+    with pytest.raises(ValueError):
+        _abi.MarshalledOptions(Options(rtol=[1, 2, 3]), 2, 0)
+
+
+def test_synth_is_counter_based_and_shardable():
+    a = synth.uniform(1000, 3)
+    b = np.concatenate([synth.uniform(400, 3), synth.uniform(600, 3, offset=400)])
+    assert np.array_equal(a, b) and a.min() >= 0.0 and a.max() < 1.0
+    assert abs(a.mean() - 0.5) < 0.02
+    # splitmix64 known answer (seed 0 -> first output of the reference splitmix64 stream)
+    assert int(synth.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+    for wl in ("vdp", "decay", "lorenz", "cr3bp", "ball", "robertson", "vdp_stiff"):
+        prob, y0, par, t0, tf = synth.ensemble(wl, 7)
+        p = api.Problem.builtin(prob)
+        assert y0.shape == (7, p.n) and (par is None or par.shape == (7, p.p))
+
+
+def test_batch_solution_views():
+    from ivp_b200.types import BatchSolution
+    N, n = 3, 2
+    b = BatchSolution(n=n, n_events=1, status=np.array([0, 1, 0], dtype=np.int32),
+                      counters=np.arange(18, dtype=np.uint32).reshape(3, 6), t_final=np.array([1.0, 0.5, 1.0]),
+                      y_final=np.ones((N, n)), n_out=np.array([2, 3, 1], dtype=np.int32),
+                      t_out=np.arange(6.0).reshape(3, 2), y_out=np.ones((3, 2, 2)),
+                      ev_count=np.array([[0], [1], [0]], dtype=np.int32), ev_t=np.full((3, 1, 2), 0.5),
+                      ev_y=np.zeros((3, 1, 2, 2)))
+    s = b.solution(1)
+    assert s.status == Status.UserInterrupt and s.truncated and len(s.t) == 2 and len(s.t_events[0]) == 1
+    assert (s.nfev, s.njev, s.nlu, s.nstep, s.naccpt, s.nrejct) == (6, 7, 8, 9, 10, 11)
+    assert not b.solution(0).truncated and len(b.solutions()) == 3

@@ -1,0 +1,233 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libivpb.so), against the
+CPU oracle on the same seeded inputs.  Bars (BASELINE.json north_star): values within
+max(10*rtol*|y|, 10*atol); accepted/rejected step counts equal for >= 99 % of non-chaotic trajectories;
+status / event counts / sample counts bit-exact."""
+import math
+
+import numpy as np
+import pytest
+
+import ivp_b200 as ib
+from ivp_b200 import Direction, EventConfig, Method, Options, Status, synth
+from ivp_b200.api import IVPB_FLAG_NO_REFILL, IVPB_FLAG_STRICT_FP, PROBLEMS
+
+pytestmark = pytest.mark.gpu
+
+
+def close(y, yref, rtol, atol):
+    """north_star tolerance: |y - yref| <= max(10 rtol |yref|, 10 atol) elementwise."""
+    return np.abs(y - yref) <= np.maximum(10.0 * rtol * np.abs(yref), 10.0 * atol)
+
+
+def run_both(oracle, wl, N, opts, threads=8):
+    prob, y0, par, t0, tf = synth.ensemble(wl, N)
+    g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts)
+    o = oracle.solve_batch(PROBLEMS[prob], t0, tf, y0, par, opts, nthreads=threads)
+    return g, o
+
+
+def check_counts(g, o, min_frac=0.99):
+    same = (g.naccpt == o.naccpt) & (g.nrejct == o.nrejct) & (g.nstep == o.nstep)
+    assert same.mean() >= min_frac, f"step-count parity {same.mean():.4f} < {min_frac}"
+    assert np.array_equal(g.nfev[same], o.nfev[same])
+    return same
+
+
+@pytest.mark.parametrize("method,rtol,atol", [(Method.DOP853, 1e-8, 1e-8), (Method.DOPRI5, 1e-6, 1e-9),
+                                              (Method.RK23, 1e-5, 1e-8)])
+@pytest.mark.parametrize("flags", [0, IVPB_FLAG_STRICT_FP])
+def test_vdp_final_state_and_counts(oracle, method, rtol, atol, flags):
+    opts = Options(method=method, rtol=rtol, atol=atol, flags=flags)
+    g, o = run_both(oracle, "vdp", 4096, opts)
+    assert np.array_equal(g.status, o.status) and np.all(g.status == Status.Success)
+    assert np.all(g.t_final == o.t_final)
+    assert close(g.y_final, o.y_final, rtol, atol).all()
+    check_counts(g, o)
+
+
+def test_vdp_rk4_fixed_step(oracle):
+    opts = Options(method=Method.RK4, first_step=0.01)
+    g, o = run_both(oracle, "vdp", 2048, opts)
+    assert np.array_equal(g.status, o.status)
+    assert np.array_equal(g.counters, o.counters)
+    np.testing.assert_allclose(g.y_final, o.y_final, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(g.t_final, o.t_final, rtol=0, atol=1e-9)
+
+
+def test_no_refill_schedule_matches_queue():
+    prob, y0, par, t0, tf = synth.ensemble("vdp", 3000)
+    a = ib.solve_ivp_batch(prob, t0, tf, y0, par, Options(method=Method.DOP853, rtol=1e-8, atol=1e-8))
+    b = ib.solve_ivp_batch(prob, t0, tf, y0, par,
+                           Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, flags=IVPB_FLAG_NO_REFILL))
+    assert np.array_equal(a.counters, b.counters) and np.array_equal(a.y_final, b.y_final)
+
+
+@pytest.mark.parametrize("method", [Method.DOPRI5, Method.RK4])
+def test_decay_and_lorenz(oracle, method):
+    # BASELINE configs[1]: decay + Lorenz ensembles, DOPRI5 and RK4
+    for wl in ("decay", "lorenz"):
+        opts = Options(method=method, rtol=1e-6, atol=1e-9)
+        g, o = run_both(oracle, wl, 2048, opts)
+        assert np.array_equal(g.status, o.status)
+        if wl == "decay":
+            assert close(g.y_final, o.y_final, 1e-6, 1e-9).all()
+            check_counts(g, o)
+        else:
+            # chaotic: exempt from step-count parity, values over the short span only
+            assert close(g.y_final, o.y_final, 1e-3, 1e-3).mean() > 0.99
+
+
+def test_cr3bp_t_eval(oracle):
+    # BASELINE configs[2]: DOP853 rtol=1e-10 with dense t_eval output
+    prob, y0, par, t0, tf = synth.ensemble("cr3bp", 512)
+    te = np.linspace(t0, tf, 101)
+    opts = Options(method=Method.DOP853, rtol=1e-10, atol=1e-12, t_eval=te)
+    g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts)
+    o = oracle.solve_batch(PROBLEMS[prob], t0, tf, y0, par, opts, nthreads=8)
+    assert np.array_equal(g.status, o.status)
+    assert np.array_equal(g.n_out, o.n_out) and np.all(g.n_out == 101)
+    assert np.array_equal(g.t_out, o.t_out)
+    same = check_counts(g, o, 0.97)
+    # the orbit is sensitive (close lunar fly-by): compare samples where step sequences agree
+    assert close(g.y_out[same], o.y_out[same], 1e-6, 1e-8).mean() > 0.999
+
+
+@pytest.mark.parametrize("method", [Method.RK23, Method.DOPRI5, Method.DOP853, Method.RK4])
+@pytest.mark.parametrize("backward", [False, True])
+def test_t_eval_sampling_fwd_bwd(oracle, method, backward):
+    # reference tests/accuracy.rs:49-76 + tests/test_ivp.py:586-646 (t_eval forward / backward / subset)
+    N = 257
+    y0 = np.tile([1.0, 0.0], (N, 1)) * (1.0 + 0.01 * np.arange(N))[:, None]
+    t0, tf = (0.0, 3.0) if not backward else (3.0, 0.0)
+    te = np.linspace(0.25, 2.75, 23)
+    if backward:
+        te = te[::-1].copy()
+    kw = dict(first_step=-0.01 if backward else 0.01) if method == Method.RK4 else dict(rtol=1e-9, atol=1e-9)
+    opts = Options(method=method, t_eval=te, **kw)
+    g = ib.solve_ivp_batch("sho", t0, tf, y0, None, opts)
+    o = oracle.solve_batch(PROBLEMS["sho"], t0, tf, y0, None, opts)
+    assert np.array_equal(g.status, o.status)
+    assert np.array_equal(g.n_out, o.n_out)
+    assert np.array_equal(g.t_out, o.t_out)
+    np.testing.assert_allclose(g.y_out, o.y_out, rtol=1e-8, atol=1e-8)
+    assert np.array_equal(g.ev_count, o.ev_count)
+
+
+@pytest.mark.parametrize("method", [Method.RK23, Method.DOPRI5, Method.DOP853])
+def test_step_mode_capture_and_first_step_rule(oracle, method):
+    # reference tests/ivp.rs:48-104: all accepted steps are reported; first output at x0 + first_step
+    N = 64
+    y0 = np.tile([1.0, 0.0], (N, 1)) * (1.0 + 0.02 * np.arange(N))[:, None]
+    for kw in (dict(max_step=0.05, rtol=1e-6, atol=1e-9), dict(first_step=0.1, rtol=1e-3, atol=1e-6)):
+        opts = Options(method=method, max_out=256, **kw)
+        g = ib.solve_ivp_batch("sho", 0.0, 3.0, y0, None, opts)
+        o = oracle.solve_batch(PROBLEMS["sho"], 0.0, 3.0, y0, None, opts)
+        assert np.array_equal(g.n_out, o.n_out)
+        np.testing.assert_allclose(g.t_out, o.t_out, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(g.y_out, o.y_out, rtol=1e-7, atol=1e-7)
+        assert np.array_equal(g.counters, o.counters)
+
+
+def test_bouncing_ball_terminal_events(oracle):
+    # BASELINE configs[3]: terminal events + event root finding, DOPRI5 rtol=1e-8 atol=1e-10
+    opts = Options(method=Method.DOPRI5, rtol=1e-8, atol=1e-10, max_events=2)
+    g, o = run_both(oracle, "ball", 4096, opts)
+    assert np.array_equal(g.status, o.status)
+    assert np.all(g.status == Status.UserInterrupt)
+    assert np.array_equal(g.ev_count, o.ev_count)        # integer event indices: bit-exact
+    check_counts(g, o)
+    np.testing.assert_allclose(g.ev_t, o.ev_t, rtol=1e-10, atol=1e-10)
+    assert close(g.ev_y, o.ev_y, 1e-8, 1e-10).all()
+    np.testing.assert_allclose(g.t_final, o.t_final, rtol=1e-10, atol=1e-10)
+    assert close(g.y_final, o.y_final, 1e-8, 1e-10).all()
+
+
+@pytest.mark.parametrize("cfg", [EventConfig(Direction.All, 2), EventConfig(Direction.Positive, 1),
+                                 EventConfig(Direction.Negative, 1), EventConfig(Direction.All, None)])
+def test_sho_event_directions(oracle, cfg):
+    # reference tests/ivp.rs:222-275
+    N = 96
+    y0 = np.tile([1.0, 0.0], (N, 1)) * (1.0 + 0.01 * np.arange(N))[:, None]
+    opts = Options(method=Method.DOPRI5, rtol=1e-9, atol=1e-9, event_config=[cfg], max_events=4, max_out=256)
+    g = ib.solve_ivp_batch("sho", 0.0, 6.0, y0, None, opts)
+    o = oracle.solve_batch(PROBLEMS["sho"], 0.0, 6.0, y0, None, opts)
+    assert np.array_equal(g.status, o.status)
+    assert np.array_equal(g.ev_count, o.ev_count)
+    assert np.array_equal(g.n_out, o.n_out)
+    np.testing.assert_allclose(g.ev_t, o.ev_t, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(g.ev_y, o.ev_y, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(g.t_out, o.t_out, rtol=0, atol=1e-10)
+    if cfg.terminal_count == 2:
+        assert abs(g.ev_t[0, 0, 0] - math.pi / 2) < 5e-3 and abs(g.ev_t[0, 0, 1] - 3 * math.pi / 2) < 5e-3
+
+
+def test_edge_cases(oracle):
+    # zero interval (reference tests/ivp.rs:277-289, solve_ivp.rs:110-145)
+    y0 = np.array([[2.0, 3.0], [1.0, -1.0]])
+    for te in (None, [1.23, 1.23, 2.0]):
+        opts = Options(method=Method.DOP853, rtol=1e-9, atol=1e-9, t_eval=te, max_out=4)
+        g = ib.solve_ivp_batch("sho", 1.23, 1.23, y0, None, opts)
+        o = oracle.solve_batch(PROBLEMS["sho"], 1.23, 1.23, y0, None, opts)
+        assert np.array_equal(g.status, o.status) and np.array_equal(g.counters, o.counters)
+        assert np.array_equal(g.n_out, o.n_out) and np.array_equal(g.y_final, o.y_final)
+        assert np.array_equal(g.t_out, o.t_out) and np.array_equal(g.y_out, o.y_out)
+    # zero RHS with t_eval (reference tests/ivp.rs:20-46): sol.t == t_eval exactly
+    te = [10.0 * i / 20.0 for i in range(21)]
+    for m in (Method.RK23, Method.DOPRI5, Method.DOP853):
+        g = ib.solve_ivp_batch("zero3", 0.0, 10.0, np.ones((5, 3)), None,
+                               Options(method=m, rtol=1e-9, atol=1e-12, t_eval=te))
+        assert np.all(g.n_out == 21) and np.array_equal(g.t_out[:, :21], np.tile(te, (5, 1)))
+        assert np.all(np.abs(g.y_out[:, :21] - 1.0) <= 1e-12)
+    # ragged: N not a multiple of the warp / block size, N = 1
+    for N in (1, 31, 129):
+        prob, yy, par, t0, tf = synth.ensemble("vdp", N)
+        opts = Options(method=Method.DOPRI5, rtol=1e-6, atol=1e-9)
+        g = ib.solve_ivp_batch(prob, t0, tf, yy, par, opts)
+        o = oracle.solve_batch(PROBLEMS[prob], t0, tf, yy, par, opts)
+        assert np.array_equal(g.counters[:, 3:], o.counters[:, 3:])
+    # empty batch
+    g = ib.solve_ivp_batch("sho", 0.0, 1.0, np.zeros((0, 2)), None, Options())
+    assert len(g) == 0
+
+
+def test_config_errors():
+    # reference: Err(Error::Config) before stepping
+    y0 = np.array([[1.0, 0.0]])
+    with pytest.raises(ib.ConfigError):      # rk4.rs:85 sign mismatch
+        ib.solve_ivp_batch("sho", 0.0, 1.0, y0, None, Options(method=Method.RK4, first_step=-0.1))
+    with pytest.raises(ib.ConfigError):      # dop853.rs:178-184 max_steps == 0
+        ib.solve_ivp_batch("sho", 0.0, 1.0, y0, None, Options(method=Method.DOP853, max_steps=0))
+    with pytest.raises(ValueError):          # Tolerance::Vector length mismatch
+        ib.solve_ivp_batch("sho", 0.0, 1.0, y0, None, Options(rtol=[1e-3, 1e-3, 1e-3]))
+
+
+def test_status_codes_nmax_and_vector_tolerance(oracle):
+    y0 = np.tile([1.0, 1.0], (40, 1))
+    opts = Options(method=Method.DOPRI5, rtol=1e-9, atol=1e-9, max_steps=5)
+    g = ib.solve_ivp_batch("exp2", 0.0, 1.0, y0, None, opts)
+    o = oracle.solve_batch(PROBLEMS["exp2"], 0.0, 1.0, y0, None, opts)
+    assert np.all(g.status == Status.NeedLargerNMax) and np.array_equal(g.status, o.status)
+    assert np.array_equal(g.counters, o.counters)
+    # reference tests/ivp.rs:299-334
+    opts = Options(method=Method.DOPRI5, rtol=[1e-2, 1e-10], atol=1e-10)
+    g = ib.solve_ivp_batch("exp2", 0.0, 1.0, y0, None, opts)
+    o = oracle.solve_batch(PROBLEMS["exp2"], 0.0, 1.0, y0, None, opts)
+    assert np.array_equal(g.counters, o.counters)
+    np.testing.assert_allclose(g.y_final, o.y_final, rtol=1e-12)
+
+
+def test_full_size_properties():
+    """BASELINE full size (1M trajectories): size-independent properties instead of the oracle."""
+    N = 1 << 20
+    prob, y0, par, t0, tf = synth.ensemble("vdp", N)
+    opts = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8)
+    g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts)
+    assert np.all(g.status == Status.Success) and np.all(g.t_final == tf)
+    assert np.array_equal(g.nfev, 2 + 11 * g.nstep + 4 * g.naccpt)       # dop853.rs nfev accounting
+    assert np.all(g.nstep >= g.naccpt + g.nrejct)
+    # idempotence + permutation invariance of the work queue: a shuffled sub-batch gives the same rows
+    perm = np.random.default_rng(0).permutation(N)[: 1 << 16]
+    g2 = ib.solve_ivp_batch(prob, t0, tf, y0[perm], par[perm], opts)
+    assert np.array_equal(g2.y_final, g.y_final[perm]) and np.array_equal(g2.counters, g.counters[perm])
+    # every VdP(mu=1) trajectory ends on the limit cycle (|y0| <= ~2.01, |y1| <= ~2.7)
+    assert np.all(np.abs(g.y_final[:, 0]) < 2.1) and np.all(np.abs(g.y_final[:, 1]) < 2.8)
