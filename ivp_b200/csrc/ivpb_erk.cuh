@@ -16,10 +16,27 @@
 #pragma once
 #include "ivpb_common.cuh"
 #include "dop853_tableau.cuh"
+#include "ivpb_fastmath.cuh"
 
 namespace ivpb {
 
 enum { K_OUT = 1, K_EVENTS = 2 };   // kernel feature bits (template parameter FEAT)
+
+// DOPRI5 tableau values (reference src/methods/dopri5.rs:482-520; rational expressions evaluated in fp64
+// at compile time exactly as the reference's consts).  Structure tables are constexpr in the step function.
+static __constant__ double D5_S_COEF[6][5] = {
+    {0.2, 0, 0, 0, 0},
+    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},
+    {35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+static __constant__ double D5_S_C[6] = {0.2, 0.3, 0.8, 8.0 / 9.0, 1.0, 1.0};
+static __constant__ double D5_E_COEF[6] = {71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0,
+                                           22.0 / 525.0, -1.0 / 40.0};
+static __constant__ double D5_D_COEF[6] = {-12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0,
+                                           -10690763975.0 / 1880347072.0, 701980252875.0 / 199316789632.0,
+                                           -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
 
 template <int METHOD> struct MethodTraits;
 template <> struct MethodTraits<M_RK23>   { static constexpr int NC = 4, IORD = 3; };
@@ -288,6 +305,11 @@ struct ErkTraj {
   bool last, reject;
   Out so;
 
+  __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
+    x = tev;
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = yev[i];
+  }
   __device__ __forceinline__ double rt(const KArgs& a, int i) const { return a.rtol[i]; }
   __device__ __forceinline__ double at(const KArgs& a, int i) const { return a.atol[i]; }
 
@@ -338,7 +360,12 @@ struct ErkTraj {
 #pragma unroll
       for (int i = 0; i < P; ++i) p[i] = a.params[index * P + i];
     }
-    facold = 1e-4; hlamb = 0.0;
+#ifdef IVPB_STRICT
+    facold = 1e-4;
+#else
+    facold = (METHOD == M_DOPRI5) ? -9.210340371976182 : 1e-4;    // fast DOPRI5 carries log(facold)
+#endif
+    hlamb = 0.0;
     nfev = 0; nstep = 0; naccpt = 0; nrejct = 0;
     iasti = 0; nonstiff = 0; status = ST_SUCCESS;
     last = false; reject = false;
@@ -359,21 +386,23 @@ struct ErkTraj {
 #pragma unroll
         for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
       double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, tev, yev)) { status = ST_INTERRUPT; return true; }
+      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
     }
     return false;
   }
 
-  __device__ __forceinline__ void finish(const KArgs& a, bool term, double tev, const double* yev) {
+  // Write the per-trajectory results.  (x, y) is the integrator's last accepted point, or the event point
+  // when a terminal event interrupted the integration (step() moves it there).
+  __device__ __forceinline__ void finish(const KArgs& a) {
     if (a.status) a.status[idx] = status;
     if (a.counters) {
       u32* c = a.counters + idx * 6;
       c[0] = nfev; c[1] = 0u; c[2] = 0u; c[3] = nstep; c[4] = naccpt; c[5] = nrejct;
     }
-    if (a.t_final) a.t_final[idx] = term ? tev : x;
+    if (a.t_final) a.t_final[idx] = x;
     if (a.y_final) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) a.y_final[idx * N + i] = term ? yev[i] : y[i];
+      for (int i = 0; i < N; ++i) a.y_final[idx * N + i] = y[i];
     }
     if (a.h_next) a.h_next[idx] = h;
     if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
@@ -385,7 +414,7 @@ struct ErkTraj {
     }
   }
 
-  // One attempted step.  Returns true when the trajectory has ended (status set, results written).
+  // One attempted step.  Returns true when the trajectory has ended (status set; the caller runs finish()).
   __device__ __forceinline__ bool step(const KArgs& a);
 };
 
@@ -407,8 +436,8 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     const double uround = 2.3e-16, safe = 0.9;
     const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0;      // beta = 0 => facold^beta == 1 exactly
     const double h_max = hmax_of(a);
-    if ((u64)nstep > a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
-    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; finish(a, false, 0.0, y); return true; }
+    if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
+    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
     if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
     nstep += 1;
 
@@ -420,13 +449,13 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (STG_LEN[s] == 1) {
-          y1[i] = y[i] + h * STG_COEF[s][0] * k[STG_SLOT[s][0]][i];        // (h*a21)*k1, dop853.rs:296
+          y1[i] = y[i] + h * D853_STG_COEF[s][0] * k[STG_SLOT[s][0]][i];   // (h*a21)*k1, dop853.rs:296
         } else {
-          IVPB_LINCOMB(acc, STG_LEN[s], STG_SLOT[s], STG_COEF[s], k, i)
+          IVPB_LINCOMB(acc, STG_LEN[s], STG_SLOT[s], D853_STG_COEF[s], k, i)
           y1[i] = y[i] + h * acc;
         }
       }
-      const double ts = (s == 10) ? (x + h) : (x + STG_C[s] * h);
+      const double ts = (s == 10) ? (x + h) : (x + D853_STG_C[s] * h);
       Prob::ode(ts, y1, p, k[STG_OUT[s]]);
     }
     const double xph = x + h;
@@ -434,27 +463,47 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     // k4 = sum b_j k_j ; k5 = y + h k4      (slots 3 and 4)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      IVPB_LINCOMB(acc, LIN_LEN[0], LIN_SLOT[0], LIN_COEF[0], k, i)
+      IVPB_LINCOMB(acc, LIN_LEN[0], LIN_SLOT[0], D853_LIN_COEF[0], k, i)
       k[3][i] = acc;
       k[4][i] = y[i] + h * acc;
     }
     double err = 0.0, err2 = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+#ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(k[4][i]));
-      double erri = k[3][i] - BHH[0] * k[0][i] - BHH[1] * k[8][i] - BHH[2] * k[2][i];
-      const double q2 = erri / sk;
+#else
+      const double sk = at(a, i) + rt(a, i) * fm::maxsel(fabs(y[i]), fabs(k[4][i]));
+#endif
+      const double erri = k[3][i] - D853_BHH[0] * k[0][i] - D853_BHH[1] * k[8][i] - D853_BHH[2] * k[2][i];
+      IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], D853_LIN_COEF[1], k, i)
+#ifdef IVPB_STRICT
+      const double q2 = erri / sk, q1 = e8 / sk;         // dop853.rs:412,423
+#else
+      const double rsk = fm::rcp(sk);                      // one reciprocal shared by both norms
+      const double q2 = erri * rsk, q1 = e8 * rsk;
+#endif
       err2 += q2 * q2;
-      IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], LIN_COEF[1], k, i)
-      const double q1 = e8 / sk;
       err += q1 * q1;
     }
     double deno = err + 0.01 * err2;
     if (deno <= 0.0) deno = 1.0;
+#ifdef IVPB_STRICT
     err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
     const double fac11 = pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
-    double fac = fmax(facc2, fmin(facc1, fac11 / safe));
+    // facold^beta == 1 exactly (beta = 0), so fac = fac11 (dop853.rs:434)
+    const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
     double hnew = h / fac;
+    const double hrej = h / fmin(facc1, fac11 / safe);       // dop853.rs:645
+#else
+    // Same controller written with the reciprocal step factor 1/fac = safe * err^(-1/8), which needs
+    // multiplications only (see ivpb_fastmath.cuh): hnew = h * clamp(safe/fac11, 1/facc1, 1/facc2).
+    err = fabs(h) * err * fm::rsqrt((double)N * deno);
+    const double ratio = safe * fm::rroot8(err);
+    double hnew = h * fm::minsel(fm::maxsel(ratio, 0.333), 6.0);
+    const double hrej = h * fm::maxsel(ratio, 0.333);
+    (void)facc1; (void)facc2;
+#endif
 
     if (err <= 1.0) {
       facold = fmax(err, 1.0e-4);
@@ -471,7 +520,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 6.1) {
           nonstiff = 0; iasti += 1;
-          if (iasti == 15) { status = ST_STIFF; finish(a, false, 0.0, y); return true; }
+          if (iasti == 15) { status = ST_STIFF; return true; }
         } else {
           nonstiff += 1;
           if (nonstiff == 6) iasti = 0;
@@ -492,7 +541,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
           cont[3][i] = ydiff - h * k[3][i] - bspl;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            IVPB_LINCOMB(acc, DF_LEN[r], DF_SLOT[r], DF_COEF[r], k, i)
+            IVPB_LINCOMB(acc, DF_LEN[r], DF_SLOT[r], D853_DF_COEF[r], k, i)
             cont[4 + r][i] = acc;
           }
         }
@@ -500,10 +549,10 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         for (int s = 0; s < 3; ++s) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            IVPB_LINCOMB(acc, DSTG_LEN[s], DSTG_SLOT[s], DSTG_COEF[s], k, i)
+            IVPB_LINCOMB(acc, DSTG_LEN[s], DSTG_SLOT[s], D853_DSTG_COEF[s], k, i)
             y1[i] = y[i] + h * acc;
           }
-          Prob::ode(x + DSTG_C[s] * h, y1, p, k[DSTG_OUT[s]]);
+          Prob::ode(x + D853_DSTG_C[s] * h, y1, p, k[DSTG_OUT[s]]);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -511,7 +560,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
           for (int r = 0; r < 4; ++r) {
             double acc = cont[4 + r][i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc += DS_COEF[r][j] * k[DS_SLOT[r][j]][i];
+            for (int j = 0; j < 4; ++j) acc += D853_DS_COEF[r][j] * k[DS_SLOT[r][j]][i];
             cont[4 + r][i] = h * acc;
           }
         }
@@ -522,14 +571,14 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       x = xph;
       if constexpr (FEAT != 0) {
         if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
-          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
-      if (last) { h = hnew; status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+      if (last) { h = hnew; status = ST_SUCCESS; return true; }
       if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
       if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
     } else {
-      hnew = h / fmin(facc1, fac11 / safe);
+      hnew = hrej;
       reject = true;
       if (naccpt > 1u) nrejct += 1;
       last = false;
@@ -540,29 +589,16 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 
   } else if constexpr (METHOD == M_DOPRI5) {
     // ---- reference src/methods/dopri5.rs:266-461 ----
-    constexpr double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
     constexpr int S_LEN[6] = {1, 2, 3, 4, 5, 5};
     constexpr int S_SLOT[6][5] = {{0, 0, 0, 0, 0}, {0, 1, 0, 0, 0}, {0, 1, 2, 0, 0}, {0, 1, 2, 3, 0}, {0, 1, 2, 3, 4}, {0, 2, 3, 4, 5}};
-    constexpr double S_COEF[6][5] = {
-        {0.2, 0, 0, 0, 0},
-        {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0},
-        {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0},
-        {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0},
-        {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},
-        {35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
     constexpr int S_OUT[6] = {1, 2, 3, 4, 5, 1};
-    constexpr double S_C[6] = {c2, c3, c4, c5, 1.0, 1.0};
-    // e / d rows over slots {k1,k3,k4,k5,k6,k2(new)}
-    constexpr int ED_SLOT[6] = {0, 2, 3, 4, 5, 1};
-    constexpr double E_COEF[6] = {71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0};
-    constexpr double D_COEF[6] = {-12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
-                                  701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
+    constexpr int ED_SLOT[6] = {0, 2, 3, 4, 5, 1};            // e / d rows over {k1,k3,k4,k5,k6,k2(new)}
     const double uround = 2.3e-16, safe = 0.9, beta = 0.04;
     const double facc1 = 1.0 / 0.2, facc2 = 1.0 / 10.0;
     const double expo1 = 0.2 - beta * 0.75;
     const double h_max = hmax_of(a);
-    if ((u64)nstep > a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
-    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; finish(a, false, 0.0, y); return true; }
+    if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
+    if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
     if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
     nstep += 1;
 
@@ -575,15 +611,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (S_LEN[s] == 1) {
-          y1[i] = y[i] + h * S_COEF[s][0] * k[S_SLOT[s][0]][i];
+          y1[i] = y[i] + h * D5_S_COEF[s][0] * k[S_SLOT[s][0]][i];
         } else {
-          double acc = S_COEF[s][0] * k[S_SLOT[s][0]][i];
+          double acc = D5_S_COEF[s][0] * k[S_SLOT[s][0]][i];
 #pragma unroll
-          for (int j = 1; j < 5; ++j) if (j < S_LEN[s]) acc += S_COEF[s][j] * k[S_SLOT[s][j]][i];
+          for (int j = 1; j < 5; ++j) if (j < S_LEN[s]) acc += D5_S_COEF[s][j] * k[S_SLOT[s][j]][i];
           y1[i] = y[i] + h * acc;
         }
       }
-      const double ts = (s >= 4) ? xph : (x + S_C[s] * h);
+      const double ts = (s >= 4) ? xph : (x + D5_S_C[s] * h);
       Prob::ode(ts, y1, p, k[S_OUT[s]]);
     }
     nfev += 6;
@@ -591,45 +627,66 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     if constexpr (DENSE) {                                       // dopri5.rs:328-334
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        double acc = D_COEF[0] * k[ED_SLOT[0]][i];
+        double acc = D5_D_COEF[0] * k[ED_SLOT[0]][i];
 #pragma unroll
-        for (int j = 1; j < 6; ++j) acc += D_COEF[j] * k[ED_SLOT[j]][i];
+        for (int j = 1; j < 6; ++j) acc += D5_D_COEF[j] * k[ED_SLOT[j]][i];
         cont[4][i] = h * acc;
       }
     }
     double err = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {                                // k4 <- scaled error vector, dopri5.rs:337-340
-      double acc = E_COEF[0] * k[ED_SLOT[0]][i];
+      double acc = D5_E_COEF[0] * k[ED_SLOT[0]][i];
 #pragma unroll
-      for (int j = 1; j < 6; ++j) acc += E_COEF[j] * k[ED_SLOT[j]][i];
+      for (int j = 1; j < 6; ++j) acc += D5_E_COEF[j] * k[ED_SLOT[j]][i];
       k[3][i] = acc * h;
+#ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
       err += (k[3][i] / sk) * (k[3][i] / sk);
+#else
+      const double sk = at(a, i) + rt(a, i) * fm::maxsel(fabs(y[i]), fabs(y1[i]));
+      const double q = k[3][i] * fm::rcp(sk);
+      err += q * q;
+#endif
     }
+#ifdef IVPB_STRICT
     err = sqrt(err / (double)N);
     const double fac11 = pow(err, expo1);
     double fac = fac11 / pow(facold, beta);
     fac = fmax(facc2, fmin(facc1, fac / safe));
     double hnew = h / fac;
+    const bool accept = err <= 1.0;
+#else
+    // Same PI controller in log space: err = sqrt(e2), so log(err) = log(e2)/2 needs no square root, and
+    // log(facold) is carried from the previous accepted step (facold holds log(max(err, 1e-4)) in this build).
+    const double e2 = err * (1.0 / (double)N);
+    const double lerr = 0.5 * log(e2);
+    double hnew = h * fm::minsel(fm::maxsel(safe * exp(beta * facold - expo1 * lerr), 0.2), 10.0);
+    const bool accept = e2 <= 1.0;
+    (void)facc1; (void)facc2;
+#endif
 
-    if (err <= 1.0) {
+    if (accept) {
+#ifdef IVPB_STRICT
       facold = fmax(err, 1.0e-4);
+#else
+      facold = fmax(lerr, -9.210340371976182);              // log(1e-4)
+#endif
       naccpt += 1;
       if ((naccpt % 1000u == 0u) || (iasti > 0)) {              // dopri5.rs:364-391 (uses overwritten k4: quirk kept)
         double stnum = 0.0, stden = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double d1 = k[1][i] - k[5][i];
-          const double ysti = y[i] + h * (S_COEF[4][0] * k[0][i] + S_COEF[4][1] * k[1][i] + S_COEF[4][2] * k[2][i] +
-                                          S_COEF[4][3] * k[3][i] + S_COEF[4][4] * k[4][i]);
+          const double ysti = y[i] + h * (D5_S_COEF[4][0] * k[0][i] + D5_S_COEF[4][1] * k[1][i] + D5_S_COEF[4][2] * k[2][i] +
+                                          D5_S_COEF[4][3] * k[3][i] + D5_S_COEF[4][4] * k[4][i]);
           const double d2 = y1[i] - ysti;
           stnum += d1 * d1; stden += d2 * d2;
         }
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 3.25) {
           nonstiff = 0; iasti += 1;
-          if (iasti == 15) { status = ST_STIFF; finish(a, false, 0.0, y); return true; }
+          if (iasti == 15) { status = ST_STIFF; return true; }
         } else {
           nonstiff += 1;
           if (nonstiff == 6) iasti = 0;
@@ -652,14 +709,18 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       x = xph;
       if constexpr (FEAT != 0) {
         if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
-          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
-      if (last) { h = hnew; status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+      if (last) { h = hnew; status = ST_SUCCESS; return true; }
       if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
       if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
     } else {
+#ifdef IVPB_STRICT
       hnew = h / fmin(facc1, fac11 / safe);
+#else
+      hnew = h * fm::maxsel(safe * exp(-expo1 * lerr), 0.2);
+#endif
       reject = true;
       if (naccpt > 1u) nrejct += 1;
       last = false;
@@ -675,7 +736,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     constexpr double d31 = 5.0 / 9.0, d32 = -2.0 / 3.0, d33 = -8.0 / 9.0, d34 = 1.0;
     const double safe = 0.9, scale_min = 0.2, scale_max = 10.0, expo = -1.0 / 3.0;
     const double hmax = hmax_of(a);
-    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
     if ((x + h - xend) * posneg > 0.0) h = xend - x;
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
@@ -693,11 +754,24 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     for (int i = 0; i < N; ++i) {
       const double ye = h * (e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i]);
       const double tol = at(a, i) + rt(a, i) * fmax(fabs(yt[i]), fabs(y[i]));
+#ifdef IVPB_STRICT
       const double q = ye / tol;
+#else
+      const double q = ye * fm::rcp(tol);
+#endif
       err += q * q;
     }
+#ifdef IVPB_STRICT
     err = sqrt(err / (double)N);
-    if (err <= 1.0) {
+    const double sfac = safe * pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
+    const bool accept = err <= 1.0;
+#else
+    const double errsq = err * (1.0 / (double)N);              // err^2; err^(-1/3) = cbrt(1/sqrt(err^2))
+    const double sfac = safe * cbrt(fm::rsqrt(errsq));
+    const bool accept = errsq <= 1.0;
+    (void)expo;
+#endif
+    if (accept) {
       nstep += 1; naccpt += 1;
       const double xold = x;
       double cont[NC][N];
@@ -714,23 +788,23 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       x += h;
       if constexpr (FEAT != 0) {
         if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
-          status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
 #pragma unroll
       for (int i = 0; i < N; ++i) k1[i] = k4[i];
-      h *= fmax(fmin(safe * pow(err, expo), scale_max), scale_min);
+      h *= fmax(fmin(sfac, scale_max), scale_min);
       if (fabs(h) > hmax) h = hmax * posneg;
-      if (x == xend) { status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+      if (x == xend) { status = ST_SUCCESS; return true; }
     } else {
       nrejct += 1;
-      h *= fmax(fmin(safe * pow(err, expo), 1.0), scale_min);
+      h *= fmax(fmin(sfac, 1.0), scale_min);
     }
     return false;
 
   } else {
     // ---- RK4: reference src/methods/rk4.rs:141-222 ----
-    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; finish(a, false, 0.0, y); return true; }
+    if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
     const bool lst = (x + 1.01 * h - xend) * signum(h) > 0.0;
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
@@ -759,10 +833,10 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     }
     if constexpr (FEAT != 0) {
       if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
-        status = ST_INTERRUPT; finish(a, true, tev, yev); return true;
+        status = ST_INTERRUPT; to_event_point(tev, yev); return true;
       }
     }
-    if (lst) { status = ST_SUCCESS; finish(a, false, 0.0, y); return true; }
+    if (lst) { status = ST_SUCCESS; return true; }
     return false;
   }
 }
@@ -778,14 +852,17 @@ __device__ __forceinline__ void erk_body(const KArgs& a) {
   if (a.static_sched) {
     const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.N) return;
-    if (T.init(a, idx)) { double z[Prob::N] = {}; T.finish(a, false, 0.0, z); return; }
-    while (!T.step(a)) {}
+    if (!T.init(a, idx)) {
+      while (!T.step(a)) {}
+    }
+    T.finish(a);
     return;
   }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
   for (;;) {
+    // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp)
     const unsigned need = __ballot_sync(FULL, !active);
     if (need && !exhausted) {
       const int leader = __ffs(need) - 1;
@@ -796,7 +873,7 @@ __device__ __forceinline__ void erk_body(const KArgs& a) {
         const i64 idx = (i64)base + __popc(need & ((1u << lane) - 1u));
         if (idx < a.N) {
           active = true;
-          if (T.init(a, idx)) { T.finish(a, true, T.x, T.y); active = false; }
+          if (T.init(a, idx)) { T.finish(a); active = false; }
         }
       }
       if ((i64)base + __popc(need) >= a.N) exhausted = true;
@@ -805,9 +882,13 @@ __device__ __forceinline__ void erk_body(const KArgs& a) {
       if (exhausted) break;
       continue;
     }
-    if (active) {
-      if (T.step(a)) active = false;
-    }
+    // ---- hot loop: every lane that owns a trajectory attempts steps until one of them finishes.  Nothing of
+    // the refill logic is live in here, so the loop is as tight as the static schedule's.
+    bool done = false;
+    do {
+      if (active) done = T.step(a);
+    } while (!__any_sync(FULL, done));
+    if (done) { T.finish(a); active = false; }
   }
 }
 

@@ -479,3 +479,28 @@ int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Debug hook (not part of include/ivpb.h): evaluates the fast-mode controller helpers of
+// ivpb_fastmath.cuh on the device so tests can bound their error against libm.
+#include "ivpb_fastmath.cuh"
+namespace {
+__global__ void fastmath_kernel(const double* x, int n, double* r_rcp, double* r_rsqrt, double* r_rroot8) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  r_rcp[i] = ivpb::fm::rcp(x[i]);
+  r_rsqrt[i] = ivpb::fm::rsqrt(x[i]);
+  r_rroot8[i] = ivpb::fm::rroot8(x[i]);
+}
+}  // namespace
+extern "C" int ivpb_debug_fastmath(const double* x, int n, double* r_rcp, double* r_rsqrt, double* r_rroot8) {
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * 4 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;
+  cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  fastmath_kernel<<<(n + 127) / 128, 128>>>(d, n, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+  cudaMemcpy(r_rcp, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaMemcpy(r_rsqrt, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(r_rroot8, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
+}
