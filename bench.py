@@ -106,10 +106,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def dist_env():
-    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-
-
 def run_reference(args, rank, world):
     """Reference arm: the reference's own algorithm on the host cores (oracle port; the Rust crate cannot be
     compiled in this image), all hardware threads, each step a bounded sample of the workload."""
@@ -156,6 +152,7 @@ def main():
     ap.add_argument("--static", action="store_true", help="disable work-queue refill (A/B)")
     ap.add_argument("--strict", action="store_true", help="-fmad=false kernel variant (A/B)")
     args = ap.parse_args()
+    from ivp_b200.dist import dist_env, reduce_time_and_count, weak_offset
     rank, local_rank, world = dist_env()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -179,7 +176,7 @@ def main():
 
     ens, method, rtol, atol, F, n = WORKLOADS[args.workload]
     Nper = args.trajectories
-    prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=rank * Nper)
+    prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=weak_offset(Nper, rank))
     problem = api.Problem.builtin(prob_name)
     flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0)
     opts = Options(method=Method[method], rtol=rtol, atol=atol, flags=flags)
@@ -232,13 +229,7 @@ def main():
     acc_local = int(naccpt.sum())
     flops_launch = algorithmic_flops(method, F, n, nstep, naccpt, dense=False)
 
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    acc = torch.tensor([acc_local], dtype=torch.float64, device=dev)
-    if use_dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-    total_ms_max = float(t.item())
-    acc_all = float(acc.item())
+    total_ms_max, acc_all = reduce_time_and_count(total_ms, acc_local, dev, use_dist)
     value = acc_all * args.steps / (total_ms_max * 1e-3)
 
     # ---- end-to-end arm: public host-buffer API, pinned host memory, copies inside the timed region ----
@@ -266,12 +257,8 @@ def main():
         ctx.solve_host(problem, t0, tf, y0_np, par_np, mo, st)     # returns after the D2H copies completed
     e2e_s = time.perf_counter() - w0
     e2e_acc = int(h_counters.numpy().view(np.uint32)[:, 4].sum())
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    ea = torch.tensor([float(e2e_acc)], dtype=torch.float64, device=dev)
-    if use_dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ea, op=dist.ReduceOp.SUM)
-    e2e_value = float(ea.item()) * e2e_steps / float(te.item())
+    e2e_s_max, e2e_acc_all = reduce_time_and_count(e2e_s, float(e2e_acc), dev, use_dist)
+    e2e_value = e2e_acc_all * e2e_steps / e2e_s_max
     assert e2e_acc == acc_local, "host-buffer and device-buffer paths disagree"
 
     # ---- roofline of the dominant (only) kernel, rank 0 ----
@@ -326,7 +313,7 @@ def main():
             "accepted_steps_per_step": acc_all, "rejected_steps_rank0": int(nrejct.sum()),
             "status_success_frac_rank0": float(np.mean(status == 0)),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(te.item()) / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers)"},
+                    "ms_per_step": e2e_s_max / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))
     if use_dist:

@@ -18,7 +18,7 @@ import numpy as np
 from . import _abi
 from .types import BatchSolution, ConfigError, Method, Options, Solution, Status  # noqa: F401
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libivpb.so")
+_LIB_PATH = os.environ.get("IVPB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libivpb.so")
 _lib = None
 
 #: Built-in problems (include/ivpb.h `ivpb_builtin`).

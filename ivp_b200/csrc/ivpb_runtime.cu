@@ -66,8 +66,27 @@ struct Device {
   int sms = 0;
   cudaStream_t stream = nullptr;
   u64* queue = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
   Buf y0, params, t_eval, out[OUT_FIELDS];
 };
+
+// bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
+void field_bytes(int n, int nev, int64_t cap, int max_events, size_t per[OUT_FIELDS]) {
+  const size_t v[OUT_FIELDS] = {4, 24, 8, 8u * n, 8, 4, 8u * (size_t)cap, 8u * (size_t)cap * n,
+                                4u * nev, 8u * (size_t)nev * max_events, 8u * (size_t)nev * max_events * n};
+  for (int f = 0; f < OUT_FIELDS; ++f) per[f] = v[f];
+}
+void out_to_array(const ivpb_outputs* o, void* a[OUT_FIELDS]) {
+  void* v[OUT_FIELDS] = {o->status, o->counters, o->t_final, o->y_final, o->h_next, o->n_out,
+                         o->t_out, o->y_out, o->ev_count, o->ev_t, o->ev_y};
+  for (int f = 0; f < OUT_FIELDS; ++f) a[f] = v[f];
+}
+void array_to_out(void* const a[OUT_FIELDS], ivpb_outputs* d) {
+  d->status = (int32_t*)a[OUT_STATUS]; d->counters = (uint32_t*)a[OUT_COUNTERS];
+  d->t_final = (double*)a[OUT_TFINAL]; d->y_final = (double*)a[OUT_YFINAL]; d->h_next = (double*)a[OUT_HNEXT];
+  d->n_out = (int32_t*)a[OUT_NOUT]; d->t_out = (double*)a[OUT_TOUT]; d->y_out = (double*)a[OUT_YOUT];
+  d->ev_count = (int32_t*)a[OUT_EVCOUNT]; d->ev_t = (double*)a[OUT_EVT]; d->ev_y = (double*)a[OUT_EVY];
+}
 
 }  // namespace
 
@@ -310,6 +329,8 @@ int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, id);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaMalloc((void**)&d.queue, sizeof(u64));
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
     if (err != cudaSuccess) { delete c; return fail(nullptr, IVPB_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(err)); }
     c->devs.push_back(d);
   }
@@ -336,6 +357,8 @@ void ivpb_destroy(ivpb_ctx* ctx) {
     d.y0.release(); d.params.release(); d.t_eval.release();
     for (auto& b : d.out) b.release();
     cudaFree(d.queue);
+    if (d.ev_ready) cudaEventDestroy(d.ev_ready);
+    if (d.ev_done) cudaEventDestroy(d.ev_done);
     cudaStreamDestroy(d.stream);
   }
   for (auto& u : ctx->user) ivpb_nvrtc_release(u);
@@ -383,9 +406,60 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   if (int rc = validate(ctx, pi, opt, N, t0, tf)) return rc;
   if (!d_y0 || !d_out) return fail(ctx, IVPB_ERR_CONFIG, "null device buffer");
   if (pi.p > 0 && !d_params) return fail(ctx, IVPB_ERR_CONFIG, "params is null but the problem has parameters");
-  Device& dev = ctx->devs[0];
-  CK(cudaSetDevice(dev.id));
-  return launch_shard(ctx, dev, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, (cudaStream_t)stream);
+  Device& dev0 = ctx->devs[0];
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int G = (int)ctx->devs.size();
+  CK(cudaSetDevice(dev0.id));
+  if (G == 1) return launch_shard(ctx, dev0, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, s0);
+
+  // Multi-device, device-resident: inputs/outputs live on the first device.  Shard g > 0 receives its
+  // slice of y0/params by a peer copy over NVLink, integrates it locally, and returns its results by peer
+  // copies into the caller's arrays -- no collective, trajectories never interact.
+  const int64_t cap = opt->has_t_eval ? (int64_t)opt->n_t_eval + 1 : (int64_t)opt->max_out;
+  const int n = pi.n;
+  size_t per[OUT_FIELDS];
+  field_bytes(n, pi.nev, cap, opt->max_events, per);
+  void* dst[OUT_FIELDS];
+  out_to_array(d_out, dst);
+  CK(cudaEventRecord(dev0.ev_ready, s0));          // inputs on device 0 are ready once s0 reaches here
+  for (int g = 1; g < G; ++g) {
+    Device& dev = ctx->devs[g];
+    const int64_t lo = N * g / G, hi = N * (g + 1) / G, Ng = hi - lo;
+    if (Ng == 0) continue;
+    CK(cudaSetDevice(dev.id));
+    CK(cudaStreamWaitEvent(dev.stream, dev0.ev_ready, 0));
+    CK(dev.y0.ensure(sizeof(double) * n * Ng));
+    CK(cudaMemcpyPeerAsync(dev.y0.p, dev.id, d_y0 + lo * n, dev0.id, sizeof(double) * n * Ng, dev.stream));
+    if (pi.p > 0) {
+      CK(dev.params.ensure(sizeof(double) * pi.p * Ng));
+      CK(cudaMemcpyPeerAsync(dev.params.p, dev.id, d_params + lo * pi.p, dev0.id, sizeof(double) * pi.p * Ng, dev.stream));
+    }
+    void* loc[OUT_FIELDS];
+    for (int f = 0; f < OUT_FIELDS; ++f) {
+      loc[f] = nullptr;
+      if (!dst[f] || per[f] == 0) continue;
+      CK(dev.out[f].ensure(per[f] * Ng));
+      loc[f] = dev.out[f].p;
+      if (f >= OUT_NOUT) CK(cudaMemsetAsync(loc[f], 0, per[f] * Ng, dev.stream));
+    }
+    ivpb_outputs d;
+    array_to_out(loc, &d);
+    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, (const double*)dev.y0.p,
+                              pi.p > 0 ? (const double*)dev.params.p : nullptr, &d, dev.stream))
+      return rc;
+    for (int f = 0; f < OUT_FIELDS; ++f)
+      if (loc[f])
+        CK(cudaMemcpyPeerAsync((char*)dst[f] + per[f] * lo, dev0.id, loc[f], dev.id, per[f] * Ng, dev.stream));
+    CK(cudaEventRecord(dev.ev_done, dev.stream));
+  }
+  CK(cudaSetDevice(dev0.id));
+  {
+    const int64_t N0 = N / G;      // shard 0 works in place on the caller's arrays
+    if (int rc = launch_shard(ctx, dev0, problem, pi, opt, N0, t0, tf, d_y0, d_params, d_out, s0)) return rc;
+  }
+  for (int g = 1; g < G; ++g)
+    if (N * (g + 1) / G - N * g / G > 0) CK(cudaStreamWaitEvent(s0, ctx->devs[g].ev_done, 0));
+  return 0;
 }
 
 int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0, double tf,
@@ -400,10 +474,10 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   const int64_t cap = opt->has_t_eval ? (int64_t)opt->n_t_eval + 1 : (int64_t)opt->max_out;
   const int n = pi.n, nev = pi.nev, me = opt->max_events;
   // bytes per trajectory of each output field, and the host base pointers
-  const size_t per[OUT_FIELDS] = {4, 24, 8, 8u * n, 8, 4, 8u * (size_t)cap, 8u * (size_t)cap * n,
-                                  4u * nev, 8u * (size_t)nev * me, 8u * (size_t)nev * me * n};
-  void* host[OUT_FIELDS] = {out->status, out->counters, out->t_final, out->y_final, out->h_next, out->n_out,
-                            out->t_out, out->y_out, out->ev_count, out->ev_t, out->ev_y};
+  size_t per[OUT_FIELDS];
+  field_bytes(n, nev, cap, me, per);
+  void* host[OUT_FIELDS];
+  out_to_array(out, host);
   // static contiguous split [g*N/G, (g+1)*N/G) -- trajectories are independent, no exchange step
   for (int g = 0; g < G; ++g) {
     Device& dev = ctx->devs[g];
@@ -424,10 +498,7 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       dptr[f] = dev.out[f].p;
     }
     ivpb_outputs d;
-    d.status = (int32_t*)dptr[OUT_STATUS]; d.counters = (uint32_t*)dptr[OUT_COUNTERS];
-    d.t_final = (double*)dptr[OUT_TFINAL]; d.y_final = (double*)dptr[OUT_YFINAL]; d.h_next = (double*)dptr[OUT_HNEXT];
-    d.n_out = (int32_t*)dptr[OUT_NOUT]; d.t_out = (double*)dptr[OUT_TOUT]; d.y_out = (double*)dptr[OUT_YOUT];
-    d.ev_count = (int32_t*)dptr[OUT_EVCOUNT]; d.ev_t = (double*)dptr[OUT_EVT]; d.ev_y = (double*)dptr[OUT_EVY];
+    array_to_out(dptr, &d);
     // sample / event slots the kernel does not touch must read as zero on the host
     if (d.t_out) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
     if (d.y_out) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));

@@ -297,3 +297,38 @@ def test_fastmath_helpers_accuracy():
         assert np.max(np.abs(r3[mid] * x[mid] ** 0.125 - 1.0)) < 1e-14
     # controller limits: tiny / zero error => factor beyond the upper clamp; huge / inf / nan => 0
     assert np.all(r3[(x < 1e-30)] > 6.0 / 0.9) and np.all(r3[~(x < 1e30)] == 0.0)
+
+
+def test_multi_device_context_matches_single_device():
+    """static split across the devices of one context, results gathered over NVLink peer copies
+    (device-resident call) or by per-device D2H copies (host call) -- identical to the one-GPU result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from ivp_b200 import _abi, api
+    N = 10007
+    prob, y0, par, t0, tf = synth.ensemble("vdp", N)
+    te = np.linspace(t0, 20.0, 7)
+    opts = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, t_eval=te)
+    one = ib.solve_ivp_batch(prob, t0, 20.0, y0, par, opts)
+    ctx = api.Context(list(range(torch.cuda.device_count())))
+    many = ib.solve_ivp_batch(prob, t0, 20.0, y0, par, opts, ctx=ctx)
+    for f in ("status", "counters", "t_final", "y_final", "n_out", "t_out", "y_out"):
+        assert np.array_equal(getattr(one, f), getattr(many, f)), f
+    # device-resident entry point: buffers on device 0, shards travel by peer copies
+    problem = api.Problem.builtin(prob)
+    mo = _abi.MarshalledOptions(opts, problem.n, problem.n_events)
+    dev = torch.device("cuda", 0)
+    y0_d, par_d = torch.from_numpy(y0).to(dev), torch.from_numpy(par).to(dev)
+    st = torch.full((N,), -1, dtype=torch.int32, device=dev)
+    cn = torch.zeros((N, 6), dtype=torch.int32, device=dev)
+    yf = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+    no = torch.zeros((N,), dtype=torch.int32, device=dev)
+    yo = torch.zeros((N, mo.cap, 2), dtype=torch.float64, device=dev)
+    ctx.solve_device(problem, t0, 20.0, N, y0_d.data_ptr(), par_d.data_ptr(), mo,
+                     {"status": st.data_ptr(), "counters": cn.data_ptr(), "y_final": yf.data_ptr(),
+                      "n_out": no.data_ptr(), "y_out": yo.data_ptr()}, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(st.cpu().numpy(), one.status)
+    assert np.array_equal(cn.cpu().numpy().view(np.uint32), one.counters)
+    assert np.array_equal(yf.cpu().numpy(), one.y_final) and np.array_equal(yo.cpu().numpy(), one.y_out)
