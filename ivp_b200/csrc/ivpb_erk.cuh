@@ -22,6 +22,15 @@ namespace ivpb {
 
 enum { K_OUT = 1, K_EVENTS = 2 };   // kernel feature bits (template parameter FEAT)
 
+// Multiply-add of the solver core.  Default build: an explicit fma, so the result does not depend on which
+// products a particular compiler run chooses to contract -- the static, work-queue and NVRTC instances of a
+// kernel agree bit for bit.  Strict build (-fmad=false): the reference's separate multiply and add.
+#ifdef IVPB_STRICT
+#define IVPB_MA(a, b, c) ((a) * (b) + (c))
+#else
+#define IVPB_MA(a, b, c) fma((a), (b), (c))
+#endif
+
 // DOPRI5 tableau values (reference src/methods/dopri5.rs:482-520; rational expressions evaluated in fp64
 // at compile time exactly as the reference's consts).  Structure tables are constexpr in the step function.
 static __constant__ double D5_S_COEF[6][5] = {
@@ -53,25 +62,26 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
     const double s = (xi - xold) / h, s1 = 1.0 - s;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double conpar = c[4][i] + s * (c[5][i] + s1 * (c[6][i] + s * c[7][i]));
-      yi[i] = c[0][i] + s * (c[1][i] + s1 * (c[2][i] + s * (c[3][i] + s1 * conpar)));
+      const double conpar = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, c[7][i], c[6][i]), c[5][i]), c[4][i]);
+      yi[i] = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, IVPB_MA(s1, conpar, c[3][i]), c[2][i]), c[1][i]), c[0][i]);
     }
   } else if constexpr (METHOD == M_DOPRI5) {   // dopri5.rs:467-478
     const double th = (xi - xold) / h, th1 = 1.0 - th;
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      yi[i] = c[0][i] + th * (c[1][i] + th1 * (c[2][i] + th * (c[3][i] + th1 * c[4][i])));
+      yi[i] = IVPB_MA(th, IVPB_MA(th1, IVPB_MA(th, IVPB_MA(th1, c[4][i], c[3][i]), c[2][i]), c[1][i]), c[0][i]);
   } else if constexpr (METHOD == M_RK23) {     // rk23.rs:313-321
     const double xc = (xi - xold) / h, x2 = xc * xc, x3 = x2 * xc;
 #pragma unroll
-    for (int i = 0; i < N; ++i) yi[i] = c[0][i] + h * (c[1][i] * xc + c[2][i] * x2 + c[3][i] * x3);
+    for (int i = 0; i < N; ++i)
+      yi[i] = IVPB_MA(h, IVPB_MA(c[3][i], x3, IVPB_MA(c[2][i], x2, c[1][i] * xc)), c[0][i]);
   } else {                                      // rk4.rs:229-244 (cubic Hermite, cont = [y_old, k4 stage, f_new, y_new])
     const double t = (xi - xold) / h, t2 = t * t, t3 = t2 * t;
     const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
     const double h01 = -2.0 * t3 + 3.0 * t2, h11 = t3 - t2;
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      yi[i] = h00 * c[0][i] + h10 * h * c[1][i] + h01 * c[3][i] + h11 * h * c[2][i];
+      yi[i] = IVPB_MA(h11 * h, c[2][i], IVPB_MA(h01, c[3][i], IVPB_MA(h10 * h, c[1][i], h00 * c[0][i])));
   }
 }
 
@@ -318,23 +328,24 @@ struct ErkTraj {
     double dnf = 0.0, dny = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double sk = at(a, i) + rt(a, i) * fabs(y[i]);
-      dnf += (k1[i] / sk) * (k1[i] / sk);
-      dny += (y[i] / sk) * (y[i] / sk);
+      const double sk = IVPB_MA(rt(a, i), fabs(y[i]), at(a, i));
+      const double qf = k1[i] / sk, qy = y[i] / sk;
+      dnf = IVPB_MA(qf, qf, dnf);
+      dny = IVPB_MA(qy, qy, dny);
     }
     double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
     if (hh > fabs(hmax)) hh = fabs(hmax);
     hh = fabs(hh) * signum(posneg);
     double y1[N], f1[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) y1[i] = y[i] + hh * k1[i];
+    for (int i = 0; i < N; ++i) y1[i] = IVPB_MA(hh, k1[i], y[i]);
     Prob::ode(x + hh, y1, p, f1);
     double der2 = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double sk = at(a, i) + rt(a, i) * fabs(y[i]);
+      const double sk = IVPB_MA(rt(a, i), fabs(y[i]), at(a, i));
       const double df = (f1[i] - k1[i]) / sk;
-      der2 += df * df;
+      der2 = IVPB_MA(df, df, der2);
     }
     der2 = sqrt(der2) / fabs(hh);
     const double der12 = fmax(fabs(der2), sqrt(dnf));
@@ -421,7 +432,7 @@ struct ErkTraj {
 // Table-driven linear combination: acc = sum_j COEF[j] * k[SLOT[j]][i], left to right.
 #define IVPB_LINCOMB(acc, LEN, SLOT, COEF, KARR, i)                               \
   double acc = (COEF)[0] * (KARR)[(SLOT)[0]][i];                                  \
-  _Pragma("unroll") for (int j_ = 1; j_ < 9; ++j_) if (j_ < (LEN)) acc += (COEF)[j_] * (KARR)[(SLOT)[j_]][i];
+  _Pragma("unroll") for (int j_ = 1; j_ < 9; ++j_) if (j_ < (LEN)) acc = IVPB_MA((COEF)[j_], (KARR)[(SLOT)[j_]][i], acc);
 
 template <class Prob, int METHOD, int FEAT>
 __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a) {
@@ -438,7 +449,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     const double h_max = hmax_of(a);
     if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
     if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
-    if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+    if ((IVPB_MA(1.01, h, x) - xend) * posneg > 0.0) { h = xend - x; last = true; }
     nstep += 1;
 
     double k[10][N], y1[N];
@@ -449,13 +460,13 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (STG_LEN[s] == 1) {
-          y1[i] = y[i] + h * D853_STG_COEF[s][0] * k[STG_SLOT[s][0]][i];   // (h*a21)*k1, dop853.rs:296
+          y1[i] = IVPB_MA(h * D853_STG_COEF[s][0], k[STG_SLOT[s][0]][i], y[i]);   // (h*a21)*k1, dop853.rs:296
         } else {
           IVPB_LINCOMB(acc, STG_LEN[s], STG_SLOT[s], D853_STG_COEF[s], k, i)
-          y1[i] = y[i] + h * acc;
+          y1[i] = IVPB_MA(h, acc, y[i]);
         }
       }
-      const double ts = (s == 10) ? (x + h) : (x + D853_STG_C[s] * h);
+      const double ts = (s == 10) ? (x + h) : IVPB_MA(D853_STG_C[s], h, x);
       Prob::ode(ts, y1, p, k[STG_OUT[s]]);
     }
     const double xph = x + h;
@@ -465,17 +476,18 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     for (int i = 0; i < N; ++i) {
       IVPB_LINCOMB(acc, LIN_LEN[0], LIN_SLOT[0], D853_LIN_COEF[0], k, i)
       k[3][i] = acc;
-      k[4][i] = y[i] + h * acc;
+      k[4][i] = IVPB_MA(h, acc, y[i]);
     }
     double err = 0.0, err2 = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #ifdef IVPB_STRICT
-      const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(k[4][i]));
+      const double sk = IVPB_MA(rt(a, i), fmax(fabs(y[i]), fabs(k[4][i])), at(a, i));
 #else
-      const double sk = at(a, i) + rt(a, i) * fm::maxsel(fabs(y[i]), fabs(k[4][i]));
+      const double sk = IVPB_MA(rt(a, i), fm::maxsel(fabs(y[i]), fabs(k[4][i])), at(a, i));
 #endif
-      const double erri = k[3][i] - D853_BHH[0] * k[0][i] - D853_BHH[1] * k[8][i] - D853_BHH[2] * k[2][i];
+      // k4 - bh1 k1 - bh2 k9 - bh3 k3 (a - b*c == (-b)*c + a exactly)
+      const double erri = IVPB_MA(-D853_BHH[2], k[2][i], IVPB_MA(-D853_BHH[1], k[8][i], IVPB_MA(-D853_BHH[0], k[0][i], k[3][i])));
       IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], D853_LIN_COEF[1], k, i)
 #ifdef IVPB_STRICT
       const double q2 = erri / sk, q1 = e8 / sk;         // dop853.rs:412,423
@@ -483,10 +495,10 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       const double rsk = fm::rcp(sk);                      // one reciprocal shared by both norms
       const double q2 = erri * rsk, q1 = e8 * rsk;
 #endif
-      err2 += q2 * q2;
-      err += q1 * q1;
+      err2 = IVPB_MA(q2, q2, err2);
+      err = IVPB_MA(q1, q1, err);
     }
-    double deno = err + 0.01 * err2;
+    double deno = IVPB_MA(0.01, err2, err);
     if (deno <= 0.0) deno = 1.0;
 #ifdef IVPB_STRICT
     err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
@@ -515,7 +527,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double d1 = k[3][i] - k[2][i], d2 = k[4][i] - y1[i];
-          stnum += d1 * d1; stden += d2 * d2;
+          stnum = IVPB_MA(d1, d1, stnum); stden = IVPB_MA(d2, d2, stden);
         }
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 6.1) {
@@ -536,9 +548,9 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
           cont[0][i] = y[i];
           const double ydiff = k[4][i] - y[i];
           cont[1][i] = ydiff;
-          const double bspl = h * k[0][i] - ydiff;
+          const double bspl = IVPB_MA(h, k[0][i], -ydiff);
           cont[2][i] = bspl;
-          cont[3][i] = ydiff - h * k[3][i] - bspl;
+          cont[3][i] = IVPB_MA(-h, k[3][i], ydiff) - bspl;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             IVPB_LINCOMB(acc, DF_LEN[r], DF_SLOT[r], D853_DF_COEF[r], k, i)
@@ -550,9 +562,9 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             IVPB_LINCOMB(acc, DSTG_LEN[s], DSTG_SLOT[s], D853_DSTG_COEF[s], k, i)
-            y1[i] = y[i] + h * acc;
+            y1[i] = IVPB_MA(h, acc, y[i]);
           }
-          Prob::ode(x + D853_DSTG_C[s] * h, y1, p, k[DSTG_OUT[s]]);
+          Prob::ode(IVPB_MA(D853_DSTG_C[s], h, x), y1, p, k[DSTG_OUT[s]]);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -560,7 +572,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
           for (int r = 0; r < 4; ++r) {
             double acc = cont[4 + r][i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc += D853_DS_COEF[r][j] * k[DS_SLOT[r][j]][i];
+            for (int j = 0; j < 4; ++j) acc = IVPB_MA(D853_DS_COEF[r][j], k[DS_SLOT[r][j]][i], acc);
             cont[4 + r][i] = h * acc;
           }
         }
@@ -599,7 +611,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     const double h_max = hmax_of(a);
     if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
     if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
-    if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+    if ((IVPB_MA(1.01, h, x) - xend) * posneg > 0.0) { h = xend - x; last = true; }
     nstep += 1;
 
     double k[6][N], y1[N];
@@ -611,15 +623,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (S_LEN[s] == 1) {
-          y1[i] = y[i] + h * D5_S_COEF[s][0] * k[S_SLOT[s][0]][i];
+          y1[i] = IVPB_MA(h * D5_S_COEF[s][0], k[S_SLOT[s][0]][i], y[i]);
         } else {
           double acc = D5_S_COEF[s][0] * k[S_SLOT[s][0]][i];
 #pragma unroll
-          for (int j = 1; j < 5; ++j) if (j < S_LEN[s]) acc += D5_S_COEF[s][j] * k[S_SLOT[s][j]][i];
-          y1[i] = y[i] + h * acc;
+          for (int j = 1; j < 5; ++j) if (j < S_LEN[s]) acc = IVPB_MA(D5_S_COEF[s][j], k[S_SLOT[s][j]][i], acc);
+          y1[i] = IVPB_MA(h, acc, y[i]);
         }
       }
-      const double ts = (s >= 4) ? xph : (x + D5_S_C[s] * h);
+      const double ts = (s >= 4) ? xph : IVPB_MA(D5_S_C[s], h, x);
       Prob::ode(ts, y1, p, k[S_OUT[s]]);
     }
     nfev += 6;
@@ -629,7 +641,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       for (int i = 0; i < N; ++i) {
         double acc = D5_D_COEF[0] * k[ED_SLOT[0]][i];
 #pragma unroll
-        for (int j = 1; j < 6; ++j) acc += D5_D_COEF[j] * k[ED_SLOT[j]][i];
+        for (int j = 1; j < 6; ++j) acc = IVPB_MA(D5_D_COEF[j], k[ED_SLOT[j]][i], acc);
         cont[4][i] = h * acc;
       }
     }
@@ -638,15 +650,16 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     for (int i = 0; i < N; ++i) {                                // k4 <- scaled error vector, dopri5.rs:337-340
       double acc = D5_E_COEF[0] * k[ED_SLOT[0]][i];
 #pragma unroll
-      for (int j = 1; j < 6; ++j) acc += D5_E_COEF[j] * k[ED_SLOT[j]][i];
+      for (int j = 1; j < 6; ++j) acc = IVPB_MA(D5_E_COEF[j], k[ED_SLOT[j]][i], acc);
       k[3][i] = acc * h;
 #ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
-      err += (k[3][i] / sk) * (k[3][i] / sk);
-#else
-      const double sk = at(a, i) + rt(a, i) * fm::maxsel(fabs(y[i]), fabs(y1[i]));
-      const double q = k[3][i] * fm::rcp(sk);
+      const double q = k[3][i] / sk;
       err += q * q;
+#else
+      const double sk = fma(rt(a, i), fm::maxsel(fabs(y[i]), fabs(y1[i])), at(a, i));
+      const double q = k[3][i] * fm::rcp(sk);
+      err = fma(q, q, err);
 #endif
     }
 #ifdef IVPB_STRICT
@@ -661,7 +674,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     // log(facold) is carried from the previous accepted step (facold holds log(max(err, 1e-4)) in this build).
     const double e2 = err * (1.0 / (double)N);
     const double lerr = 0.5 * log(e2);
-    double hnew = h * fm::minsel(fm::maxsel(safe * exp(beta * facold - expo1 * lerr), 0.2), 10.0);
+    double hnew = h * fm::minsel(fm::maxsel(safe * exp(fma(beta, facold, -(expo1 * lerr))), 0.2), 10.0);
     const bool accept = e2 <= 1.0;
     (void)facc1; (void)facc2;
 #endif
@@ -678,10 +691,12 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double d1 = k[1][i] - k[5][i];
-          const double ysti = y[i] + h * (D5_S_COEF[4][0] * k[0][i] + D5_S_COEF[4][1] * k[1][i] + D5_S_COEF[4][2] * k[2][i] +
-                                          D5_S_COEF[4][3] * k[3][i] + D5_S_COEF[4][4] * k[4][i]);
+          double sacc = D5_S_COEF[4][0] * k[0][i];
+#pragma unroll
+          for (int j = 1; j < 5; ++j) sacc = IVPB_MA(D5_S_COEF[4][j], k[j][i], sacc);
+          const double ysti = IVPB_MA(h, sacc, y[i]);
           const double d2 = y1[i] - ysti;
-          stnum += d1 * d1; stden += d2 * d2;
+          stnum = IVPB_MA(d1, d1, stnum); stden = IVPB_MA(d2, d2, stden);
         }
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 3.25) {
@@ -696,11 +711,11 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double ydiff = y1[i] - y[i];
-          const double bspl = h * k[0][i] - ydiff;
+          const double bspl = IVPB_MA(h, k[0][i], -ydiff);
           cont[0][i] = y[i];
           cont[1][i] = ydiff;
           cont[2][i] = bspl;
-          cont[3][i] = -h * k[1][i] + ydiff - bspl;
+          cont[3][i] = IVPB_MA(-h, k[1][i], ydiff) - bspl;
         }
       }
       const double xold = x;
@@ -740,26 +755,26 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     if ((x + h - xend) * posneg > 0.0) h = xend - x;
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k1[i];
-    Prob::ode(x + 0.5 * h, yt, p, k2);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k1[i], y[i]);
+    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k2);
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.75 * k2[i];
-    Prob::ode(x + 0.75 * h, yt, p, k3);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.75, k2[i], y[i]);
+    Prob::ode(IVPB_MA(0.75, h, x), yt, p, k3);
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * (b1 * k1[i] + b2 * k2[i] + b3 * k3[i]);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h, IVPB_MA(b3, k3[i], IVPB_MA(b2, k2[i], b1 * k1[i])), y[i]);
     Prob::ode(x + h, yt, p, k4);
     nfev += 3;
     double err = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double ye = h * (e1 * k1[i] + e2 * k2[i] + e3 * k3[i] + e4 * k4[i]);
-      const double tol = at(a, i) + rt(a, i) * fmax(fabs(yt[i]), fabs(y[i]));
+      const double ye = h * IVPB_MA(e4, k4[i], IVPB_MA(e3, k3[i], IVPB_MA(e2, k2[i], e1 * k1[i])));
+      const double tol = IVPB_MA(rt(a, i), fmax(fabs(yt[i]), fabs(y[i])), at(a, i));
 #ifdef IVPB_STRICT
       const double q = ye / tol;
 #else
       const double q = ye * fm::rcp(tol);
 #endif
-      err += q * q;
+      err = IVPB_MA(q, q, err);
     }
 #ifdef IVPB_STRICT
     err = sqrt(err / (double)N);
@@ -780,8 +795,8 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         if constexpr (DENSE) {
           cont[0][i] = y[i];
           cont[1][i] = k1[i];
-          cont[2][i] = d21 * k1[i] + d22 * k2[i] + d23 * k3[i] + d24 * k4[i];
-          cont[3][i] = d31 * k1[i] + d32 * k2[i] + d33 * k3[i] + d34 * k4[i];
+          cont[2][i] = IVPB_MA(d24, k4[i], IVPB_MA(d23, k3[i], IVPB_MA(d22, k2[i], d21 * k1[i])));
+          cont[3][i] = IVPB_MA(d34, k4[i], IVPB_MA(d33, k3[i], IVPB_MA(d32, k2[i], d31 * k1[i])));
         }
         y[i] = yt[i];
       }
@@ -805,24 +820,24 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
   } else {
     // ---- RK4: reference src/methods/rk4.rs:141-222 ----
     if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
-    const bool lst = (x + 1.01 * h - xend) * signum(h) > 0.0;
+    const bool lst = (IVPB_MA(1.01, h, x) - xend) * signum(h) > 0.0;
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k1[i];
-    Prob::ode(x + 0.5 * h, yt, p, k2);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k1[i], y[i]);
+    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k2);
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 0.5 * k2[i];
-    Prob::ode(x + 0.5 * h, yt, p, k3);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k2[i], y[i]);
+    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k3);
 #pragma unroll
-    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * 1.0 * k3[i];
-    Prob::ode(x + 1.0 * h, yt, p, k4);
+    for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 1.0, k3[i], y[i]);
+    Prob::ode(IVPB_MA(1.0, h, x), yt, p, k4);
     const double xold = x;
     double cont[NC][N];
     x += h;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       if constexpr (DENSE) { cont[0][i] = y[i]; cont[1][i] = k4[i]; }
-      y[i] += h * ((1.0 / 6.0) * k1[i] + (1.0 / 3.0) * k2[i] + (1.0 / 3.0) * k3[i] + (1.0 / 6.0) * k4[i]);
+      y[i] = IVPB_MA(h, IVPB_MA(1.0 / 6.0, k4[i], IVPB_MA(1.0 / 3.0, k3[i], IVPB_MA(1.0 / 3.0, k2[i], (1.0 / 6.0) * k1[i]))), y[i]);
     }
     Prob::ode(x, y, p, k1);
     nfev += 4;
@@ -849,41 +864,38 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 template <class Prob, int METHOD, int FEAT>
 __device__ __forceinline__ void erk_body(const KArgs& a) {
   ErkTraj<Prob, METHOD, FEAT> T;
-  if (a.static_sched) {
-    const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.N) return;
-    if (!T.init(a, idx)) {
-      while (!T.step(a)) {}
-    }
-    T.finish(a);
-    return;
-  }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
   for (;;) {
-    // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp)
+    // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp).
+    // The static schedule is the same loop with a "queue" that hands every thread exactly its own index, so
+    // both schedules execute one and the same copy of the step code (bit-identical results, half the code).
     const unsigned need = __ballot_sync(FULL, !active);
     if (need && !exhausted) {
-      const int leader = __ffs(need) - 1;
-      u64 base = 0;
-      if (lane == leader) base = atomicAdd(a.queue, (u64)__popc(need));
-      base = __shfl_sync(FULL, base, leader);
-      if (!active) {
-        const i64 idx = (i64)base + __popc(need & ((1u << lane) - 1u));
-        if (idx < a.N) {
-          active = true;
-          if (T.init(a, idx)) { T.finish(a); active = false; }
-        }
+      i64 idx;
+      if (a.static_sched) {
+        idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        exhausted = true;
+      } else {
+        const int leader = __ffs(need) - 1;
+        u64 base = 0;
+        if (lane == leader) base = atomicAdd(a.queue, (u64)__popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        idx = (i64)base + __popc(need & ((1u << lane) - 1u));
+        if ((i64)base + __popc(need) >= a.N) exhausted = true;
       }
-      if ((i64)base + __popc(need) >= a.N) exhausted = true;
+      if (!active && idx < a.N) {
+        active = true;
+        if (T.init(a, idx)) { T.finish(a); active = false; }
+      }
     }
     if (__ballot_sync(FULL, active) == 0u) {
       if (exhausted) break;
       continue;
     }
     // ---- hot loop: every lane that owns a trajectory attempts steps until one of them finishes.  Nothing of
-    // the refill logic is live in here, so the loop is as tight as the static schedule's.
+    // the refill logic is live in here.
     bool done = false;
     do {
       if (active) done = T.step(a);

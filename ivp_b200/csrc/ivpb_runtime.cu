@@ -279,7 +279,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
 
   if (pi.user) {
-    int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, &a, sizeof(a), stream);
+    int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, strict, &a, sizeof(a), N,
+                               a.static_sched, stream);
     if (rc) return rc;
     ctx->launches += 1;
     return 0;

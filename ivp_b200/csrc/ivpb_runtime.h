@@ -22,7 +22,7 @@ struct ivpb_user_problem {
   void* impl = nullptr;   // NVRTC module cache, owned by ivpb_nvrtc.cpp
 };
 
-int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms, int method, int feat,
-                      const void* kargs, size_t kargs_bytes, cudaStream_t stream);
+int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms, int method, int feat, int strict,
+                      const void* kargs, size_t kargs_bytes, long long N, int static_sched, cudaStream_t stream);
 void ivpb_nvrtc_release(ivpb_user_problem& up);
 void ivpb_set_error(ivpb_ctx* ctx, const std::string& msg);

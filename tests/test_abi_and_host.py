@@ -118,3 +118,39 @@ def test_batch_solution_views():
     assert s.status == Status.UserInterrupt and s.truncated and len(s.t) == 2 and len(s.t_events[0]) == 1
     assert (s.nfev, s.njev, s.nlu, s.nstep, s.naccpt, s.nrejct) == (6, 7, 8, 9, 10, 11)
     assert not b.solution(0).truncated and len(b.solutions()) == 3
+
+
+USER_VDP = r"""
+// user problem in CUDA C: the device form of `impl IVP for VanDerPol` (reference src/ivp.rs:27-53)
+__device__ void ivp_ode(double t, const double* y, const double* p, double* dydt) {
+  dydt[0] = y[1];
+  dydt[1] = p[0] * (1.0 - y[0] * y[0]) * y[1] - y[0];
+}
+__device__ void ivp_events(double t, const double* y, const double* p, double* g) { g[0] = y[0]; }
+"""
+
+
+def _nvrtc_compile(src, n, p, nev, has_jac, method, feat, strict=0):
+    lib = api.load_library()
+    lib.ivpb_debug_nvrtc_compile.restype = ctypes.c_longlong
+    log = ctypes.create_string_buffer(1 << 16)
+    r = lib.ivpb_debug_nvrtc_compile(src.encode(), n, p, nev, has_jac, method, feat, strict, log, 1 << 16)
+    return r, log.value.decode()
+
+
+def test_nvrtc_compiles_user_problem_for_sm100a_without_gpu():
+    """The NVRTC half of the user-problem path needs no driver: solver headers (embedded in libivpb.so) +
+    user CUDA C -> sm_100a cubin, for every explicit method and feature set, fast and strict."""
+    for method in (0, 1, 2, 3):
+        for feat, nev in ((0, 0), (1, 0), (3, 1)):
+            for strict in (0, 1):
+                size, log = _nvrtc_compile(USER_VDP, 2, 1, nev, 0, method, feat, strict)
+                assert size > 10000, log
+
+
+def test_nvrtc_reports_compile_errors():
+    size, log = _nvrtc_compile("__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = undefined_symbol; }",
+                               1, 0, 0, 0, 2, 0)
+    assert size == -3 and "undefined_symbol" in log          # IVPB_ERR_NVRTC
+    size, log = _nvrtc_compile("// no ivp_ode at all", 1, 0, 0, 0, 2, 0)
+    assert size == -3 and "ivp_ode" in log
