@@ -97,6 +97,7 @@ int run_batch(const ivpb_options* o, int64_t N, double t0, double tf, const doub
         P prob;
         prob.p = (p > 0 && params) ? params + (int64_t)p * i : nullptr;
         prob.ev_cfg = evc.empty() ? nullptr : evc.data();
+        prob.jac_mode = o->jac_mode;
         std::vector<double> yy(y0 + (int64_t)n * i, y0 + (int64_t)n * (i + 1));
         try {
           Solution S = solve_ivp(prob, t0, tf, yy, O);
@@ -124,7 +125,7 @@ int dense_eval(const ivpb_options* o, double t0, double tf, const double* y0, co
   constexpr int n = P::N;
   Options O = make_options(o, n);
   O.dense_output = true;
-  P prob; prob.p = params;
+  P prob; prob.p = params; prob.jac_mode = o->jac_mode;
   std::vector<double> yy(y0, y0 + n);
   try {
     Solution S = solve_ivp(prob, t0, tf, yy, O);

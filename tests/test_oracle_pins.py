@@ -204,3 +204,96 @@ def test_vdp_against_scipy(oracle, method, scipy_name):
 def test_abi_struct_sizes():
     import ctypes
     assert ctypes.sizeof(_abi.IvpbOutputs) == 11 * 8
+
+
+# ----------------------------------------------------------------------------------------------
+# Implicit path (RADAU, BDF): reference tests/accuracy.rs, tests/ivp.rs, tests/backward_and_bounds.rs,
+# tests/test_ivp.py (test_integration, test_integration_stiff), tests/test_stiff.py, examples/van_der_pol.rs
+IMPLICIT = [Method.RADAU, Method.BDF]
+
+
+@pytest.mark.parametrize("method", IMPLICIT)
+def test_implicit_harmonic_accuracy_and_t_eval(oracle, method):
+    s = one(oracle, P_SHO, 0.0, 2.0 * math.pi, [1.0, 0.0], None, Options(method=method, rtol=1e-9, atol=1e-9, max_out=BIG))
+    assert s.status == Status.Success and abs(s.y[-1][0] - 1.0) < 1e-5 and abs(s.y[-1][1]) < 1e-5   # accuracy.rs:17-47
+    te = [i / 10.0 for i in range(11)]
+    s = one(oracle, P_SHO, 0.0, 1.0, [1.0, 0.0], None, Options(method=method, rtol=1e-9, atol=1e-9, t_eval=te))
+    assert all(np.any(np.abs(s.t - t) <= 1e-9) for t in te)                                        # accuracy.rs:49-76
+    np.testing.assert_allclose(s.y[:, 0], np.cos(s.t), atol=1e-5)
+
+
+def test_radau_zero_rhs_and_controls(oracle):
+    te = [10.0 * i / 20.0 for i in range(21)]                                                      # ivp.rs:20-46 (BDF excluded there)
+    s = one(oracle, P_ZERO3, 0.0, 10.0, [1.0, 1.0, 1.0], None, Options(method=Method.RADAU, rtol=1e-9, atol=1e-12, t_eval=te))
+    assert list(s.t) == te and np.all(np.abs(s.y - 1.0) <= 1e-12)
+    for m in IMPLICIT:                                                                             # ivp.rs:48-74 max_step
+        s = one(oracle, P_SHO, 0.0, 3.0, [1.0, 0.0], None, Options(method=m, rtol=1e-6, atol=1e-9, max_step=0.05, max_out=BIG))
+        assert np.all(np.abs(np.diff(s.t)) <= 0.05 + 1e-12)
+    s = one(oracle, P_SHO, 0.0, 3.0, [1.0, 0.0], None, Options(method=Method.RADAU, rtol=1e-3, atol=1e-6, first_step=0.1, max_out=BIG))
+    assert abs(abs(s.t[1] - s.t[0]) - 0.1) <= 1e-6                                                 # ivp.rs:76-103
+
+
+@pytest.mark.parametrize("method", IMPLICIT)
+def test_implicit_backward_and_dense(oracle, method):
+    opts = Options(method=method, rtol=1e-9, atol=1e-9, dense_output=True)
+    x0 = 2.0 * math.pi
+    _, _, span = oracle.dense_eval(P_SHO, x0, 0.0, [1.0, 0.0], None, opts, [0.5 * x0])              # backward_and_bounds.rs:6-31
+    assert span is not None and span[0] > span[1]
+    mid = 0.5 * (span[0] + span[1])
+    ys, ok, _ = oracle.dense_eval(P_SHO, x0, 0.0, [1.0, 0.0], None, opts, [mid])
+    assert ok[0] and abs(ys[0][0] - math.cos(mid)) < 1e-6 and abs(ys[0][1] + math.sin(mid)) < 1e-6
+    if method == Method.RADAU:                                                                     # ivp.rs:106-136
+        o2 = Options(method=method, rtol=1e-8, atol=1e-10, dense_output=True, max_out=BIG)
+        s = one(oracle, P_SHO, 0.0, 2.0, [1.0, 0.0], None, o2)
+        ys, ok, _ = oracle.dense_eval(P_SHO, 0.0, 2.0, [1.0, 0.0], None, o2, s.t)
+        assert ok.all() and np.max(np.abs(ys - s.y)) <= 1e-8
+
+
+@pytest.mark.parametrize("method", IMPLICIT)
+@pytest.mark.parametrize("span", [(5.0, 9.0), (5.0, 1.0)])
+@pytest.mark.parametrize("jac_mode", [0, 1])
+def test_implicit_integration_rational(oracle, method, span, jac_mode):
+    # tests/test_ivp.py:172-241 with jac in {None, jac_rational}
+    rtol, atol = 1e-3, 1e-6
+    opts = Options(method=method, rtol=rtol, atol=atol, dense_output=True, max_out=BIG, jac_mode=jac_mode)
+    s = one(oracle, P_RATIONAL, span[0], span[1], [1 / 3, 2 / 9], None, opts)
+    assert s.t[0] == span[0] and s.status == Status.Success
+    assert 0 < s.njev and 0 < s.nlu
+    assert np.all(compute_error(s.y, sol_rational(s.t), rtol, atol) < 5)
+    tc = np.linspace(*span)
+    yc, ok, _ = oracle.dense_eval(P_RATIONAL, span[0], span[1], [1 / 3, 2 / 9], None, opts, tc)
+    assert ok.all() and np.all(compute_error(yc, sol_rational(tc), rtol, atol) < 5)
+
+
+def test_stiff_robertson_counts(oracle):
+    # tests/test_stiff.py:97-143 / tests/test_ivp.py:319-342
+    y0, par = [1e4, 0.0, 0.0], [0.04, 1e4, 3e7]
+    s = one(oracle, P_ROBER, 0.0, 1e8, y0, par, Options(method=Method.RADAU, rtol=1e-6, atol=1e-6))
+    assert s.status == Status.Success and s.nfev < 5000 and s.njev < 200
+    b = one(oracle, P_ROBER, 0.0, 1e8, y0, par, Options(method=Method.BDF, rtol=1e-6, atol=1e-6))
+    assert b.status == Status.Success and b.nfev < 5000 and b.njev < 600
+    # mass conservation and agreement between the two methods
+    assert abs(s.y[-1].sum() - 1e4) < 1e-3 * 1e4 and np.allclose(s.y[-1], b.y[-1], rtol=1e-3, atol=1e-6)
+    si = pytest.importorskip("scipy.integrate")
+    ref = si.solve_ivp(lambda t, u: [-0.04 * u[0] + 1e4 * u[1] * u[2], 0.04 * u[0] - 1e4 * u[1] * u[2] - 3e7 * u[1] ** 2,
+                                     3e7 * u[1] ** 2], (0, 1e8), y0, method="Radau", rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(s.y[-1], ref.y[:, -1], rtol=1e-3, atol=1e-6)
+
+
+def test_vdp_eps_example_bdf(oracle):
+    # reference examples/van_der_pol.rs:17-29 exactly as shipped
+    te = [i * 0.1 for i in range(21)]
+    s = one(oracle, P_VDP_EPS, 0.0, 2.0, [2.0, 0.0], [1e-3], Options(method=Method.BDF, rtol=1e-6, atol=1e-8, t_eval=te))
+    assert s.status == Status.Success and len(s.t) == 21
+    si = pytest.importorskip("scipy.integrate")
+    ref = si.solve_ivp(lambda t, y: [y[1], ((1 - y[0] ** 2) * y[1] - y[0]) / 1e-3], (0, 2), [2.0, 0.0], method="Radau",
+                       rtol=1e-10, atol=1e-10, t_eval=te)
+    np.testing.assert_allclose(s.y, ref.y.T, rtol=2e-4, atol=2e-4)
+
+
+def test_lu_kats(oracle):
+    # src/matrix/lu.rs:304-404, src/matrix/linear.rs:219-254: exercised through a 1x1 / 2x2 linear problem:
+    # decay (n = 1) with Radau/BDF uses the n == 1 branches of lu_decomp / lin_solve / lin_solve_complex
+    for m in IMPLICIT:
+        s = one(oracle, P_DECAY, 0.0, 10.0, [10.0], [0.5], Options(method=m, rtol=1e-8, atol=1e-10))
+        assert s.status == Status.Success and abs(s.y[-1][0] - 10.0 * math.exp(-5.0)) < 1e-5
