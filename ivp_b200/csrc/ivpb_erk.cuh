@@ -52,6 +52,8 @@ template <> struct MethodTraits<M_RK23>   { static constexpr int NC = 4, IORD = 
 template <> struct MethodTraits<M_DOPRI5> { static constexpr int NC = 5, IORD = 5; };
 template <> struct MethodTraits<M_DOP853> { static constexpr int NC = 8, IORD = 8; };
 template <> struct MethodTraits<M_RK4>    { static constexpr int NC = 4, IORD = 4; };
+template <> struct MethodTraits<M_RADAU>  { static constexpr int NC = 4, IORD = 5; };   // cont: radau.rs:697-705
+template <> struct MethodTraits<M_BDF>    { static constexpr int NC = 7, IORD = 1; };   // D0..D5 + order marker
 
 // ---------------------------------------------------------------------------------------------
 // Step interpolants (Method::interpolate).  cont is coefficient-major: c[coef][state].
@@ -75,6 +77,32 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
 #pragma unroll
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(h, IVPB_MA(c[3][i], x3, IVPB_MA(c[2][i], x2, c[1][i] * xc)), c[0][i]);
+  } else if constexpr (METHOD == M_RADAU) {    // radau.rs:798-809
+    const double s = (xi - (xold + h)) / h;
+    const double C1M1 = -0.8449489742783178, C2M1 = -0.3550510257216822;
+#pragma unroll
+    for (int i = 0; i < N; ++i) yi[i] = c[0][i] + s * (c[1][i] + (s - C2M1) * (c[2][i] + (s - C1M1) * c[3][i]));
+  } else if constexpr (METHOD == M_BDF) {      // bdf.rs:618-656 (device cont is coefficient-major; c[6][0] = order)
+    if (h == 0.0) return;
+    const int order = (int)fmin(fmax(round(c[6][0]), 1.0), 5.0);
+    const double x_new = xold + h;
+    double pk[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (k < order) {
+        const double denom = h * ((double)k + 1.0);
+        const double t_shift = x_new - h * (double)k;
+        const double xf = (xi - t_shift) / denom;
+        pk[k] = (k == 0) ? xf : pk[k > 0 ? k - 1 : 0] * xf;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double sum = c[0][i];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) if (k < order) sum += c[1 + k][i] * pk[k];
+      yi[i] = sum;
+    }
   } else {                                      // rk4.rs:229-244 (cubic Hermite, cont = [y_old, k4 stage, f_new, y_new])
     const double t = (xi - xold) / h, t2 = t * t, t3 = t2 * t;
     const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
@@ -83,6 +111,42 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(h11 * h, c[2][i], IVPB_MA(h01, c[3][i], IVPB_MA(h10 * h, c[1][i], h00 * c[0][i])));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hinit -- reference src/methods/mod.rs:217-281 (initial step guess; one extra RHS call; the final
+// min(|h|, 100|h|, h1, hmax) keeps the reference's extra |h| term, mod.rs:279)
+template <class Prob, int IORD>
+__device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const double* y, const double* f0,
+                                            const double* p, double posneg, double hmax) {
+  constexpr int N = Prob::N;
+  double dnf = 0.0, dny = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double sk = IVPB_MA(a.rtol[i], fabs(y[i]), a.atol[i]);
+    const double qf = f0[i] / sk, qy = y[i] / sk;
+    dnf = IVPB_MA(qf, qf, dnf);
+    dny = IVPB_MA(qy, qy, dny);
+  }
+  double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
+  if (hh > fabs(hmax)) hh = fabs(hmax);
+  hh = fabs(hh) * signum(posneg);
+  double y1[N], f1[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y1[i] = IVPB_MA(hh, f0[i], y[i]);
+  Prob::ode(x + hh, y1, p, f1);
+  double der2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double sk = IVPB_MA(a.rtol[i], fabs(y[i]), a.atol[i]);
+    const double df = (f1[i] - f0[i]) / sk;
+    der2 = IVPB_MA(df, df, der2);
+  }
+  der2 = sqrt(der2) / fabs(hh);
+  const double der12 = fmax(fabs(der2), sqrt(dnf));
+  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : pow(0.01 / der12, 1.0 / (double)IORD);
+  const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));
+  return fabs(hf) * signum(posneg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -323,36 +387,8 @@ struct ErkTraj {
   __device__ __forceinline__ double rt(const KArgs& a, int i) const { return a.rtol[i]; }
   __device__ __forceinline__ double at(const KArgs& a, int i) const { return a.atol[i]; }
 
-  // hinit -- reference src/methods/mod.rs:217-281 (f0 == k1)
   __device__ __forceinline__ double hinit(const KArgs& a, double posneg, double hmax) {
-    double dnf = 0.0, dny = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const double sk = IVPB_MA(rt(a, i), fabs(y[i]), at(a, i));
-      const double qf = k1[i] / sk, qy = y[i] / sk;
-      dnf = IVPB_MA(qf, qf, dnf);
-      dny = IVPB_MA(qy, qy, dny);
-    }
-    double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
-    if (hh > fabs(hmax)) hh = fabs(hmax);
-    hh = fabs(hh) * signum(posneg);
-    double y1[N], f1[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) y1[i] = IVPB_MA(hh, k1[i], y[i]);
-    Prob::ode(x + hh, y1, p, f1);
-    double der2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const double sk = IVPB_MA(rt(a, i), fabs(y[i]), at(a, i));
-      const double df = (f1[i] - k1[i]) / sk;
-      der2 = IVPB_MA(df, df, der2);
-    }
-    der2 = sqrt(der2) / fabs(hh);
-    const double der12 = fmax(fabs(der2), sqrt(dnf));
-    const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3)
-                                         : pow(0.01 / der12, 1.0 / (double)MethodTraits<METHOD>::IORD);
-    const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));   // mod.rs:279 quirk kept
-    return fabs(hf) * signum(posneg);
+    return hinit_dev<Prob, MethodTraits<METHOD>::IORD>(a, x, y, k1, p, posneg, hmax);
   }
 
   __device__ __forceinline__ double hmax_of(const KArgs& a) const {
@@ -861,9 +897,10 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #define IVPB_BLOCK 128
 #endif
 
-template <class Prob, int METHOD, int FEAT>
-__device__ __forceinline__ void erk_body(const KArgs& a) {
-  ErkTraj<Prob, METHOD, FEAT> T;
+// Generic persistent scheduler: Traj provides init(a, idx) -> done, step(a) -> done, finish(a).
+template <class Traj>
+__device__ __forceinline__ void run_schedule(const KArgs& a) {
+  Traj T;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
@@ -902,6 +939,11 @@ __device__ __forceinline__ void erk_body(const KArgs& a) {
     } while (!__any_sync(FULL, done));
     if (done) { T.finish(a); active = false; }
   }
+}
+
+template <class Prob, int METHOD, int FEAT>
+__device__ __forceinline__ void erk_body(const KArgs& a) {
+  run_schedule<ErkTraj<Prob, METHOD, FEAT>>(a);
 }
 
 }  // namespace ivpb
