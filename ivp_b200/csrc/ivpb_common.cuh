@@ -37,6 +37,7 @@ struct KArgs {
   const double* t_eval;  // device copy, [n_t_eval]
   int n_t_eval, out_cap;
   int max_events, jac_mode;
+  double newton_tol;     // implicit methods: Newton stopping tolerance (radau.rs:198-205, bdf.rs:174-184), host-computed
   int ev_dir[MAX_EVENTS_FN];
   i64 ev_term[MAX_EVENTS_FN];   // < 0: not terminal
   // outputs (any may be null)
@@ -52,6 +53,10 @@ struct KArgs {
   double* ev_t;
   double* ev_y;
 };
+
+// std::conditional without <type_traits> (NVRTC has no standard headers)
+template <bool B, class T, class F> struct std_conditional { typedef T type; };
+template <class T, class F> struct std_conditional<false, T, F> { typedef F type; };
 
 __device__ __forceinline__ double signum(double x) {   // f64::signum: +-1 by sign bit, NaN -> NaN
   return (x != x) ? x : copysign(1.0, x);

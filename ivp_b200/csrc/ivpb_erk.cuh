@@ -17,6 +17,7 @@
 #include "ivpb_common.cuh"
 #include "dop853_tableau.cuh"
 #include "ivpb_fastmath.cuh"
+#include "ivpb_libm_pow.cuh"
 
 namespace ivpb {
 
@@ -144,7 +145,7 @@ __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const doub
   }
   der2 = sqrt(der2) / fabs(hh);
   const double der12 = fmax(fabs(der2), sqrt(dnf));
-  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : pow(0.01 / der12, 1.0 / (double)IORD);
+  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(0.01 / der12, 1.0 / (double)IORD);
   const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));
   return fabs(hf) * signum(posneg);
 }
@@ -192,9 +193,11 @@ struct SolOutDev {
   }
 
   // Returns true for ControlFlag::Interrupt; then (tev, yev) hold the terminal event point.
-  // `first` marks the initial callback (interpolant == None, xold == x).
+  // `first` marks the initial callback (interpolant == None, xold == x).  (ixold, hstep) are the
+  // StepInterpolant's own xold / h (src/dense.rs:32-97): BDF passes xold = x - h to solout but x_start to the
+  // interpolant (bdf.rs:516-519); every other method passes the same value twice.
   __device__ __forceinline__ bool solout(const KArgs& a, i64 idx, const double* p, bool first, double xold, double x,
-                                         const double* y, const double (&cont)[NC][N], double hstep,
+                                         const double* y, const double (&cont)[NC][N], double hstep, double ixold,
                                          double& tev, double* yev) {
     if constexpr (NEV > 0) {
       double g[NEV];
@@ -246,11 +249,11 @@ struct SolOutDev {
               aa = b; fa = fb;
               if (fabs(d) > tol1) b += d;
               else b += (xm > 0.0 ? tol1 : -tol1);
-              erk_interp<METHOD, N>(b, ey, cont, xold, hstep);
+              erk_interp<METHOD, N>(b, ey, cont, ixold, hstep);
               Prob::events(b, ey, p, gm);
               fb = gm[e];
             }
-            erk_interp<METHOD, N>(b, ey, cont, xold, hstep);
+            erk_interp<METHOD, N>(b, ey, cont, ixold, hstep);
             et = b;
           }
           // append at position ndet (compile-time slot selected by predicate)
@@ -325,14 +328,14 @@ struct SolOutDev {
             while (i < a.n_t_eval) {
               const double te = a.t_eval[i];
               if (!(te <= x + TOL)) break;
-              if (te >= xold - TOL) { erk_interp<METHOD, N>(te, yi, cont, xold, hstep); push(a, idx, te, yi); }
+              if (te >= xold - TOL) { erk_interp<METHOD, N>(te, yi, cont, ixold, hstep); push(a, idx, te, yi); }
               ++i;
             }
           } else {
             while (i < a.n_t_eval) {
               const double te = a.t_eval[i];
               if (!(te >= x - TOL)) break;
-              if (te <= xold + TOL) { erk_interp<METHOD, N>(te, yi, cont, xold, hstep); push(a, idx, te, yi); }
+              if (te <= xold + TOL) { erk_interp<METHOD, N>(te, yi, cont, ixold, hstep); push(a, idx, te, yi); }
               ++i;
             }
           }
@@ -345,7 +348,7 @@ struct SolOutDev {
           if (direction * (x - target) >= -TOL) {
             if (!first) {
               double yi[N];
-              erk_interp<METHOD, N>(target, yi, cont, xold, hstep);
+              erk_interp<METHOD, N>(target, yi, cont, ixold, hstep);
               push(a, idx, target, yi);
               first_output_done = true;
             }
@@ -433,7 +436,7 @@ struct ErkTraj {
 #pragma unroll
         for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
       double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
     }
     return false;
   }
@@ -538,7 +541,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     if (deno <= 0.0) deno = 1.0;
 #ifdef IVPB_STRICT
     err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
-    const double fac11 = pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
+    const double fac11 = ivpb_libm_pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
     // facold^beta == 1 exactly (beta = 0), so fac = fac11 (dop853.rs:434)
     const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
     double hnew = h / fac;
@@ -618,7 +621,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       for (int i = 0; i < N; ++i) { k1[i] = k[3][i]; y[i] = k[4][i]; }
       x = xph;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
           status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
@@ -700,8 +703,8 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     }
 #ifdef IVPB_STRICT
     err = sqrt(err / (double)N);
-    const double fac11 = pow(err, expo1);
-    double fac = fac11 / pow(facold, beta);
+    const double fac11 = ivpb_libm_pow(err, expo1);
+    double fac = fac11 / ivpb_libm_pow(facold, beta);
     fac = fmax(facc2, fmin(facc1, fac / safe));
     double hnew = h / fac;
     const bool accept = err <= 1.0;
@@ -759,7 +762,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       for (int i = 0; i < N; ++i) { k1[i] = k[1][i]; y[i] = y1[i]; }
       x = xph;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
           status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
@@ -814,7 +817,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     }
 #ifdef IVPB_STRICT
     err = sqrt(err / (double)N);
-    const double sfac = safe * pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
+    const double sfac = safe * ivpb_libm_pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
     const bool accept = err <= 1.0;
 #else
     const double errsq = err * (1.0 / (double)N);              // err^2; err^(-1/3) = cbrt(1/sqrt(err^2))
@@ -838,7 +841,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       }
       x += h;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
           status = ST_INTERRUPT; to_event_point(tev, yev); return true;
         }
       }
@@ -883,7 +886,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       for (int i = 0; i < N; ++i) { cont[2][i] = k1[i]; cont[3][i] = y[i]; }
     }
     if constexpr (FEAT != 0) {
-      if (so.solout(a, idx, p, false, xold, x, y, cont, h, tev, yev)) {
+      if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
         status = ST_INTERRUPT; to_event_point(tev, yev); return true;
       }
     }

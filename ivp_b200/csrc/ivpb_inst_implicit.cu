@@ -1,0 +1,20 @@
+// ivpb_inst_implicit.cu -- instantiates the RADAU / BDF kernels of ONE built-in problem (same scheme as
+// ivpb_inst.cu: one object per problem and per floating-point mode, -DIVPB_PROBLEM / -DIVPB_TAG).
+#ifdef IVPB_STRICT
+#define ivpb ivpb_strict
+#endif
+#define IVPB_WITH_IMPLICIT 1
+#include "ivpb_problems.cuh"
+#include "ivpb_kernels.cuh"
+
+#define IVPB_CAT2(a, b) a##b
+#define IVPB_CAT(a, b) IVPB_CAT2(a, b)
+#ifdef IVPB_STRICT
+#define IVPB_SYM(tag) IVPB_CAT(ivpb_lookup_impl_strict_, tag)
+#else
+#define IVPB_SYM(tag) IVPB_CAT(ivpb_lookup_impl_, tag)
+#endif
+
+extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, int* block, int* smem) {
+  return ivpb::implicit_lookup<ivpb::IVPB_PROBLEM>(method, feat, block, smem);
+}

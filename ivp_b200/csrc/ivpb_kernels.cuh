@@ -3,6 +3,9 @@
 // -DIVPB_PROBLEM=<struct> -DIVPB_PROBLEM_TAG=<name>), and by the NVRTC program for user problems.
 #pragma once
 #include "ivpb_erk.cuh"
+#ifdef IVPB_WITH_IMPLICIT
+#include "ivpb_implicit.cuh"
+#endif
 
 namespace ivpb {
 
@@ -37,5 +40,41 @@ __host__ inline const void* erk_lookup(int method, int feat) {
     default: return nullptr;
   }
 }
+
+
+#ifdef IVPB_WITH_IMPLICIT
+// Implicit kernels (ivpb_implicit.cuh): one resident block per SM is assumed for the launch bounds; the
+// runtime asks the occupancy API for the real number.
+template <class Prob, int METHOD, int FEAT>
+__global__ void __launch_bounds__(ImplicitSel<Prob, METHOD, FEAT>::BLK, 1) implicit_kernel(const __grid_constant__ KArgs a) {
+  implicit_body<Prob, METHOD, FEAT>(a);
+}
+
+template <class Prob, int METHOD>
+__host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem) {
+  if constexpr (Prob::N > IMPLICIT_MAX_N) return nullptr;
+  else {
+    if (block) *block = ImplicitSel<Prob, METHOD, 0>::BLK;
+    if (smem) *smem = ImplicitSel<Prob, METHOD, 0>::SMEM_BYTES;
+    switch (feat) {
+      case 0: return (const void*)&implicit_kernel<Prob, METHOD, 0>;
+      case K_OUT: return (const void*)&implicit_kernel<Prob, METHOD, K_OUT>;
+      case K_OUT | K_EVENTS:
+        if constexpr (Prob::NEV > 0) return (const void*)&implicit_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
+        else return nullptr;
+      default: return nullptr;
+    }
+  }
+}
+
+template <class Prob>
+__host__ inline const void* implicit_lookup(int method, int feat, int* block, int* smem) {
+  switch (method) {
+    case M_RADAU: return implicit_lookup_feat<Prob, M_RADAU>(feat, block, smem);
+    case M_BDF: return implicit_lookup_feat<Prob, M_BDF>(feat, block, smem);
+    default: return nullptr;
+  }
+}
+#endif
 
 }  // namespace ivpb

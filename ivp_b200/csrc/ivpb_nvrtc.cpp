@@ -41,6 +41,7 @@ struct Api {
                            void**, void**);
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
   CUresult (*GetErrorStringDrv)(CUresult, const char**);
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
 };
 
 void* open_first(const std::vector<const char*>& names) {
@@ -68,7 +69,7 @@ Api& api() {
     SYM(hc, ModuleLoadData, "cuModuleLoadData") SYM(hc, ModuleUnload, "cuModuleUnload")
     SYM(hc, ModuleGetFunction, "cuModuleGetFunction") SYM(hc, LaunchKernel, "cuLaunchKernel")
     SYM(hc, OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
-    SYM(hc, GetErrorStringDrv, "cuGetErrorString")
+    SYM(hc, GetErrorStringDrv, "cuGetErrorString") SYM(hc, FuncSetAttribute, "cuFuncSetAttribute")
 #undef SYM
     a.ok = true;
   });
@@ -105,9 +106,14 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
     s += "  static __device__ __forceinline__ void jac(double t, const double* y, const double* p, double* J) { ivp_jac(t, y, p, J); }\n";
   }
   s += "};\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(IVPB_BLOCK) ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
-  s += implicit ? "  ivpb::implicit_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n"
-                : "  ivpb::erk_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
+  if (implicit) {
+    s += "extern \"C\" __global__ void __launch_bounds__((ivpb::ImplicitSel<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>::BLK), 1) "
+         "ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
+    s += "  ivpb::implicit_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
+  } else {
+    s += "extern \"C\" __global__ void __launch_bounds__(IVPB_BLOCK) ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
+    s += "  ivpb::erk_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
+  }
   return s;
 }
 
@@ -166,9 +172,10 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   const int key = device * 4096 + method * 64 + feat * 2 + (strict ? 1 : 0);
   auto it = cache->mods.find(key);
   if (it == cache->mods.end()) {
-#ifndef IVPB_HAVE_IMPLICIT_HEADER
-    if (method >= 4) { ivpb_set_error(ctx, "implicit methods are not available for NVRTC problems in this build"); return IVPB_ERR_CONFIG; }
-#endif
+    if (method >= 4 && up.n > 8) {
+      ivpb_set_error(ctx, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
+      return IVPB_ERR_CONFIG;
+    }
     std::vector<char> cubin;
     std::string log;
     if (int rc = compile_cubin(up, method, feat, strict, cubin, log)) { ivpb_set_error(ctx, log); return rc; }
@@ -179,16 +186,26 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
     if (cr != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuModuleGetFunction: " + drv_err(cr)); return IVPB_ERR_CUDA; }
     it = cache->mods.emplace(key, c).first;
   }
-  const int block = 128;
+  // launch shape: explicit kernels 128 threads; implicit kernels follow ivpb::MatSel (ivpb_implicit.cuh)
+  int block = 128;
+  size_t smem = 0;
+  if (method >= 4) {
+    block = up.n <= 6 ? 128 : 64;
+    if (up.n > 3) smem = (size_t)(method == 4 ? 4 : 2) * up.n * up.n * block * 8;
+    if (smem > 0) {
+      CUresult ar = A.FuncSetAttribute(it->second.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+      if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
+    }
+  }
   int occ = 1;
-  A.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, it->second.fn, block, 0);
+  A.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, it->second.fn, block, smem);
   if (occ < 1) occ = 1;
   long long grid = (long long)sms * occ;
   const long long need = (N + block - 1) / block;
   if (static_sched || need < grid) grid = need;
   std::vector<char> copy((const char*)kargs, (const char*)kargs + kargs_bytes);
   void* params[] = {copy.data()};
-  CUresult cr = A.LaunchKernel(it->second.fn, (unsigned)grid, 1, 1, block, 1, 1, 0, (CUstream)stream, params, nullptr);
+  CUresult cr = A.LaunchKernel(it->second.fn, (unsigned)grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)stream, params, nullptr);
   if (cr != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuLaunchKernel: " + drv_err(cr)); return IVPB_ERR_CUDA; }
   return 0;
 }

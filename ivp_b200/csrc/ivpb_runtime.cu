@@ -24,9 +24,12 @@ using ivpb::u64;
 // ------------------------------------------------------------------------------------------------
 // Built-in kernel tables (one lookup function per problem and floating-point mode; ivpb_inst.cu)
 typedef const void* (*lookup_fn)(int method, int feat, ivpb_pinfo* info);
+typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* smem);
 #define DECL(tag)                                                                  \
   extern "C" const void* ivpb_lookup_##tag(int, int, ivpb_pinfo*);                 \
-  extern "C" const void* ivpb_lookup_strict_##tag(int, int, ivpb_pinfo*);
+  extern "C" const void* ivpb_lookup_strict_##tag(int, int, ivpb_pinfo*);          \
+  extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*);             \
+  extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
 DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon)
 #undef DECL
@@ -35,9 +38,12 @@ static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
 #undef ROW
-
-// implicit-method kernels (ivpb_inst_implicit.cu); null until that path is built for a problem
-extern "C" const void* ivpb_lookup_implicit(int problem, int method, int feat, int strict) __attribute__((weak));
+// RADAU / BDF kernels (ivpb_inst_implicit.cu)
+#define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag}
+static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
+    ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
+#undef ROW
 
 namespace {
 
@@ -165,6 +171,26 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
     if (h == 0.0 || sg != posneg || std::isnan(h))
       return fail(ctx, IVPB_ERR_CONFIG, "RK4: step size is zero or its sign does not match tf - t0");
   }
+  if (o->method == IVPB_RADAU && std::fabs(tf - t0) >= 1e-15) {
+    // radau.rs:250-262: the initial step is clamp(h, -hmax, hmax) -- f64::clamp panics for min > max -- and a
+    // zero step is ConfigError::InvalidStepSize; the accepted-step clamp(hmin, hmax) needs hmin <= hmax (:752)
+    const double hmax = o->has_max_step ? o->max_step : std::fabs(tf - t0);
+    const double hmin = o->has_min_step ? o->min_step : 0.0;
+    if (!(hmax >= 0.0)) return fail(ctx, IVPB_ERR_CONFIG, "RADAU: max_step must be non-negative");
+    if (hmin > hmax) return fail(ctx, IVPB_ERR_CONFIG, "RADAU: min_step exceeds max_step");
+    if (o->has_first_step && o->first_step == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "RADAU: first_step is zero");
+    if (hmax == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "RADAU: max_step is zero");
+    for (int i = 0; i < (o->n_rtol == 1 ? 1 : pi.n); ++i)
+      if (!(o->rtol[i] > 0.0)) return fail(ctx, IVPB_ERR_CONFIG, "RADAU: rtol must be positive");
+  }
+  if (o->method == IVPB_BDF && std::fabs(tf - t0) >= 1e-15) {
+    // bdf.rs:113-136 (negative tolerances), :192-197 (zero first step)
+    for (int i = 0; i < (o->n_rtol == 1 ? 1 : pi.n); ++i)
+      if (o->rtol[i] < 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: negative relative tolerance");
+    for (int i = 0; i < (o->n_atol == 1 ? 1 : pi.n); ++i)
+      if (o->atol[i] < 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: negative absolute tolerance");
+    if (o->has_first_step && o->first_step == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: first_step is zero");
+  }
   if (o->jac_mode == 1 && !pi.has_jac && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
   return 0;
@@ -224,6 +250,27 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
   a.out_cap = o->has_t_eval ? o->n_t_eval + 1 : o->max_out;
   a.max_events = o->max_events;
   a.jac_mode = o->jac_mode;
+  if (o->method == IVPB_RADAU) {
+    // Tolerance transform and Newton tolerance of radau.rs:188-205, evaluated here with the host libm (the
+    // same pow the reference calls) so every trajectory sees bit-identical scaled tolerances.
+    const double uround = 2.3e-16;
+    for (int i = 0; i < ivpb::MAX_N; ++i) {
+      const double rt = a.rtol[i], at = a.atol[i];
+      const double quot = at / rt;
+      a.rtol[i] = 0.1 * std::pow(rt, 2.0 / 3.0);
+      a.atol[i] = a.rtol[i] * quot;
+    }
+    const double tolst = a.rtol[0];
+    a.newton_tol = std::fmax(10.0 * uround / tolst, std::fmin(0.03, std::sqrt(tolst)));
+  } else if (o->method == IVPB_BDF) {
+    // bdf.rs:174-184
+    const double eps = std::numeric_limits<double>::epsilon();
+    double rtol_min = std::numeric_limits<double>::infinity();
+    for (int i = 0; i < pi.n; ++i) rtol_min = std::fmin(rtol_min, a.rtol[i]);
+    rtol_min = std::fmax(rtol_min, eps);
+    a.newton_tol = std::fmax(10.0 * eps / rtol_min, std::fmin(std::sqrt(rtol_min), 0.03));
+    if (a.newton_tol <= 0.0) a.newton_tol = 1e-9;
+  }
   for (int e = 0; e < ivpb::MAX_EVENTS_FN; ++e) { a.ev_dir[e] = 0; a.ev_term[e] = -1; }
 }
 
@@ -287,21 +334,23 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   }
 
   const void* kern = nullptr;
+  int kblock = block, ksmem = 0;
   if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
-    if (ivpb_lookup_implicit) kern = ivpb_lookup_implicit(problem, o->method, feat, strict);
-    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods are not built for this problem");
+    kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem);
+    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
+    if (ksmem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
   } else {
     kern = BUILTIN[problem][strict](o->method, feat, nullptr);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
   }
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kblock, ksmem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)dev.sms * occ;
-  const int64_t need = (N + block - 1) / block;
+  const int64_t need = (N + kblock - 1) / kblock;
   if (a.static_sched || need < grid) grid = need;
   void* kargs[] = {&a};
-  CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
+  CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kblock), kargs, ksmem, stream));
   ctx->launches += 1;
   return 0;
 }
@@ -556,6 +605,7 @@ int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops) {
 // Debug hook (not part of include/ivpb.h): evaluates the fast-mode controller helpers of
 // ivpb_fastmath.cuh on the device so tests can bound their error against libm.
 #include "ivpb_fastmath.cuh"
+#include "ivpb_libm_pow.cuh"
 namespace {
 __global__ void fastmath_kernel(const double* x, int n, double* r_rcp, double* r_rsqrt, double* r_rroot8) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,6 +615,25 @@ __global__ void fastmath_kernel(const double* x, int n, double* r_rcp, double* r
   r_rroot8[i] = ivpb::fm::rroot8(x[i]);
 }
 }  // namespace
+namespace {
+__global__ void libm_pow_kernel(const double* x, const double* y, int n, double* r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = ivpb_libm_pow(x[i], y[i]);
+}
+}  // namespace
+// Debug hook: ivpb_libm_pow (ivpb_libm_pow.cuh) evaluated on the device, so tests can compare it bit for bit
+// with the host libm.
+extern "C" int ivpb_debug_pow(const double* x, const double* y, int n, double* r) {
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * 3 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;
+  cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice);
+  libm_pow_kernel<<<(n + 127) / 128, 128>>>(d, d + n, n, d + 2 * (size_t)n);
+  cudaError_t e = cudaMemcpy(r, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
+}
+
 extern "C" int ivpb_debug_fastmath(const double* x, int n, double* r_rcp, double* r_rsqrt, double* r_rroot8) {
   double* d = nullptr;
   if (cudaMalloc((void**)&d, sizeof(double) * 4 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;

@@ -148,9 +148,71 @@ def test_nvrtc_compiles_user_problem_for_sm100a_without_gpu():
                 assert size > 10000, log
 
 
+def test_nvrtc_compiles_implicit_kernels_without_gpu():
+    """RADAU / BDF for user problems: finite-difference Jacobian, and ivp_jac when has_jac; n = 5 uses the
+    shared-memory matrix storage."""
+    jac = USER_VDP + """
+__device__ void ivp_jac(double t, const double* y, const double* p, double* J) {
+  J[0] = 0.0; J[1] = 1.0; J[2] = -2.0 * p[0] * y[0] * y[1] - 1.0; J[3] = p[0] * (1.0 - y[0] * y[0]);
+}
+"""
+    for method in (4, 5):
+        size, log = _nvrtc_compile(jac, 2, 1, 1, 1, method, 3, 1)
+        assert size > 10000, log
+        size, log = _nvrtc_compile(USER_VDP, 2, 1, 0, 0, method, 0, 0)
+        assert size > 10000, log
+    five = "__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { for (int i = 0; i < 5; ++i) d[i] = -y[(i + 1) % 5] * y[i]; }"
+    size, log = _nvrtc_compile(five, 5, 0, 0, 0, 4, 1, 0)
+    assert size > 10000, log
+
+
 def test_nvrtc_reports_compile_errors():
     size, log = _nvrtc_compile("__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = undefined_symbol; }",
                                1, 0, 0, 0, 2, 0)
     assert size == -3 and "undefined_symbol" in log          # IVPB_ERR_NVRTC
     size, log = _nvrtc_compile("// no ivp_ode at all", 1, 0, 0, 0, 2, 0)
     assert size == -3 and "ivp_ode" in log
+
+
+def test_libm_pow_transcription_matches_host_libm(tmp_path):
+    """ivpb_libm_pow.cuh (glibc's pow, operation for operation; compiled here for the host) must be bit-identical
+    to the pow of the libm the oracle -- and a Rust build of the reference -- calls on this machine."""
+    import subprocess
+    src = tmp_path / "powcheck.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include "ivpb_libm_pow.cuh"
+int main() {
+  std::mt19937_64 g(2024);
+  std::uniform_real_distribution<double> U(0, 1);
+  const double ys[] = {0.125, 0.2, 0.17, 0.04, 0.25, 0.8, -1.0 / 3.0, 1.0 / 3.0, 2.0 / 3.0, -0.5, -0.25, -1.0 / 6.0, 4.0, 1.0};
+  long bad = 0;
+  for (long it = 0; it < 6000000; ++it) {
+    double x, y;
+    switch (it % 4) {
+      case 0: x = std::exp(40 * (U(g) - 0.5)); y = ys[g() % (sizeof(ys) / sizeof(ys[0]))]; break;
+      case 1: x = std::exp(20 * (U(g) - 0.5)); y = 8 * (U(g) - 0.5); break;
+      case 2: x = 2 * U(g); y = ys[g() % (sizeof(ys) / sizeof(ys[0]))]; break;
+      default: x = std::exp(600 * (U(g) - 0.5)); y = 2 * (U(g) - 0.5);
+    }
+    const double a = std::pow(x, y), b = ivpb_libm_pow(x, y);
+    if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) ++bad;
+  }
+  const double sx[] = {0.0, -1.0, 1.0, INFINITY, 1e-310, 2.0, 1e300, 1e-300, NAN};
+  const double sy[] = {0.125, 0.5, 2.0, -0.25, 1e-70, INFINITY, 5.0, -5.0, 0.0};
+  for (double x : sx) for (double y : sy) {
+    const double a = std::pow(x, y), b = ivpb_libm_pow(x, y);
+    if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) ++bad;
+  }
+  std::printf("%ld\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "powcheck"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma",
+                           "-I", os.path.join(ROOT, "ivp_b200", "csrc"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout
