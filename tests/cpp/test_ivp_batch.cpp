@@ -1,0 +1,220 @@
+// C++ host-API tests: the reference's own integration tests (tests/ivp.rs, tests/accuracy.rs,
+// tests/backward_and_bounds.rs, examples/*.rs) restated against ivp::solve_ivp / ivp::solve_ivp_batch.
+// Built and run by tests/test_cpp_host_api.py.   usage: test_ivp_batch [--api-only]
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ivp_batch.hpp"
+
+using namespace ivp;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond, ...)                                                                  \
+  do {                                                                                    \
+    ++g_checks;                                                                           \
+    if (!(cond)) { ++g_fail; std::printf("FAIL %s:%d: %s -- ", __FILE__, __LINE__, #cond); std::printf(__VA_ARGS__); std::printf("\n"); } \
+  } while (0)
+
+static std::vector<Method> all_methods() { return {Method::RK23, Method::DOPRI5, Method::DOP853, Method::RADAU, Method::BDF}; }
+static const char* name(Method m) { static const char* n[] = {"RK23", "DOPRI5", "DOP853", "RK4", "RADAU", "BDF"}; return n[(int)m]; }
+static Options default_opts(Method m) { return Options::builder().method(m).rtol(1e-9).atol(1e-9).build(); }   // tests/common.rs:21-27
+
+// ---- API surface only: runs without a GPU ----------------------------------------------------------------
+static void api_surface() {
+  Options d = Options::builder().build();                       // options.rs:77-123 defaults
+  CHECK(d.method == Method::DOPRI5 && d.rtol[0] == 1e-3 && d.atol[0] == 1e-6, "defaults");
+  CHECK(!d.max_steps && !d.t_eval && !d.first_step && !d.max_step && !d.min_step && !d.dense_output, "Option fields default to None");
+  CHECK(method_from_str("rk45") == Method::DOPRI5 && method_from_str("Radau5") == Method::RADAU &&
+        method_from_str("bdf15") == Method::BDF && method_from_str("nonsense") == Method::DOPRI5, "From<&str> for Method");
+  CHECK(coeffs_per_state(Method::DOP853) == 8 && coeffs_per_state(Method::BDF) == 7 && coeffs_per_state(Method::RK4) == 4, "coeffs_per_state");
+  CHECK((int)Status::Success == 0 && (int)Status::UserInterrupt == 1 && (int)Status::PoorConvergence == 6, "Status declaration order");
+  CHECK(direction_from(3) == Direction::Positive && direction_from(-1) == Direction::Negative && direction_from(0) == Direction::All, "From<i32> for Direction");
+  EventConfig c; c.negative().terminal();
+  CHECK(c.direction == Direction::Negative && c.terminal_count_ && *c.terminal_count_ == 1, "EventConfig setters");
+  Tolerance tv{1e-2, 1e-10};
+  CHECK(tv.is_vector() && tv[1] == 1e-10 && Tolerance(1e-3)[5] == 1e-3, "Tolerance scalar broadcast / vector index");
+  Problem p = Problem::builtin("cr3bp");
+  CHECK(p.n() == 6 && p.n_params() == 1 && p.n_events() == 0, "built-in problem sizes");
+  bool threw = false;
+  try { Problem::builtin("no_such_problem"); } catch (const ConfigError&) { threw = true; }
+  CHECK(threw, "unknown built-in problem is a ConfigError");
+}
+
+static void no_device_fails_loudly() {
+  bool threw = false;
+  try { Context c; } catch (const DeviceError& e) { threw = std::strstr(e.what(), "no CPU fallback") != nullptr; }
+  CHECK(threw, "without a CUDA device the context must fail loudly");
+}
+
+// ---- tests/ivp.rs:20-46 ----------------------------------------------------------------------------------
+static void integration_zero_rhs_all_methods() {
+  Problem f = Problem::builtin("zero3");
+  std::vector<double> t_eval;
+  for (int i = 0; i <= 20; ++i) t_eval.push_back(0.0 + 10.0 * i / 20.0);
+  for (Method m : {Method::RK23, Method::DOPRI5, Method::DOP853, Method::RADAU}) {      // BDF excluded, as in the reference
+    Options o = Options::builder().method(m).rtol(1e-9).atol(1e-12).t_eval(t_eval).build();
+    Solution sol = solve_ivp(f, 0.0, 10.0, {1.0, 1.0, 1.0}, o);
+    CHECK(sol.t == t_eval, "%s: sol.t == t_eval", name(m));
+    for (auto& yi : sol.y) for (double v : yi) CHECK(std::fabs(v - 1.0) <= 1e-12, "%s", name(m));
+  }
+}
+
+// ---- tests/ivp.rs:48-104 ---------------------------------------------------------------------------------
+static void max_step_and_first_step_controls() {
+  Problem sho = Problem::builtin("sho");
+  const double max_step = 0.05;
+  for (Method m : all_methods()) {
+    Options o = Options::builder().method(m).rtol(1e-6).atol(1e-9).max_step(max_step).build();
+    Solution sol = solve_ivp(sho, 0.0, 3.0, {1.0, 0.0}, o);
+    CHECK(sol.status == Status::Success && sol.t.size() > 10, "%s", name(m));
+    for (size_t i = 1; i < sol.t.size(); ++i)
+      CHECK(std::fabs(sol.t[i] - sol.t[i - 1]) <= max_step * 1.01 + 1e-12, "dt exceeds max_step for %s", name(m));
+  }
+  for (Method m : {Method::RK23, Method::DOPRI5, Method::DOP853, Method::RADAU}) {
+    Options o = Options::builder().method(m).rtol(1e-3).atol(1e-6).first_step(0.1).build();
+    Solution sol = solve_ivp(sho, 0.0, 3.0, {1.0, 0.0}, o);
+    CHECK(sol.t.size() >= 2, "%s", name(m));
+    if (sol.t.size() >= 2) CHECK(std::fabs(std::fabs(sol.t[1] - sol.t[0]) - 0.1) <= 1e-6, "first step mismatch for %s: %g", name(m), sol.t[1] - sol.t[0]);
+  }
+}
+
+// ---- tests/ivp.rs:151-275 --------------------------------------------------------------------------------
+static void event_detection_all_and_directional() {
+  Problem sho = Problem::builtin("sho");     // events: g = y[0]
+  const double pi_2 = std::acos(-1.0) / 2;
+  auto run = [&](EventConfig c) {
+    Options o = default_opts(Method::DOPRI5);
+    o.event_config = std::vector<EventConfig>{c};
+    return solve_ivp(sho, 0.0, 6.0, {1.0, 0.0}, o);
+  };
+  Solution all = run(EventConfig().all().terminal_count(2));
+  CHECK(all.t_events[0].size() == 2, "two zero crossings recorded");
+  if (all.t_events[0].size() == 2) {
+    CHECK(std::fabs(all.t_events[0][0] - pi_2) < 5e-3 && std::fabs(all.t_events[0][1] - 3 * pi_2) < 5e-3, "zeros at pi/2, 3pi/2");
+    CHECK(std::fabs(all.y_events[0][0][0]) <= 1e-8 && std::fabs(all.y_events[0][1][0]) <= 1e-8, "event states on the zero");
+    CHECK(all.status == Status::UserInterrupt && all.t.back() == all.t_events[0][1], "terminal event point appended to t");
+  }
+  Solution pos = run(EventConfig().positive().terminal());
+  CHECK(!pos.t_events[0].empty() && std::fabs(pos.t_events[0][0] - 3 * pi_2) < 5e-3, "positive crossing near 3pi/2");
+  Solution neg = run(EventConfig().negative().terminal());
+  CHECK(!neg.t_events[0].empty() && std::fabs(neg.t_events[0][0] - pi_2) < 5e-3, "negative crossing near pi/2");
+}
+
+// ---- tests/ivp.rs:277-289 --------------------------------------------------------------------------------
+static void zero_interval_returns_initial_state() {
+  Problem sho = Problem::builtin("sho");
+  for (Method m : all_methods()) {
+    Solution sol = solve_ivp(sho, 1.23, 1.23, {2.0, 3.0}, default_opts(m));
+    CHECK(!sol.t.empty(), "%s", name(m));
+    CHECK(std::fabs(sol.y.back()[0] - 2.0) <= 1e-12 && std::fabs(sol.y.back()[1] - 3.0) <= 1e-12, "%s", name(m));
+  }
+}
+
+// ---- tests/ivp.rs:299-334 --------------------------------------------------------------------------------
+static void vector_rtol_componentwise_control() {
+  Problem f = Problem::builtin("exp2");
+  Options loose = Options::builder().method(Method::DOPRI5).rtol({1e-2, 1e-2}).atol(1e-10).build();
+  Options tight = Options::builder().method(Method::DOPRI5).rtol({1e-2, 1e-10}).atol(1e-10).build();
+  Solution a = solve_ivp(f, 0.0, 1.0, {1.0, 1.0}, loose), b = solve_ivp(f, 0.0, 1.0, {1.0, 1.0}, tight);
+  const double e = std::exp(1.0);
+  CHECK(std::fabs(b.y.back()[1] - e) < 0.5 * std::fabs(a.y.back()[1] - e), "tightening the second component reduces its error");
+  CHECK(std::fabs(b.y.back()[0] - e) <= 10.0 * std::fabs(a.y.back()[0] - e), "first component not dramatically worse");
+}
+
+// ---- tests/accuracy.rs:17-76 -----------------------------------------------------------------------------
+static void harmonic_accuracy_and_t_eval() {
+  Problem sho = Problem::builtin("sho");
+  const double xend = 2.0 * std::acos(-1.0);
+  for (Method m : {Method::RK4, Method::RK23, Method::DOPRI5, Method::DOP853, Method::RADAU, Method::BDF}) {
+    Options o = m == Method::RK4 ? Options::builder().method(m).first_step(xend / 2000.0).build() : default_opts(m);
+    Solution sol = solve_ivp(sho, 0.0, xend, {1.0, 0.0}, o);
+    CHECK(std::fabs(sol.y.back()[0] - 1.0) < 1e-5 && std::fabs(sol.y.back()[1]) < 1e-5, "end state after one period, %s", name(m));
+    std::vector<double> te;
+    for (int i = 0; i <= 10; ++i) te.push_back(i / 10.0);
+    Options ot = m == Method::RK4 ? Options::builder().method(m).first_step(0.01).t_eval(te).build()
+                                  : Options::builder().method(m).rtol(1e-9).atol(1e-9).t_eval(te).build();
+    Solution st = solve_ivp(sho, 0.0, 1.0, {1.0, 0.0}, ot);
+    CHECK(st.t == te && st.y.size() == st.t.size(), "t_eval respected for %s", name(m));
+    size_t k = 0;
+    for (auto [t, y] : st) { CHECK(std::fabs(y[0] - std::cos(t)) < 1e-4, "%s sample %zu", name(m), k); ++k; }   // Solution::iter
+  }
+}
+
+// ---- tests/backward_and_bounds.rs:6-31 (end state instead of the dense span) --------------------------------
+static void backward_integration_works() {
+  Problem sho = Problem::builtin("sho");
+  const double x0 = 2.0 * std::acos(-1.0);
+  for (Method m : all_methods()) {
+    Options o = Options::builder().method(m).rtol(1e-9).atol(1e-9).t_eval({x0, 0.5 * x0, 0.0}).build();
+    Solution sol = solve_ivp(sho, x0, 0.0, {1.0, 0.0}, o);
+    CHECK(sol.status == Status::Success && sol.t.size() == 3, "%s", name(m));
+    if (sol.t.size() == 3) CHECK(std::fabs(sol.y[1][0] - std::cos(0.5 * x0)) < 1e-6 && std::fabs(sol.y[1][1] + std::sin(0.5 * x0)) < 1e-6, "%s mid point", name(m));
+  }
+}
+
+// ---- examples/bouncing_ball.rs, examples/van_der_pol.rs, examples/cr3bp.rs as batches ----------------------
+static void example_programs_as_batches() {
+  const size_t N = 1000;
+  {  // bouncing ball: terminal event y[0] = 0, negative direction (bouncing_ball.rs:11-31)
+    Problem ball = Problem::builtin("bouncing_ball");
+    std::vector<double> y0, par;
+    for (size_t i = 0; i < N; ++i) { y0.push_back(1.0 + 0.01 * i); y0.push_back(0.0); par.push_back(9.81); par.push_back(0.0); }
+    auto sols = solve_ivp_batch(ball, 0.0, 10.0, y0, par, Options::builder().method(Method::DOPRI5).rtol(1e-8).atol(1e-10).build());
+    for (size_t i = 0; i < N; i += 111) {
+      const double t_hit = std::sqrt(2.0 * (1.0 + 0.01 * i) / 9.81);
+      CHECK(sols[i].status == Status::UserInterrupt && sols[i].t_events[0].size() == 1, "ball %zu", i);
+      CHECK(std::fabs(sols[i].t_events[0][0] - t_hit) < 1e-7, "impact time %g vs %g", sols[i].t_events[0][0], t_hit);
+    }
+  }
+  {  // stiff Van der Pol, eps = 1e-3, BDF, t_eval 0..2 (van_der_pol.rs:17-29), whole batch identical rows
+    Problem vdp = Problem::builtin("vdp_eps");
+    std::vector<double> y0, par, te;
+    for (size_t i = 0; i < 64; ++i) { y0.push_back(2.0); y0.push_back(0.0); par.push_back(1e-3); }
+    for (int i = 0; i <= 20; ++i) te.push_back(0.1 * i);
+    for (Method m : {Method::BDF, Method::RADAU}) {
+      auto sols = solve_ivp_batch(vdp, 0.0, 2.0, y0, par, Options::builder().method(m).rtol(1e-6).atol(1e-8).t_eval(te).build());
+      CHECK(sols[0].status == Status::Success && sols[0].t == te && sols[0].njev > 0 && sols[0].nlu > 0, "%s", name(m));
+      for (auto& s : sols) CHECK(s.y == sols[0].y && s.naccpt == sols[0].naccpt, "identical rows give identical solutions (%s)", name(m));
+      CHECK(std::fabs(sols[0].y.back()[0] + 1.2) < 0.6, "y(2) on the other branch of the limit cycle (%s): %g", name(m), sols[0].y.back()[0]);   // relaxation jump near t = 0.8
+    }
+  }
+  {  // user problem as CUDA C through NVRTC == `impl IVP for Decay` (exponential_decay.rs:10-12)
+    Problem decay = Problem::from_cuda_source(
+        "__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = -p[0] * y[0]; }", 1, 1);
+    std::vector<double> y0(N, 1.0), k(N);
+    for (size_t i = 0; i < N; ++i) k[i] = 0.1 + 0.001 * i;
+    auto sols = solve_ivp_batch(decay, 0.0, 5.0, y0, k, Options::builder().method(Method::DOP853).rtol(1e-10).atol(1e-12).build());
+    for (size_t i = 0; i < N; i += 97) CHECK(std::fabs(sols[i].y.back()[0] - std::exp(-5.0 * k[i])) < 1e-9, "decay %zu", i);
+    bool threw = false;
+    try { solve_ivp(decay, 0.0, 1.0, {1.0}, Options::builder().method(Method::RK4).first_step(-0.1).build(), {0.5}); }
+    catch (const ConfigError&) { threw = true; }                  // rk4.rs:84-90
+    CHECK(threw, "RK4 with a step of the wrong sign is Error::Config");
+    threw = false;
+    try { solve_ivp(decay, 0.0, 1.0, {1.0}, Options::builder().max_steps(0).build(), {0.5}); } catch (const ConfigError&) { threw = true; }
+    CHECK(threw, "max_steps == 0 is Error::Config");
+    Solution s = solve_ivp(decay, 0.0, 1.0, {1.0}, Options::builder().rtol(1e-10).atol(1e-12).max_steps(3).build(), {0.5});
+    CHECK(s.status == Status::NeedLargerNMax, "numerical failure is a status, not an error: %s", to_string(s.status));
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool api_only = argc > 1 && std::strcmp(argv[1], "--api-only") == 0;
+  api_surface();
+  if (api_only) {
+    if (argc > 2 && std::strcmp(argv[2], "--expect-no-device") == 0) no_device_fails_loudly();
+  } else {
+    integration_zero_rhs_all_methods();
+    max_step_and_first_step_controls();
+    event_detection_all_and_directional();
+    zero_interval_returns_initial_state();
+    vector_rtol_componentwise_control();
+    harmonic_accuracy_and_t_eval();
+    backward_integration_works();
+    example_programs_as_batches();
+  }
+  std::printf("%d checks, %d failed\n", g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}
