@@ -37,19 +37,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (ensemble, method, rtol, atol, F = flops of one RHS call, n)
-    "vdp_dop853": ("vdp", "DOP853", 1e-8, 1e-8, 5, 2),
+    # name: (ensemble, method, rtol, atol, F = flops of one RHS call, n)      [BASELINE.json configs]
+    "vdp_dop853": ("vdp", "DOP853", 1e-8, 1e-8, 5, 2),                       # north star (the default bench line)
     "vdp_dopri5": ("vdp", "DOPRI5", 1e-6, 1e-9, 5, 2),
-    "decay_dopri5": ("decay", "DOPRI5", 1e-6, 1e-9, 2, 1),
+    "decay_dopri5": ("decay", "DOPRI5", 1e-6, 1e-9, 2, 1),                   # configs[1]
     "lorenz_dopri5": ("lorenz", "DOPRI5", 1e-6, 1e-9, 8, 3),
+    "lorenz_rk4": ("lorenz", "RK4", 1e-6, 1e-9, 8, 3),
+    "cr3bp_dop853_teval": ("cr3bp", "DOP853", 1e-10, 1e-12, 48, 6),          # configs[2]: 101 t_eval samples
+    "ball_dopri5_events": ("ball", "DOPRI5", 1e-8, 1e-10, 4, 2),             # configs[3]
+    "robertson_radau": ("robertson", "RADAU", 1e-6, 1e-6, 13, 3),            # configs[4]
+    "robertson_bdf": ("robertson", "BDF", 1e-6, 1e-6, 13, 3),
+    "vdpstiff_radau": ("vdp_stiff", "RADAU", 1e-4, 1e-6, 5, 2),
+    "vdpstiff_bdf": ("vdp_stiff", "BDF", 1e-4, 1e-6, 5, 2),
 }
+N_T_EVAL = {"cr3bp_dop853_teval": 101}
 NOMINAL_FP64_TFLOPS = 37.0   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 
-def algorithmic_flops(method: str, F: int, n: int, nstep, naccpt, dense: bool) -> float:
+def algorithmic_flops(method: str, F: int, n: int, nstep, naccpt, dense: bool, counters=None, n_samples: int = 0) -> float:
     """SURVEY 8d table (mul/add/sub/div/sqrt = 1, FMA = 2); only work the kernel executes is counted."""
     nstep = np.asarray(nstep, dtype=np.float64)
     naccpt = np.asarray(naccpt, dtype=np.float64)
+    if method in ("RADAU", "BDF"):
+        # SURVEY appendix B (approximate: Newton iterations recovered from nfev; FD Jacobian = n + 1 RHS calls)
+        c = np.asarray(counters, dtype=np.float64)
+        nfev, njev, nlu = c[:, 0], c[:, 1], c[:, 2]
+        if method == "RADAU":
+            iters = np.maximum(nfev - 1 - naccpt, 0) / 3.0
+            decomps = np.maximum(nlu - nstep, 0) / 2.0                        # nlu also counts one error solve per attempt
+            fl = iters * (3 * F + 10 * n * n + 49 * n) + decomps * (10.0 / 3.0 * n ** 3) + nstep * (3 * n * n + 8 * n) \
+                + njev * (n + 1) * F + naccpt * (F + 12 * n)
+        else:
+            iters = np.maximum(nfev - 1, 0)
+            fl = iters * (F + 2 * n * n + 8 * n) + nlu * (2.0 / 3.0 * n ** 3 + n * n) + njev * (n + 1) * F + nstep * 20 * n
+        return float(fl.sum())
     if method == "DOP853":
         fl = nstep * (11 * F + 157 * n + 45) + naccpt * F
         if dense:
@@ -60,7 +81,21 @@ def algorithmic_flops(method: str, F: int, n: int, nstep, naccpt, dense: bool) -
         fl = nstep * (3 * F + 27 * n + 20)
     else:
         fl = nstep * (4 * F + 18 * n + 8)
-    return float(fl.sum())
+    interp = {"DOP853": 14 * n + 3, "DOPRI5": 8 * n + 3, "RK23": 7 * n + 4}.get(method, 9 * n + 16)
+    return float(fl.sum()) + float(n_samples) * interp
+
+
+def workload_options(name: str, t0: float, tf: float, flags: int = 0, jac_mode: int = 0):
+    """Options of a named workload (shared by the GPU arm, the cpu_baseline leg and --impl reference)."""
+    from ivp_b200 import Method, Options
+    ens, method, rtol, atol, F, n = WORKLOADS[name]
+    n_te = N_T_EVAL.get(name, 0)
+    extra = {"t_eval": np.linspace(t0, tf, n_te)} if n_te else {}
+    if method == "RK4":
+        extra["first_step"] = (tf - t0) / 1000.0
+    if jac_mode:
+        extra["jac_mode"] = 1
+    return Options(method=Method[method], rtol=rtol, atol=atol, flags=flags, max_events=1, **extra)
 
 
 class ClockSampler:
@@ -118,7 +153,7 @@ def run_reference(args, rank, world):
     cores = pyoracle.hardware_threads()
     sample = args.cpu_sample
     prob, y0, par, t0, tf = synth.ensemble(ens, sample)
-    opts = Options(method=Method[method], rtol=rtol, atol=atol)
+    opts = workload_options(args.workload, t0, tf, jac_mode=args.jac_mode)
     for _ in range(args.warmup):
         pyoracle.solve_batch(PROBLEMS[prob], t0, tf, y0[:256], par[:256] if par is not None else None, opts, nthreads=cores)
     t_begin = time.perf_counter()
@@ -151,6 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--static", action="store_true", help="disable work-queue refill (A/B)")
     ap.add_argument("--strict", action="store_true", help="-fmad=false kernel variant (A/B)")
+    ap.add_argument("--jac-mode", type=int, default=0, help="implicit workloads: 0 finite differences, 1 analytic")
     args = ap.parse_args()
     from ivp_b200.dist import dist_env, reduce_time_and_count, weak_offset
     rank, local_rank, world = dist_env()
@@ -179,9 +215,11 @@ def main():
     prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=weak_offset(Nper, rank))
     problem = api.Problem.builtin(prob_name)
     flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0)
-    opts = Options(method=Method[method], rtol=rtol, atol=atol, flags=flags)
+    n_te = N_T_EVAL.get(args.workload, 0)
+    opts = workload_options(args.workload, t0, tf, flags, args.jac_mode)
     mo = _abi.MarshalledOptions(opts, problem.n, problem.n_events)
     ctx = api.Context([local_rank])
+    ne = problem.n_events
 
     # ---- device-resident arm -------------------------------------------------------------------
     y0_d = torch.from_numpy(y0_h).to(dev)
@@ -192,6 +230,17 @@ def main():
     yfin_d = torch.empty((Nper, problem.n), dtype=torch.float64, device=dev)
     d_out = {"status": status_d.data_ptr(), "counters": counters_d.data_ptr(), "t_final": tfin_d.data_ptr(),
              "y_final": yfin_d.data_ptr()}
+    out_bytes_per_traj = 4 + 24 + 8 + 8 * problem.n
+    if n_te:        # t_eval samples written straight to the preallocated [N][cap][n] block
+        nout_d = torch.zeros(Nper, dtype=torch.int32, device=dev)
+        yout_d = torch.zeros((Nper, mo.cap, problem.n), dtype=torch.float64, device=dev)
+        d_out.update({"n_out": nout_d.data_ptr(), "y_out": yout_d.data_ptr()})
+        out_bytes_per_traj += 4 + 8 * n_te * problem.n
+    if ne:
+        evc_d = torch.zeros((Nper, ne), dtype=torch.int32, device=dev)
+        evt_d = torch.zeros((Nper, ne, 1), dtype=torch.float64, device=dev)
+        d_out.update({"ev_count": evc_d.data_ptr(), "ev_t": evt_d.data_ptr()})
+        out_bytes_per_traj += ne * 12
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def solve_device():
@@ -227,7 +276,9 @@ def main():
     status = status_d.cpu().numpy()
     nstep, naccpt, nrejct = counters[:, 3], counters[:, 4], counters[:, 5]
     acc_local = int(naccpt.sum())
-    flops_launch = algorithmic_flops(method, F, n, nstep, naccpt, dense=False)
+    n_samples = int(nout_d.sum().item()) if n_te else 0
+    flops_launch = algorithmic_flops(method, F, n, nstep, naccpt, dense=bool(n_te or ne), counters=counters,
+                                     n_samples=n_samples)
 
     total_ms_max, acc_all = reduce_time_and_count(total_ms, acc_local, dev, use_dist)
     value = acc_all * args.steps / (total_ms_max * 1e-3)
@@ -248,6 +299,18 @@ def main():
     y0_np, par_np = y0_p.numpy(), (par_p.numpy() if par_p is not None else None)
     h2d = y0_np.nbytes + (par_np.nbytes if par_np is not None else 0)
     d2h = h_status.numel() * 4 + h_counters.numel() * 4 + h_tfin.numel() * 8 + h_yfin.numel() * 8
+    if n_te:
+        h_nout = torch.empty(Nper, dtype=torch.int32).pin_memory()
+        h_yout = torch.empty((Nper, mo.cap, problem.n), dtype=torch.float64).pin_memory()
+        st.n_out = C.cast(h_nout.data_ptr(), _abi.c_int32_p)
+        st.y_out = C.cast(h_yout.data_ptr(), _abi.c_double_p)
+        d2h += h_nout.numel() * 4 + h_yout.numel() * 8
+    if ne:
+        h_evc = torch.empty((Nper, ne), dtype=torch.int32).pin_memory()
+        h_evt = torch.empty((Nper, ne, 1), dtype=torch.float64).pin_memory()
+        st.ev_count = C.cast(h_evc.data_ptr(), _abi.c_int32_p)
+        st.ev_t = C.cast(h_evt.data_ptr(), _abi.c_double_p)
+        d2h += h_evc.numel() * 4 + h_evt.numel() * 8
     for _ in range(2):
         ctx.solve_host(problem, t0, tf, y0_np, par_np, mo, st)
     barrier()
@@ -272,7 +335,7 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload)
         except Exception:
             traffic = None
-    alg_bytes = Nper * (8 * problem.n + 8 * problem.p + 4 + 24 + 8 + 8 * problem.n)
+    alg_bytes = Nper * (8 * problem.n + 8 * problem.p + out_bytes_per_traj)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
                 "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
                 "peak_source": "measured on this GPU: libivpb DFMA-chain microbenchmark (MEASURED_PEAKS.json has no fp64 entry)",
@@ -307,7 +370,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "problem": prob_name, "method": method, "rtol": rtol, "atol": atol,
                        "t_span": [t0, tf], "trajectories_per_gpu": Nper, "trajectories_total": Nper * world,
-                       "outputs": "final state + status + counters", "parallelism": f"trajectory-sharded x{world}",
+                       "outputs": "final state + status + counters" + (f" + {n_te} t_eval samples" if n_te else "") +
+                                  (" + event times" if ne else ""), "parallelism": f"trajectory-sharded x{world}",
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "schedule": "static" if args.static else "work-queue refill", "fp": "strict" if args.strict else "fma"},
             "accepted_steps_per_step": acc_all, "rejected_steps_rank0": int(nrejct.sum()),

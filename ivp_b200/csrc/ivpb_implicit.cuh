@@ -611,6 +611,15 @@ __device__ __forceinline__ double alpha(int k) { return (1.0 - kappa(k)) * gamma
 __device__ __forceinline__ double error_const(int k) { return kappa(k) * gamma(k) + 1.0 / ((double)k + 1.0); }
 }  // namespace bdf_c
 
+// c ? a : b through an opaque selp: keeps "slot k of a register array, chosen by a run-time order" as a chain
+// of selects.  Written as a plain ternary, LLVM folds the chain back into one dynamically indexed load / store,
+// which forces the whole trajectory state out of registers into local memory (measured: 528 B stack frame).
+__device__ __forceinline__ double opaque_sel(bool c, double a, double b) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+  return r;
+}
+
 template <class Prob, int FEAT, bool REG, int BLK>
 struct BdfTraj {
   static constexpr int N = Prob::N, P = Prob::P;
@@ -652,45 +661,62 @@ struct BdfTraj {
     return sqrt(sum / (double)N);
   }
 
-  // change_d (bdf.rs:669-713): D <- (R(order, factor) U(order, 1))^T D on rows 0..order.
+  // change_d (bdf.rs:669-713): D <- (R(order, factor) U(order, 1))^T D on rows 0..order, where
+  // compute_r(order, f)[i][j] = prod_{l=1..i} (l - 1 - f j) / l  (row 0 = 1, column 0 = 0 below row 0) and the
+  // order only selects the leading (order+1) x (order+1) block.  The reference forms RU = R U first (matmul,
+  // zero R entries skipped) and then accumulates scratch[row] += RU[k][row] * D[k] over k ascending; the loop
+  // below walks k once, carrying row k of R in six registers, which performs the same operations in the same
+  // order per output element.  U is a compile-time constant (u_entry), upper triangular.
+  static __host__ __device__ constexpr double u_entry(int i, int j) {      // compute_r(order, 1.0)[i][j]
+    if (i == 0) return 1.0;
+    if (j == 0) return 0.0;
+    double r = 1.0;
+    for (int l = 1; l <= i; ++l) r = r * (((double)l - 1.0 - 1.0 * (double)j) / (double)l);
+    return r;
+  }
   __device__ __forceinline__ void change_d(double factor) {
     constexpr int S = bdf_c::MAX_ORDER + 1;
     if (factor == 1.0) return;
     const int ord = order < bdf_c::MAX_ORDER ? order : bdf_c::MAX_ORDER;
-    // compute_r(order, f): r[0][j] = 1, r[i][j] = prod_{l<=i} (l - 1 - f j) / l; the order only sets the size
-    double r[S][S], u[S][S];
-#pragma unroll
-    for (int j = 0; j < S; ++j) { r[0][j] = 1.0; u[0][j] = 1.0; }
-#pragma unroll
-    for (int i = 1; i < S; ++i) {
-      r[i][0] = r[i - 1][0] * 0.0;        // m[i][0] is never written (stays 0), bdf.rs:698-703
-      u[i][0] = u[i - 1][0] * 0.0;
-#pragma unroll
-      for (int j = 1; j < S; ++j) {
-        r[i][j] = r[i - 1][j] * (((double)i - 1.0 - factor * (double)j) / (double)i);
-        u[i][j] = u[i - 1][j] * (((double)i - 1.0 - 1.0 * (double)j) / (double)i);
-      }
-    }
     double scratch[S][N];
 #pragma unroll
-    for (int row = 0; row < S; ++row) {
+    for (int row = 0; row < S; ++row)
 #pragma unroll
       for (int i = 0; i < N; ++i) scratch[row][i] = 0.0;
-      if (row > ord) continue;
+    double rk[S];                      // row k of R
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        if (k > ord) continue;
-        double coeff = 0.0;               // ru[k][row] = sum_m r[k][m] u[m][row], zero r-entries skipped
+    for (int j = 0; j < S; ++j) rk[j] = 1.0;
 #pragma unroll
-        for (int m = 0; m < S; ++m) {
-          if (m > ord) continue;
-          const double rc = r[k][m];
-          if (rc == 0.0) continue;
-          coeff += rc * u[m][row];
+    for (int k = 0; k < S; ++k) {
+      if (k > 0) {
+        rk[0] = rk[0] * 0.0;           // m[k][0] is never written (stays 0), bdf.rs:698-703
+#pragma unroll
+        for (int j = 1; j < S; ++j) rk[j] = rk[j] * (((double)k - 1.0 - factor * (double)j) / (double)k);
+      }
+      if (k <= ord) {
+#pragma unroll
+        for (int row = 0; row < S; ++row) {
+          if (row <= ord) {
+            double coeff = 0.0;        // RU[k][row] = sum_m R[k][m] U[m][row]
+#pragma unroll
+            for (int m = 0; m < S; ++m) {
+              // U is upper triangular (u_entry(m, row) == 0 for m > row): those terms add an exact zero in the
+              // reference and are skipped here at compile time; m <= row <= ord holds for the rest.
+              if (u_entry(m, row) != 0.0) {
+                const double um = u_entry(m, row);
+#ifdef IVPB_STRICT
+                if (rk[m] != 0.0) coeff += rk[m] * um;     // matmul skips zero R entries (bdf.rs:722-725)
+#else
+                coeff = fma(rk[m], um, coeff);
+#endif
+              }
+            }
+            if (coeff != 0.0) {
+#pragma unroll
+              for (int i = 0; i < N; ++i) scratch[row][i] += coeff * d[k][i];
+            }
+          }
         }
-        if (coeff == 0.0) continue;
-#pragma unroll
-        for (int i = 0; i < N; ++i) scratch[row][i] += coeff * d[k][i];
       }
     }
 #pragma unroll
@@ -907,13 +933,12 @@ struct BdfTraj {
     for (int i = 0; i < N; ++i) {
       y[i] = y_new[i];
 #pragma unroll
-      for (int k = 2; k < ND; ++k) {       // d[order+2] = delta - d[order+1]; d[order+1] = delta
-        if (k == order + 2) d[k][i] = delta[i] - d[k - 1][i];
-      }
+      for (int k = 2; k < ND; ++k)         // d[order+2] = delta - d[order+1]; d[order+1] = delta
+        d[k][i] = opaque_sel(k == order + 2, delta[i] - d[k - 1][i], d[k][i]);
 #pragma unroll
-      for (int k = 1; k < ND; ++k) if (k == order + 1) d[k][i] = delta[i];
+      for (int k = 1; k < ND; ++k) d[k][i] = opaque_sel(k == order + 1, delta[i], d[k][i]);
 #pragma unroll
-      for (int k = MAX_ORDER; k >= 0; --k) if (k <= order) d[k][i] += d[k + 1][i];
+      for (int k = MAX_ORDER; k >= 0; --k) d[k][i] = opaque_sel(k <= order, d[k][i] + d[k + 1][i], d[k][i]);
     }
     if constexpr (FEAT != 0) {
       double cont[7][N];                    // D0, D1..D5 (zero above the order), order marker (bdf.rs:506-514)
@@ -938,7 +963,7 @@ struct BdfTraj {
         for (int i = 0; i < N; ++i) {
           double dv = 0.0;
 #pragma unroll
-          for (int k = 2; k <= MAX_ORDER; ++k) if (k == order) dv = d[k][i];
+          for (int k = 2; k <= MAX_ORDER; ++k) dv = opaque_sel(k == order, d[k][i], dv);
           rhs[i] = error_const(order - 1) * dv;
         }
         err_m = wrms(rhs, scale);
@@ -948,7 +973,7 @@ struct BdfTraj {
         for (int i = 0; i < N; ++i) {
           double dv = 0.0;
 #pragma unroll
-          for (int k = 3; k < ND; ++k) if (k == order + 2) dv = d[k][i];
+          for (int k = 3; k < ND; ++k) dv = opaque_sel(k == order + 2, d[k][i], dv);
           rhs[i] = error_const(order + 1) * dv;
         }
         err_p = wrms(rhs, scale);

@@ -44,10 +44,15 @@ static inline double ivpb_libm_u2d(unsigned long long u) { double x; std::memcpy
 
 IVPB_LIBM_FN double ivpb_libm_pow(double x, double y) {
   typedef unsigned long long u64_t;
-  const u64_t ix = IVPB_LIBM_D2U(x), iy = IVPB_LIBM_D2U(y);
+  u64_t ix = IVPB_LIBM_D2U(x);
+  const u64_t iy = IVPB_LIBM_D2U(y);
   const unsigned topx = (unsigned)(ix >> 52), topy = (unsigned)(iy >> 52) & 0x7ffu;
-  // e_pow.c: x must be a positive normal number and 2^-65 <= |y| < 2^63 for the main path
-  if (topx - 1u > 0x7fdu || topy - 0x3beu > 0x7fu) return IVPB_LIBM_FALLBACK(x, y);
+  // e_pow.c: x must be a positive finite number and 2^-65 <= |y| < 2^63 for the main path
+  if (topy - 0x3beu > 0x7fu) return IVPB_LIBM_FALLBACK(x, y);
+  if (topx - 1u > 0x7fdu) {
+    if (topx != 0u || ix == 0ULL) return IVPB_LIBM_FALLBACK(x, y);      // zero, negative, inf, nan
+    ix = IVPB_LIBM_D2U(IVPB_LIBM_MUL(x, 4503599627370496.0)) - (52ULL << 52);   // positive subnormal: normalise
+  }
 
   // ---- log_inline: log(x) = hi + lo ----
   const u64_t tmp = ix - 0x3fe6955500000000ULL;

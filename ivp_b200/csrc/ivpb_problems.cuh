@@ -3,6 +3,7 @@
 // jac, with the struct fields of the reference programs read from the trajectory's parameter row `p`.
 #pragma once
 #include "ivpb_problems_min.cuh"
+#include "ivpb_fastmath.cuh"
 
 namespace ivpb {
 
@@ -56,13 +57,25 @@ struct PCr3bp : ProblemDefaults<6, 1, 0> {      // reference examples/cr3bp.rs:2
   IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
     const double mu = p[0];
     const double x = s[0], y = s[1], z = s[2];
+    d[0] = s[3]; d[1] = s[4]; d[2] = s[5];
+#ifdef IVPB_STRICT
     const double r1 = sqrt((x + mu) * (x + mu) + y * y + z * z);
     const double r2 = sqrt((x - 1.0 + mu) * (x - 1.0 + mu) + y * y + z * z);
     const double r13 = (r1 * r1) * r1, r23 = (r2 * r2) * r2;   // powi(3)
-    d[0] = s[3]; d[1] = s[4]; d[2] = s[5];
     d[3] = x + 2.0 * s[4] - (1.0 - mu) * (x + mu) / r13 - mu * (x - 1.0 + mu) / r23;
     d[4] = y - 2.0 * s[3] - (1.0 - mu) * y / r13 - mu * y / r23;
     d[5] = -(1.0 - mu) * z / r13 - mu * z / r23;
+#else
+    // fast build: 1/r^3 = rsqrt(r^2)^3 -- two slow-path-free reciprocal square roots (ivpb_fastmath.cuh)
+    // replace the reference's 2 sqrt + 6 divisions (a few ulp apart, like every other fast-mode operation)
+    const double xm = x + mu, xn = x - 1.0 + mu;
+    const double yz = fma(y, y, z * z);
+    const double i1 = fm::rsqrt(fma(xm, xm, yz)), i2 = fm::rsqrt(fma(xn, xn, yz));
+    const double g1 = (1.0 - mu) * ((i1 * i1) * i1), g2 = mu * ((i2 * i2) * i2);
+    d[3] = fma(-g2, xn, fma(-g1, xm, fma(2.0, s[4], x)));
+    d[4] = fma(-(g1 + g2), y, fma(-2.0, s[3], y));
+    d[5] = -(g1 + g2) * z;
+#endif
   }
 };
 

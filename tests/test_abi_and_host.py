@@ -201,7 +201,7 @@ int main() {
     const double a = std::pow(x, y), b = ivpb_libm_pow(x, y);
     if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) ++bad;
   }
-  const double sx[] = {0.0, -1.0, 1.0, INFINITY, 1e-310, 2.0, 1e300, 1e-300, NAN};
+  const double sx[] = {0.0, -1.0, 1.0, INFINITY, 1e-310, 4.9e-324, 2.2e-308, 2.0, 1e300, 1e-300, NAN};
   const double sy[] = {0.125, 0.5, 2.0, -0.25, 1e-70, INFINITY, 5.0, -5.0, 0.0};
   for (double x : sx) for (double y : sy) {
     const double a = std::pow(x, y), b = ivpb_libm_pow(x, y);

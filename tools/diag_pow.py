@@ -12,3 +12,5 @@ assert lib.ivpb_debug_pow(_abi.ptr(x), _abi.ptr(y), C.c_int(n), _abi.ptr(r)) == 
 ref = np.array([math.pow(a, b) if not (a == 1e300 and b == 5.0) else np.inf for a, b in zip(x.tolist(), y.tolist())])
 bad = (r.view(np.uint64) != ref.view(np.uint64)) & ~(np.isnan(r) & np.isnan(ref))
 print("device pow vs host libm: mismatches", int(bad.sum()), "of", n, r[:8], ref[:8])
+for i in np.nonzero(bad)[0][:10]:
+    print("  mismatch at", i, float(x[i]).hex(), float(y[i]).hex(), "device", float(r[i]).hex(), "host", float(ref[i]).hex())
