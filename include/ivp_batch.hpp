@@ -108,6 +108,7 @@ struct Options {
   std::optional<std::vector<Float>> t_eval;
   std::optional<Float> first_step, max_step, min_step;
   bool dense_output = false;
+  int max_segments = 4096;   // dense_output: interpolant segments kept per trajectory (one per accepted step)
   // jac_storage / mass_storage / nind1-3 of the reference select Banded / DAE variants that the device path
   // does not implement (Full Jacobian, Identity mass, pure ODE == the values solve_ivp passes by default).
   // ---- batched-solve additions (no reference equivalent) ----
@@ -130,6 +131,7 @@ class OptionsBuilder {
   OptionsBuilder& max_step(Float h) { o_.max_step = h; return *this; }
   OptionsBuilder& min_step(Float h) { o_.min_step = h; return *this; }
   OptionsBuilder& dense_output(bool b) { o_.dense_output = b; return *this; }
+  OptionsBuilder& max_segments(int n) { o_.max_segments = n; return *this; }
   OptionsBuilder& event_config(std::vector<EventConfig> c) { o_.event_config = std::move(c); return *this; }
   OptionsBuilder& max_events(int n) { o_.max_events = n; return *this; }
   OptionsBuilder& max_out(int n) { o_.max_out = n; return *this; }
@@ -141,6 +143,15 @@ class OptionsBuilder {
 };
 inline OptionsBuilder Options::builder() { return OptionsBuilder(); }
 
+// ---- ContinuousOutput handle (reference src/solve/cont.rs:9-154) ---------------------------------
+// The segments stay on the device; evaluation is ivpb_dense_eval.  Valid until the next dense_output solve on
+// the same context (the context retains one log).
+struct ContinuousOutput {
+  std::shared_ptr<ivpb_ctx> ctx;
+  int64_t index = 0;
+  int n = 0;
+};
+
 // ---- Solution (reference src/solve/solution.rs:7-97) -------------------------------------------
 struct Solution {
   std::vector<Float> t;
@@ -149,6 +160,34 @@ struct Solution {
   std::vector<std::vector<std::vector<Float>>> y_events;
   size_t nfev = 0, njev = 0, nlu = 0, nstep = 0, naccpt = 0, nrejct = 0;
   Status status = Status::Success;
+  std::optional<ContinuousOutput> continuous_sol;
+  // Solution::sol_span / sol / sol_many (solution.rs:25-72)
+  std::optional<std::pair<Float, Float>> sol_span() const {
+    if (!continuous_sol) return std::nullopt;
+    double a = 0, b = 0; int32_t m = 0;
+    if (ivpb_dense_span(continuous_sol->ctx.get(), continuous_sol->index, 1, &a, &b, &m) != IVPB_OK || m <= 0) return std::nullopt;
+    return std::make_pair(a, b);
+  }
+  std::vector<std::vector<Float>> sol_many(const std::vector<Float>& ts) const {
+    if (!continuous_sol) throw InterpolationError("dense output not enabled");
+    const auto span = sol_span();
+    if (!span) throw InterpolationError("dense output not enabled");
+    const Float lo = std::min(span->first, span->second), hi = std::max(span->first, span->second);
+    for (Float t : ts) if (t < lo || t > hi) throw InterpolationError("t outside the dense output span");
+    const int n = continuous_sol->n;
+    std::vector<int64_t> tr(ts.size(), continuous_sol->index);
+    std::vector<Float> y(ts.size() * (size_t)n);
+    std::vector<int32_t> ok(ts.size());
+    if (ivpb_dense_eval(continuous_sol->ctx.get(), (int64_t)ts.size(), tr.data(), ts.data(), y.data(), ok.data()) != IVPB_OK)
+      throw InterpolationError(ivpb_last_error(continuous_sol->ctx.get()));
+    std::vector<std::vector<Float>> out(ts.size());
+    for (size_t k = 0; k < ts.size(); ++k) {
+      if (!ok[k]) throw InterpolationError("t outside the dense output span");
+      out[k].assign(&y[k * n], &y[k * n] + n);
+    }
+    return out;
+  }
+  std::vector<Float> sol(Float t) const { return sol_many({t}).at(0); }
   // batched-solve additions
   Float h_next = 0.0;          // IntegrationResult.h (src/methods/mod.rs:31-32)
   bool truncated = false;      // more samples / event hits than max_out / max_events allowed
@@ -173,6 +212,7 @@ class Context {
     ctx_.reset(c, [](ivpb_ctx* p) { ivpb_destroy(p); });
   }
   ivpb_ctx* get() const { return ctx_.get(); }
+  const std::shared_ptr<ivpb_ctx>& shared() const { return ctx_; }
   int device_count() const { return ivpb_device_count(ctx_.get()); }
  private:
   std::shared_ptr<ivpb_ctx> ctx_;
@@ -251,6 +291,7 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
   o.n_t_eval = o.has_t_eval ? (int32_t)options.t_eval->size() : 0;
   o.t_eval = o.has_t_eval ? options.t_eval->data() : nullptr;
   o.dense_output = options.dense_output;
+  o.max_segments = options.dense_output ? options.max_segments : 0;
   std::vector<int32_t> dirs;
   std::vector<int64_t> terms;
   if (options.event_config) {
@@ -287,6 +328,7 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
     const uint32_t* c = &counters[6 * i];
     s.nfev = c[0]; s.njev = c[1]; s.nlu = c[2]; s.nstep = c[3]; s.naccpt = c[4]; s.nrejct = c[5];
     s.h_next = h_next[i];
+    if (options.dense_output) s.continuous_sol = ContinuousOutput{ctx.shared(), (int64_t)i, n};
     const size_t m = std::min<size_t>((size_t)std::max(n_out[i], 0), cap);
     s.truncated = (size_t)std::max(n_out[i], 0) > cap;
     s.t.assign(&t_out[i * cap], &t_out[i * cap] + m);

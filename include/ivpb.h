@@ -70,7 +70,8 @@ typedef struct {
   int32_t has_t_eval;          /* Option<Vec<Float>>: Some(empty) is legal */
   int32_t n_t_eval;
   const double* t_eval;        /* shared by all trajectories; ascending (descending for tf < t0) */
-  int32_t dense_output;        /* reserved: per-trajectory segment log; does not change t/y */
+  int32_t dense_output;        /* keep every accepted step's interpolant (Solution::sol; src/solve/solout.rs:141-146,
+                                  src/solve/cont.rs:9-30) in device memory; needs max_segments >= 1; does not change t/y */
   int32_t n_event_cfg;         /* 0 => problem defaults; else must equal the problem's n_events */
   const int32_t* ev_direction;        /* >0 Positive, <0 Negative, 0 All (src/solve/event.rs:68-77) */
   const int64_t* ev_terminal_count;   /* <0 => None */
@@ -78,6 +79,7 @@ typedef struct {
   int32_t max_out;             /* step-mode (no t_eval) capacity of t_out / y_out per trajectory; 0 => samples not stored */
   int32_t jac_mode;            /* 0 finite differences (src/ivp.rs:67-107), 1 analytic ivp_jac */
   int32_t flags;               /* IVPB_FLAG_* */
+  int32_t max_segments;        /* dense_output: interpolant segments stored per trajectory (one per accepted step) */
 } ivpb_options;
 
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
@@ -100,6 +102,12 @@ typedef struct {
   int32_t* ev_count;    /* [N][n_events]   hits per event function (may exceed max_events => truncated) */
   double* ev_t;         /* [N][n_events][max_events]                                    */
   double* ev_y;         /* [N][n_events][max_events][n]                                 */
+  /* dense_output: the reference's ContinuousOutput segments (src/dense.rs:104-147).  Optional copies -- the
+   * segments always stay resident on the device for ivpb_dense_eval. */
+  int32_t* n_seg;       /* [N]      accepted steps with h != 0 (may exceed max_segments => truncated) */
+  double* seg_x;        /* [N][max_segments][2]        xold, h of each segment           */
+  double* seg_cont;     /* [N][max_segments][c*n]      cont in the reference's layout: coefficient-major cont[k*n+i]
+                                                        (c = Method::coeffs_per_state), BDF state-major cont[i*7+k] */
 } ivpb_outputs;
 
 typedef struct ivpb_ctx ivpb_ctx;
@@ -141,6 +149,16 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
 int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0,
                             double tf, const double* d_y0, const double* d_params,
                             const ivpb_outputs* d_out, void* stream);
+
+/* Solution::sol / sol_many on the device (reference src/solve/solution.rs:25-72, ContinuousOutput::evaluate
+ * src/solve/cont.rs:82-114): evaluates the dense output retained by the most recent ivpb_solve_batch call that
+ * had dense_output = 1.  Query q: trajectory traj[q] (index into that batch), time ts[q]; y[q][n] receives the
+ * interpolated state, ok[q] = 1 if a stored segment covers ts[q] within 1e-12 (first match in step order, like
+ * the reference's linear search), else 0 and y[q] is untouched.  All pointers are HOST pointers. */
+int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok);
+/* Solution::sol_span for trajectories [first, first + count): t_start = first.xold, t_end = last.xold + last.h
+ * (src/solve/cont.rs:67-76); n_seg = segments stored (0 => no span). */
+int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg);
 
 /* Pinned host memory for y0 / params / outputs, so the H2D / D2H copies of ivpb_solve_batch run at full
  * PCIe rate and asynchronously (pageable buffers work too, but are staged by the driver). */

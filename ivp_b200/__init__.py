@@ -4,10 +4,10 @@ Public surface (mirrors reference src/prelude.rs:35-43 plus the batched call):
     Method, Status, Direction, EventConfig, Options, Solution, BatchSolution, ConfigError,
     Problem, Context, solve_ivp_batch, solve_ivp
 """
-from .types import (BatchSolution, ConfigError, Direction, EventConfig, Method, Options, Solution,  # noqa: F401
-                    Status)
+from .types import (BatchSolution, ConfigError, Direction, EventConfig, InterpolationError, Method,  # noqa: F401
+                    Options, Solution, Status)
 
-__all__ = ["BatchSolution", "ConfigError", "Direction", "EventConfig", "Method", "Options", "Solution", "Status",
+__all__ = ["InterpolationError", "BatchSolution", "ConfigError", "Direction", "EventConfig", "Method", "Options", "Solution", "Status",
            "Problem", "Context", "solve_ivp_batch", "solve_ivp", "builtin"]
 
 

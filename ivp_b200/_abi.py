@@ -42,6 +42,7 @@ class IvpbOptions(C.Structure):
         ("max_out", C.c_int32),
         ("jac_mode", C.c_int32),
         ("flags", C.c_int32),
+        ("max_segments", C.c_int32),
     ]
 
 
@@ -58,6 +59,9 @@ class IvpbOutputs(C.Structure):
         ("ev_count", c_int32_p),
         ("ev_t", c_double_p),
         ("ev_y", c_double_p),
+        ("n_seg", c_int32_p),
+        ("seg_x", c_double_p),
+        ("seg_cont", c_double_p),
     ]
 
 
@@ -66,6 +70,7 @@ _OUT_DTYPES = {
     "status": np.int32, "counters": np.uint32, "t_final": np.float64, "y_final": np.float64,
     "h_next": np.float64, "n_out": np.int32, "t_out": np.float64, "y_out": np.float64,
     "ev_count": np.int32, "ev_t": np.float64, "ev_y": np.float64,
+    "n_seg": np.int32, "seg_x": np.float64, "seg_cont": np.float64,
 }
 _PTR_TYPES = {np.dtype(np.int32): c_int32_p, np.dtype(np.uint32): c_uint32_p,
               np.dtype(np.float64): c_double_p, np.dtype(np.int64): c_int64_p}
@@ -84,17 +89,19 @@ def out_cap(opt_has_t_eval: bool, n_t_eval: int, max_out: int) -> int:
     return n_t_eval + 1 if opt_has_t_eval else max_out
 
 
-def output_shapes(N: int, n: int, n_events: int, cap: int, max_events: int) -> dict:
+def output_shapes(N: int, n: int, n_events: int, cap: int, max_events: int, seg_cap: int = 0, n_cont: int = 0) -> dict:
     return {
+        "n_seg": (N,), "seg_x": (N, seg_cap, 2), "seg_cont": (N, seg_cap, n_cont),
         "status": (N,), "counters": (N, 6), "t_final": (N,), "y_final": (N, n), "h_next": (N,),
         "n_out": (N,), "t_out": (N, cap), "y_out": (N, cap, n),
         "ev_count": (N, n_events), "ev_t": (N, n_events, max_events), "ev_y": (N, n_events, max_events, n),
     }
 
 
-def alloc_outputs(N, n, n_events, cap, max_events, want=None):
-    """Allocate host output arrays (zero-filled) for the requested fields; returns (dict, IvpbOutputs)."""
-    shapes = output_shapes(N, n, n_events, cap, max_events)
+def alloc_outputs(N, n, n_events, cap, max_events, want=None, seg_cap=0, n_cont=0):
+    """Allocate host output arrays (zero-filled) for the requested fields; returns (dict, IvpbOutputs).
+    The dense-output segment copies (n_seg, seg_x, seg_cont) are only allocated when named in `want`."""
+    shapes = output_shapes(N, n, n_events, cap, max_events, seg_cap, n_cont)
     arrays = {}
     for f in OUTPUT_FIELDS:
         if want is not None and f not in want:
@@ -103,6 +110,8 @@ def alloc_outputs(N, n, n_events, cap, max_events, want=None):
         if f in ("t_out", "y_out") and cap == 0:
             continue
         if f in ("ev_count", "ev_t", "ev_y") and n_events == 0:
+            continue
+        if f in ("n_seg", "seg_x", "seg_cont") and (seg_cap == 0 or want is None or f not in want):
             continue
         arrays[f] = np.zeros(shp, dtype=_OUT_DTYPES[f])
     st = IvpbOutputs()
@@ -153,6 +162,11 @@ class MarshalledOptions:
         o.max_out = int(opts.max_out)
         o.jac_mode = int(opts.jac_mode)
         o.flags = int(opts.flags)
+        o.max_segments = int(getattr(opts, "max_segments", 0))
+
+    @property
+    def seg_cap(self) -> int:
+        return int(self.struct.max_segments) if self.struct.dense_output else 0
 
     @property
     def cap(self) -> int:

@@ -34,7 +34,7 @@ IVPB_FLAG_NO_REFILL = 2
 ABI_SYMBOLS = [
     "ivpb_create", "ivpb_destroy", "ivpb_last_error", "ivpb_device_count", "ivpb_builtin_problem",
     "ivpb_nvrtc_problem", "ivpb_solve_batch", "ivpb_solve_batch_device", "ivpb_host_alloc", "ivpb_host_free",
-    "ivpb_launch_count", "ivpb_measure_fp64_peak", "ivpb_version",
+    "ivpb_launch_count", "ivpb_measure_fp64_peak", "ivpb_version", "ivpb_dense_eval", "ivpb_dense_span",
 ]
 
 
@@ -75,6 +75,10 @@ def load_library():
     L.ivpb_measure_fp64_peak.restype = C.c_int
     L.ivpb_measure_fp64_peak.argtypes = [vp, _abi.c_double_p]
     L.ivpb_version.restype = C.c_char_p
+    L.ivpb_dense_eval.restype = C.c_int
+    L.ivpb_dense_eval.argtypes = [vp, C.c_int64, _abi.c_int64_p, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
+    L.ivpb_dense_span.restype = C.c_int
+    L.ivpb_dense_span.argtypes = [vp, C.c_int64, C.c_int64, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
     _lib = L
     return L
 
@@ -169,6 +173,24 @@ class Context:
         self.check(self.lib.ivpb_measure_fp64_peak(self.ptr, C.byref(v)))
         return v.value
 
+    # -- dense output (Solution::sol on the device) ------------------------------------------------
+    def dense_eval(self, traj: np.ndarray, ts: np.ndarray, n: int):
+        """ivpb_dense_eval on the log retained by the last dense_output solve: (y[Q, n], ok[Q])."""
+        traj = np.ascontiguousarray(np.asarray(traj, dtype=np.int64).reshape(-1))
+        ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
+        if traj.size != ts.size:
+            raise ValueError("traj and ts must have the same length")
+        y = np.zeros((ts.size, n))
+        ok = np.zeros(ts.size, dtype=np.int32)
+        self.check(self.lib.ivpb_dense_eval(self.ptr, ts.size, _abi.ptr(traj), _abi.ptr(ts), _abi.ptr(y), _abi.ptr(ok)))
+        return y, ok.astype(bool)
+
+    def dense_span(self, first: int, count: int):
+        t0, t1 = np.zeros(count), np.zeros(count)
+        m = np.zeros(count, dtype=np.int32)
+        self.check(self.lib.ivpb_dense_span(self.ptr, int(first), int(count), _abi.ptr(t0), _abi.ptr(t1), _abi.ptr(m)))
+        return t0, t1, m
+
     # -- host buffers ---------------------------------------------------------------------------
     def solve_host(self, problem: Problem, t0: float, tf: float, y0: np.ndarray, params: Optional[np.ndarray],
                    mo: _abi.MarshalledOptions, out_struct: _abi.IvpbOutputs):
@@ -233,19 +255,24 @@ def solve_ivp_batch(problem, t0: float, tf: float, y0, params=None, options: Opt
         if par.shape != (N, problem.p):
             raise ConfigError(f"params must have shape [{N}, {problem.p}], got {par.shape}")
     mo = _abi.MarshalledOptions(options, problem.n, problem.n_events)
-    arrays, st = _abi.alloc_outputs(N, problem.n, problem.n_events, mo.cap, int(options.max_events), want)
+    n_cont = Method(options.method).coeffs_per_state() * problem.n
+    arrays, st = _abi.alloc_outputs(N, problem.n, problem.n_events, mo.cap, int(options.max_events), want,
+                                    seg_cap=mo.seg_cap, n_cont=n_cont)
     if N > 0:
         ctx.solve_host(problem, t0, tf, y0, par, mo, st)
-    return BatchSolution(n=problem.n, n_events=problem.n_events, **{k: arrays.get(k) for k in _abi.OUTPUT_FIELDS})
+    return BatchSolution(n=problem.n, n_events=problem.n_events, extras={"ctx": ctx, "dense": mo.seg_cap > 0 and N > 0},
+                         **{k: arrays.get(k) for k in _abi.OUTPUT_FIELDS})
 
 
 def solve_ivp(problem, x0: float, xend: float, y0, options: Optional[Options] = None, params=None,
               ctx: Optional[Context] = None) -> Solution:
     """Single-trajectory convenience with the reference's argument order (solve_ivp.rs:99-105)."""
     opts = options or Options()
+    import dataclasses
     if opts.t_eval is None and opts.max_out == 0:
-        import dataclasses
         opts = dataclasses.replace(opts, max_out=4096)
+    if opts.dense_output and opts.max_segments == 0:
+        opts = dataclasses.replace(opts, max_segments=4096)
     b = solve_ivp_batch(problem, x0, xend, np.asarray(y0, dtype=np.float64).reshape(1, -1),
                         None if params is None else np.asarray(params, dtype=np.float64).reshape(1, -1), opts, ctx)
     return b.solution(0)

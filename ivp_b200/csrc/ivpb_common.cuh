@@ -52,6 +52,11 @@ struct KArgs {
   int* ev_count;
   double* ev_t;
   double* ev_y;
+  // dense_output: per-trajectory interpolant log (src/solve/solout.rs:141-146); seg_cap == 0 => off
+  int seg_cap, n_cont;   // n_cont = coeffs_per_state * n doubles per segment
+  int* seg_n;
+  double* seg_x;
+  double* seg_cont;
 };
 
 // std::conditional without <type_traits> (NVRTC has no standard headers)

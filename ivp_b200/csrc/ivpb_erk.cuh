@@ -160,7 +160,7 @@ struct SolOutDev {
   static constexpr int NC = MethodTraits<METHOD>::NC;
   static constexpr double TOL = 1e-12;      // solout.rs:86
 
-  int next_idx, n_out;
+  int next_idx, n_out, n_seg;
   double last_t;                 // self.t.last()
   bool first_output_done, have_prev;
   double prev_g[NEVS];
@@ -168,7 +168,7 @@ struct SolOutDev {
   double yold[(NEV > 0) ? N : 1];
 
   __device__ __forceinline__ void reset() {
-    next_idx = 0; n_out = 0; last_t = 0.0; first_output_done = false; have_prev = false;
+    next_idx = 0; n_out = 0; n_seg = 0; last_t = 0.0; first_output_done = false; have_prev = false;
 #pragma unroll
     for (int e = 0; e < NEVS; ++e) { prev_g[e] = 0.0; hits[e] = 0; }
   }
@@ -199,6 +199,23 @@ struct SolOutDev {
   __device__ __forceinline__ bool solout(const KArgs& a, i64 idx, const double* p, bool first, double xold, double x,
                                          const double* y, const double (&cont)[NC][N], double hstep, double ixold,
                                          double& tev, double* yev) {
+    // Dense-output capture (solout.rs:141-146): every accepted step's (cont, xold, h), before the events.
+    if (a.seg_cap > 0 && !first && x != xold && hstep != 0.0) {
+      if (n_seg < a.seg_cap) {
+        const i64 sg = idx * (i64)a.seg_cap + n_seg;
+        a.seg_x[2 * sg] = ixold;
+        a.seg_x[2 * sg + 1] = hstep;
+        double* dst = a.seg_cont + sg * (i64)a.n_cont;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            if constexpr (METHOD == M_BDF) dst[i * NC + c] = cont[c][i];      // state-major (bdf.rs:506-514)
+            else dst[c * N + i] = cont[c][i];                                 // coefficient-major
+          }
+      }
+      ++n_seg;
+    }
     if constexpr (NEV > 0) {
       double g[NEV];
       Prob::events(x, y, p, g);
@@ -456,6 +473,7 @@ struct ErkTraj {
     }
     if (a.h_next) a.h_next[idx] = h;
     if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
+    if (a.seg_n) a.seg_n[idx] = so.n_seg;
     if constexpr (Out::NEV > 0) {
       if (a.ev_count) {
 #pragma unroll

@@ -365,6 +365,7 @@ struct RadauTraj {
     }
     if (a.h_next) a.h_next[idx] = h;
     if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
+    if (a.seg_n) a.seg_n[idx] = so.n_seg;
     if constexpr (Out::NEV > 0) {
       if (a.ev_count) {
 #pragma unroll
@@ -789,6 +790,7 @@ struct BdfTraj {
     }
     if (a.h_next) a.h_next[idx] = signum(a.tf - a.t0) * current_h;
     if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
+    if (a.seg_n) a.seg_n[idx] = so.n_seg;
     if constexpr (Out::NEV > 0) {
       if (a.ev_count) {
 #pragma unroll

@@ -6,6 +6,7 @@
 // CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,12 @@ static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
 #undef ROW
+// dense-output evaluation kernels (ivpb_dense.cu)
+extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
+                                              const double* seg_cont, long long M, const long long* traj, long long lo,
+                                              long long Ng, const double* ts, double* y, int* ok, cudaStream_t stream);
+extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const double* seg_x, long long first, long long count,
+                                              double* t_start, double* t_end, int* n_out, cudaStream_t stream);
 // RADAU / BDF kernels (ivpb_inst_implicit.cu)
 #define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag}
 static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
@@ -65,7 +72,7 @@ struct Buf {
 };
 
 enum { OUT_STATUS, OUT_COUNTERS, OUT_TFINAL, OUT_YFINAL, OUT_HNEXT, OUT_NOUT, OUT_TOUT, OUT_YOUT, OUT_EVCOUNT,
-       OUT_EVT, OUT_EVY, OUT_FIELDS };
+       OUT_EVT, OUT_EVY, OUT_NSEG, OUT_SEGX, OUT_SEGC, OUT_FIELDS };
 
 struct Device {
   int id = 0;
@@ -77,14 +84,18 @@ struct Device {
 };
 
 // bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
-void field_bytes(int n, int nev, int64_t cap, int max_events, size_t per[OUT_FIELDS]) {
+int coeffs_per_state(int method) {   // Method::coeffs_per_state, src/solve/options.rs:34-43
+  return method == IVPB_DOPRI5 ? 5 : method == IVPB_DOP853 ? 8 : method == IVPB_BDF ? 7 : 4;
+}
+void field_bytes(int n, int nev, int64_t cap, int max_events, int64_t seg_cap, int n_cont, size_t per[OUT_FIELDS]) {
   const size_t v[OUT_FIELDS] = {4, 24, 8, 8u * n, 8, 4, 8u * (size_t)cap, 8u * (size_t)cap * n,
-                                4u * nev, 8u * (size_t)nev * max_events, 8u * (size_t)nev * max_events * n};
+                                4u * nev, 8u * (size_t)nev * max_events, 8u * (size_t)nev * max_events * n,
+                                4, 16u * (size_t)seg_cap, 8u * (size_t)seg_cap * n_cont};
   for (int f = 0; f < OUT_FIELDS; ++f) per[f] = v[f];
 }
 void out_to_array(const ivpb_outputs* o, void* a[OUT_FIELDS]) {
   void* v[OUT_FIELDS] = {o->status, o->counters, o->t_final, o->y_final, o->h_next, o->n_out,
-                         o->t_out, o->y_out, o->ev_count, o->ev_t, o->ev_y};
+                         o->t_out, o->y_out, o->ev_count, o->ev_t, o->ev_y, o->n_seg, o->seg_x, o->seg_cont};
   for (int f = 0; f < OUT_FIELDS; ++f) a[f] = v[f];
 }
 void array_to_out(void* const a[OUT_FIELDS], ivpb_outputs* d) {
@@ -92,14 +103,24 @@ void array_to_out(void* const a[OUT_FIELDS], ivpb_outputs* d) {
   d->t_final = (double*)a[OUT_TFINAL]; d->y_final = (double*)a[OUT_YFINAL]; d->h_next = (double*)a[OUT_HNEXT];
   d->n_out = (int32_t*)a[OUT_NOUT]; d->t_out = (double*)a[OUT_TOUT]; d->y_out = (double*)a[OUT_YOUT];
   d->ev_count = (int32_t*)a[OUT_EVCOUNT]; d->ev_t = (double*)a[OUT_EVT]; d->ev_y = (double*)a[OUT_EVY];
+  d->n_seg = (int32_t*)a[OUT_NSEG]; d->seg_x = (double*)a[OUT_SEGX]; d->seg_cont = (double*)a[OUT_SEGC];
 }
 
 }  // namespace
+
+// The dense output retained by the last host-buffer solve with dense_output = 1 (ivpb_dense_eval).
+struct DenseLog {
+  bool valid = false;
+  int method = 0, n = 0, n_cont = 0, cap = 0;
+  int64_t N = 0;
+  std::vector<int64_t> lo, count;     // shard of every device
+};
 
 struct ivpb_ctx {
   std::vector<Device> devs;
   std::string err;
   uint64_t launches = 0;
+  DenseLog dense;
   std::vector<ivpb_user_problem> user;   // NVRTC problems (ivpb_nvrtc.cpp)
 };
 
@@ -163,6 +184,8 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
     return fail(ctx, IVPB_ERR_CONFIG, "n_event_cfg must be 0 or the problem's n_events");
   if (o->n_event_cfg != 0 && (!o->ev_direction || !o->ev_terminal_count))
     return fail(ctx, IVPB_ERR_CONFIG, "event config arrays are null");
+  if (o->dense_output && o->max_segments < 1)
+    return fail(ctx, IVPB_ERR_CONFIG, "dense_output needs max_segments >= 1 (interpolant segments stored per trajectory)");
   if (o->method == IVPB_RK4 && std::fabs(tf - t0) >= 1e-15) {
     // ConfigError::InvalidStepSize (src/methods/rk4.rs:84-90); h as chosen by solve_ivp.rs:185
     const double h = o->has_first_step ? o->first_step : (tf - t0) / 100.0;
@@ -196,7 +219,7 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
   return 0;
 }
 
-__global__ void zero_interval_kernel(KArgs a, int n, int nev) {
+__global__ void zero_interval_kernel(KArgs a, int n, int nev, int method) {
   // reference src/solve/solve_ivp.rs:110-145: |xend - x0| < 1e-15 => Success, nothing evaluated.
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.N) return;
@@ -223,6 +246,15 @@ __global__ void zero_interval_kernel(KArgs a, int n, int nev) {
   }
   if (a.n_out) a.n_out[i] = m;
   if (a.ev_count) for (int e = 0; e < nev; ++e) a.ev_count[i * nev + e] = 0;
+  if (a.seg_cap > 0) {   // ContinuousOutput::constant (src/solve/cont.rs:32-64): one segment at x0 with h = 1e-15
+    a.seg_n[i] = 1;
+    a.seg_x[2 * i * a.seg_cap] = a.t0;
+    a.seg_x[2 * i * a.seg_cap + 1] = 1e-15;
+    double* c = a.seg_cont + i * (long long)a.seg_cap * a.n_cont;
+    for (int k = 0; k < a.n_cont; ++k) c[k] = 0.0;
+    if (method == ivpb::M_BDF) for (int k = 0; k < n; ++k) { c[k * 7] = a.y0[i * n + k]; c[k * 7 + 6] = 1.0; }
+    else for (int k = 0; k < n; ++k) c[k] = a.y0[i * n + k];
+  }
 }
 
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
@@ -250,6 +282,8 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
   a.out_cap = o->has_t_eval ? o->n_t_eval + 1 : o->max_out;
   a.max_events = o->max_events;
   a.jac_mode = o->jac_mode;
+  a.seg_cap = o->dense_output ? o->max_segments : 0;
+  a.n_cont = coeffs_per_state(o->method) * pi.n;
   if (o->method == IVPB_RADAU) {
     // Tolerance transform and Newton tolerance of radau.rs:188-205, evaluated here with the host libm (the
     // same pow the reference calls) so every trajectory sees bit-identical scaled tolerances.
@@ -288,6 +322,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   a.status = d->status; a.counters = d->counters; a.t_final = d->t_final; a.y_final = d->y_final;
   a.h_next = d->h_next; a.n_out = d->n_out; a.t_out = d->t_out; a.y_out = d->y_out;
   a.ev_count = d->ev_count; a.ev_t = d->ev_t; a.ev_y = d->ev_y;
+  a.seg_n = d->n_seg; a.seg_x = d->seg_x; a.seg_cont = d->seg_cont;
+  if (!a.seg_n || !a.seg_x || !a.seg_cont) a.seg_cap = 0;      // nowhere to log the segments
   if (a.out_cap == 0 || (!a.t_out && !a.y_out && !a.n_out)) {
     if (!o->has_t_eval) a.out_cap = 0;    // nothing to store in step mode
   }
@@ -301,7 +337,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
 
   if (std::fabs(tf - t0) < 1e-15) {
     const int grid = (int)((N + block - 1) / block);
-    zero_interval_kernel<<<grid, block, 0, stream>>>(a, pi.n, pi.nev);
+    zero_interval_kernel<<<grid, block, 0, stream>>>(a, pi.n, pi.nev, o->method);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return 0;
@@ -318,7 +354,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
       for (int e = 0; e < pi.nev; ++e) { a.ev_dir[e] = pi.ev_dir[e]; a.ev_term[e] = pi.ev_term[e]; }
     }
   }
-  const bool want_out = o->has_t_eval || a.out_cap > 0;
+  const bool want_out = o->has_t_eval || a.out_cap > 0 || a.seg_cap > 0;
   int feat = 0;
   if (pi.nev > 0) feat = 3;            // K_OUT | K_EVENTS: events always run (they can terminate)
   else if (want_out) feat = 1;         // K_OUT
@@ -468,7 +504,8 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   const int64_t cap = opt->has_t_eval ? (int64_t)opt->n_t_eval + 1 : (int64_t)opt->max_out;
   const int n = pi.n;
   size_t per[OUT_FIELDS];
-  field_bytes(n, pi.nev, cap, opt->max_events, per);
+  const int64_t seg_cap = opt->dense_output ? opt->max_segments : 0;
+  field_bytes(n, pi.nev, cap, opt->max_events, seg_cap, coeffs_per_state(opt->method) * n, per);
   void* dst[OUT_FIELDS];
   out_to_array(d_out, dst);
   CK(cudaEventRecord(dev0.ev_ready, s0));          // inputs on device 0 are ready once s0 reaches here
@@ -490,7 +527,7 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
       if (!dst[f] || per[f] == 0) continue;
       CK(dev.out[f].ensure(per[f] * Ng));
       loc[f] = dev.out[f].p;
-      if (f >= OUT_NOUT) CK(cudaMemsetAsync(loc[f], 0, per[f] * Ng, dev.stream));
+      if ((f >= OUT_NOUT && f <= OUT_EVY) || f == OUT_NSEG) CK(cudaMemsetAsync(loc[f], 0, per[f] * Ng, dev.stream));
     }
     ivpb_outputs d;
     array_to_out(loc, &d);
@@ -525,9 +562,16 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   const int n = pi.n, nev = pi.nev, me = opt->max_events;
   // bytes per trajectory of each output field, and the host base pointers
   size_t per[OUT_FIELDS];
-  field_bytes(n, nev, cap, me, per);
+  const int64_t seg_cap = opt->dense_output ? opt->max_segments : 0;
+  const int n_cont = coeffs_per_state(opt->method) * n;
+  field_bytes(n, nev, cap, me, seg_cap, n_cont, per);
   void* host[OUT_FIELDS];
   out_to_array(out, host);
+  ctx->dense.valid = false;
+  if (seg_cap > 0) {
+    ctx->dense.method = opt->method; ctx->dense.n = n; ctx->dense.n_cont = n_cont; ctx->dense.cap = (int)seg_cap;
+    ctx->dense.N = N; ctx->dense.lo.assign(G, 0); ctx->dense.count.assign(G, 0);
+  }
   // static contiguous split [g*N/G, (g+1)*N/G) -- trajectories are independent, no exchange step
   for (int g = 0; g < G; ++g) {
     Device& dev = ctx->devs[g];
@@ -543,12 +587,17 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
     void* dptr[OUT_FIELDS];
     for (int f = 0; f < OUT_FIELDS; ++f) {
       dptr[f] = nullptr;
-      if (!host[f] || per[f] == 0) continue;
+      const bool seg_field = f >= OUT_NSEG && seg_cap > 0;      // the dense log stays on the device even if
+      if ((!host[f] && !seg_field) || per[f] == 0) continue;    // the caller wants no host copy of it
       CK(dev.out[f].ensure(per[f] * Ng));
       dptr[f] = dev.out[f].p;
     }
     ivpb_outputs d;
     array_to_out(dptr, &d);
+    if (seg_cap > 0) {
+      ctx->dense.lo[g] = lo; ctx->dense.count[g] = Ng;
+      CK(cudaMemsetAsync(d.n_seg, 0, per[OUT_NSEG] * Ng, dev.stream));
+    }
     // sample / event slots the kernel does not touch must read as zero on the host
     if (d.t_out) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
     if (d.y_out) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
@@ -560,13 +609,88 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
                               pi.p > 0 ? (const double*)dev.params.p : nullptr, &d, dev.stream))
       return rc;
     for (int f = 0; f < OUT_FIELDS; ++f) {
-      if (!dptr[f]) continue;
+      if (!dptr[f] || !host[f]) continue;
       CK(cudaMemcpyAsync((char*)host[f] + per[f] * lo, dptr[f], per[f] * Ng, cudaMemcpyDeviceToHost, dev.stream));
     }
   }
+  if (seg_cap > 0) ctx->dense.valid = true;
   for (int g = 0; g < G; ++g) {
     CK(cudaSetDevice(ctx->devs[g].id));
     CK(cudaStreamSynchronize(ctx->devs[g].stream));
+  }
+  CK(cudaSetDevice(ctx->devs[0].id));
+  return 0;
+}
+
+int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok) {
+  if (!ctx) return IVPB_ERR_CONFIG;
+  const DenseLog& L = ctx->dense;
+  if (!L.valid) return fail(ctx, IVPB_ERR_CONFIG, "no dense output retained: solve with dense_output = 1 first (InterpolationError::NotEnabled)");
+  if (n_query < 0 || (n_query > 0 && (!traj || !ts || !y || !ok))) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
+  for (int64_t q = 0; q < n_query; ++q)
+    if (traj[q] < 0 || traj[q] >= L.N) return fail(ctx, IVPB_ERR_CONFIG, "trajectory index out of range");
+  if (n_query == 0) return 0;
+  const size_t M = (size_t)n_query;
+  std::vector<double> yg;
+  std::vector<int32_t> okg;
+  for (size_t g = 0; g < ctx->devs.size(); ++g) {
+    if (L.count[g] == 0) continue;
+    Device& dev = ctx->devs[g];
+    CK(cudaSetDevice(dev.id));
+    Buf q_traj, q_ts, q_y, q_ok;
+    cudaError_t e = q_traj.ensure(8 * M);
+    if (e == cudaSuccess) e = q_ts.ensure(8 * M);
+    if (e == cudaSuccess) e = q_y.ensure(8 * M * L.n);
+    if (e == cudaSuccess) e = q_ok.ensure(4 * M);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_traj.p, traj, 8 * M, cudaMemcpyHostToDevice, dev.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_ts.p, ts, 8 * M, cudaMemcpyHostToDevice, dev.stream);
+    if (e == cudaSuccess)
+      e = ivpb_launch_dense_eval(L.method, L.n, L.n_cont, L.cap, (const int*)dev.out[OUT_NSEG].p,
+                                 (const double*)dev.out[OUT_SEGX].p, (const double*)dev.out[OUT_SEGC].p, (long long)M,
+                                 (const long long*)q_traj.p, L.lo[g], L.count[g], (const double*)q_ts.p, (double*)q_y.p,
+                                 (int*)q_ok.p, dev.stream);
+    ctx->launches += 1;
+    yg.resize(M * L.n); okg.resize(M);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(yg.data(), q_y.p, 8 * M * L.n, cudaMemcpyDeviceToHost, dev.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(okg.data(), q_ok.p, 4 * M, cudaMemcpyDeviceToHost, dev.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev.stream);
+    q_traj.release(); q_ts.release(); q_y.release(); q_ok.release();
+    if (e != cudaSuccess) return fail(ctx, IVPB_ERR_CUDA, std::string("ivpb_dense_eval: ") + cudaGetErrorString(e));
+    for (size_t q = 0; q < M; ++q) {
+      if (traj[q] < L.lo[g] || traj[q] >= L.lo[g] + L.count[g]) continue;
+      ok[q] = okg[q];
+      if (okg[q]) std::memcpy(y + q * L.n, yg.data() + q * L.n, 8 * (size_t)L.n);
+    }
+  }
+  CK(cudaSetDevice(ctx->devs[0].id));
+  return 0;
+}
+
+int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg) {
+  if (!ctx) return IVPB_ERR_CONFIG;
+  const DenseLog& L = ctx->dense;
+  if (!L.valid) return fail(ctx, IVPB_ERR_CONFIG, "no dense output retained: solve with dense_output = 1 first (InterpolationError::NotEnabled)");
+  if (first < 0 || count < 0 || first + count > L.N || !t_start || !t_end || !n_seg) return fail(ctx, IVPB_ERR_CONFIG, "bad range / null argument");
+  for (size_t g = 0; g < ctx->devs.size(); ++g) {
+    const int64_t a = std::max<int64_t>(first, L.lo[g]), b = std::min<int64_t>(first + count, L.lo[g] + L.count[g]);
+    if (b <= a) continue;
+    Device& dev = ctx->devs[g];
+    CK(cudaSetDevice(dev.id));
+    const size_t m = (size_t)(b - a);
+    Buf t0b, t1b, nb;
+    cudaError_t e = t0b.ensure(8 * m);
+    if (e == cudaSuccess) e = t1b.ensure(8 * m);
+    if (e == cudaSuccess) e = nb.ensure(4 * m);
+    if (e == cudaSuccess)
+      e = ivpb_launch_dense_span(L.cap, (const int*)dev.out[OUT_NSEG].p, (const double*)dev.out[OUT_SEGX].p, a - L.lo[g],
+                                 (long long)m, (double*)t0b.p, (double*)t1b.p, (int*)nb.p, dev.stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t_start + (a - first), t0b.p, 8 * m, cudaMemcpyDeviceToHost, dev.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t_end + (a - first), t1b.p, 8 * m, cudaMemcpyDeviceToHost, dev.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_seg + (a - first), nb.p, 4 * m, cudaMemcpyDeviceToHost, dev.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev.stream);
+    t0b.release(); t1b.release(); nb.release();
+    if (e != cudaSuccess) return fail(ctx, IVPB_ERR_CUDA, std::string("ivpb_dense_span: ") + cudaGetErrorString(e));
   }
   CK(cudaSetDevice(ctx->devs[0].id));
   return 0;

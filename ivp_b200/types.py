@@ -92,6 +92,10 @@ class ConfigError(ValueError):
     """`Error::Config` (reference src/error.rs:18-60): invalid solver parameters, detected before stepping."""
 
 
+class InterpolationError(RuntimeError):
+    """`Error::Interpolation` (src/error.rs): dense output disabled or t outside the covered span."""
+
+
 @dataclass
 class Options:
     """`Options` (options.rs:75-123).  Field names and defaults are the reference's; the trailing block
@@ -116,6 +120,7 @@ class Options:
     max_out: int = 0             # step-mode capacity of Solution.t/.y per trajectory (0 = final state only)
     jac_mode: int = 0            # 0 finite differences (ivp.rs:67-107), 1 analytic
     flags: int = 0
+    max_segments: int = 0        # dense_output: interpolant segments kept per trajectory (one per accepted step)
 
     def __post_init__(self):
         if isinstance(self.method, str):
@@ -183,7 +188,34 @@ class BatchSolution:
     ev_count: Optional[np.ndarray] = None
     ev_t: Optional[np.ndarray] = None
     ev_y: Optional[np.ndarray] = None
+    n_seg: Optional[np.ndarray] = None      # dense_output segment copies (only when asked for via `want`)
+    seg_x: Optional[np.ndarray] = None
+    seg_cont: Optional[np.ndarray] = None
     extras: dict = field(default_factory=dict)
+
+    # ---- Solution::sol / sol_many / sol_span (solution.rs:25-72), evaluated on the device ----
+    def sol_many(self, traj, ts):
+        """Dense output of trajectory `traj[q]` at `ts[q]`; returns (y[Q, n], ok[Q])."""
+        return self.extras["ctx"].dense_eval(np.asarray(traj), np.asarray(ts), self.n)
+
+    def sol(self, i: int, t: float):
+        """Solution::sol for trajectory i: InterpolationError semantics of solution.rs:25-44."""
+        span = self.sol_span(i)
+        if span is None:
+            raise InterpolationError("dense output not enabled")
+        lo, hi = min(span), max(span)
+        if t < lo or t > hi:
+            raise InterpolationError(f"t={t} outside the dense output span {span}")
+        y, ok = self.sol_many([i], [t])
+        if not ok[0]:
+            raise InterpolationError(f"t={t} outside the dense output span {span}")
+        return y[0]
+
+    def sol_span(self, i: int):
+        if "ctx" not in self.extras or not self.extras.get("dense"):
+            return None
+        t0, t1, m = self.extras["ctx"].dense_span(i, 1)
+        return (float(t0[0]), float(t1[0])) if m[0] > 0 else None
 
     def __len__(self):
         return int(self.status.shape[0])

@@ -57,6 +57,15 @@ void scatter(const Solution& S, const P&, const ivpb_options* o, const ivpb_outp
   const int64_t m = std::min<int64_t>((int64_t)S.t.size(), cap);
   if (out->t_out && m > 0) std::memcpy(out->t_out + cap * i, S.t.data(), sizeof(double) * m);
   if (out->y_out && m > 0) std::memcpy(out->y_out + cap * n * i, S.y.data(), sizeof(double) * m * n);
+  if (o->dense_output && o->max_segments > 0) {   // ContinuousOutput segments in the layout of include/ivpb.h
+    const int64_t sc = o->max_segments, nc = (int64_t)coeffs_per_state((Method)o->method) * n;
+    if (out->n_seg) out->n_seg[i] = (int32_t)S.segs.size();
+    const int64_t ms = std::min<int64_t>((int64_t)S.segs.size(), sc);
+    for (int64_t k = 0; k < ms; ++k) {
+      if (out->seg_x) { out->seg_x[(sc * i + k) * 2] = S.segs[k].xold; out->seg_x[(sc * i + k) * 2 + 1] = S.segs[k].h; }
+      if (out->seg_cont) std::memcpy(out->seg_cont + (sc * i + k) * nc, S.segs[k].cont.data(), sizeof(double) * nc);
+    }
+  }
   for (int e = 0; e < ne; ++e) {
     const int64_t k = (int64_t)S.t_events[e].size();
     if (out->ev_count) out->ev_count[(int64_t)ne * i + e] = (int32_t)k;

@@ -63,7 +63,8 @@ def solve_batch(problem: int, t0: float, tf: float, y0, params, options: Options
     if p > 0:
         par = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(N, p))
     mo = _abi.MarshalledOptions(options, n, ne)
-    arrays, st = _abi.alloc_outputs(N, n, ne, mo.cap, int(options.max_events), want)
+    n_cont = options.method.coeffs_per_state() * n
+    arrays, st = _abi.alloc_outputs(N, n, ne, mo.cap, int(options.max_events), want, seg_cap=mo.seg_cap, n_cont=n_cont)
     rc = lib().oracle_solve_batch(int(problem), C.byref(mo.struct), N, float(t0), float(tf), _abi.ptr(y0),
                                   _abi.ptr(par), C.byref(st), int(nthreads))
     if rc:

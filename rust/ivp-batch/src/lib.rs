@@ -65,14 +65,14 @@ pub struct Options {
     pub t_eval: Option<Vec<Float>>, pub first_step: Option<Float>, pub max_step: Option<Float>,
     pub min_step: Option<Float>, pub dense_output: bool,
     pub event_config: Option<Vec<EventConfig>>, pub max_events: usize, pub max_out: usize,
-    pub analytic_jac: bool, pub strict_fp: bool,
+    pub analytic_jac: bool, pub strict_fp: bool, pub max_segments: usize,
 }
 impl Options { pub fn builder() -> OptionsBuilder { OptionsBuilder(Options::default()) } }
 impl Default for Options {
     fn default() -> Self {
         Options { method: Method::DOPRI5, rtol: 1e-3.into(), atol: 1e-6.into(), max_steps: None, t_eval: None,
                   first_step: None, max_step: None, min_step: None, dense_output: false, event_config: None,
-                  max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false }
+                  max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false, max_segments: 4096 }
     }
 }
 pub struct OptionsBuilder(Options);
@@ -133,6 +133,15 @@ impl Problem {
     }
 }
 
+/// `Solution::sol_many` for trajectory `index` of the last dense_output solve (evaluated on the device).
+pub fn sol_many(ctx: &Context, index: usize, n: usize, ts: &[Float]) -> Result<Vec<Vec<Float>>, Error> {
+    let traj = vec![index as i64; ts.len()];
+    let mut y = vec![0.0; ts.len() * n]; let mut ok = vec![0i32; ts.len()];
+    let rc = unsafe { sys::ivpb_dense_eval(ctx.raw, ts.len() as i64, traj.as_ptr(), ts.as_ptr(), y.as_mut_ptr(), ok.as_mut_ptr()) };
+    if rc != sys::IVPB_OK || ok.iter().any(|&k| k == 0) { return Err(Error::Config("t outside the dense output span (InterpolationError)".into())); }
+    Ok(y.chunks(n).map(|c| c.to_vec()).collect())
+}
+
 /// `y0` is `[N x n]` row-major, `params` `[N x p]` row-major.  One `Solution` per trajectory.
 pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[Float], params: &[Float], options: Options)
                        -> Result<Vec<Solution>, Error> {
@@ -161,6 +170,7 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         ev_terminal_count: if terms.is_empty() { ptr::null() } else { terms.as_ptr() },
         max_events: if ne > 0 { options.max_events as i32 } else { 0 }, max_out: options.max_out as i32,
         jac_mode: options.analytic_jac as i32, flags: if options.strict_fp { sys::IVPB_FLAG_STRICT_FP } else { 0 },
+        max_segments: if options.dense_output { options.max_segments as i32 } else { 0 },
     };
     let cap = te.map_or(options.max_out, |t| t.len() + 1);
     let me = o.max_events as usize;
@@ -175,6 +185,7 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         t_out: if cap > 0 { t_out.as_mut_ptr() } else { ptr::null_mut() }, y_out: if cap > 0 { y_out.as_mut_ptr() } else { ptr::null_mut() },
         ev_count: if ne > 0 { ev_count.as_mut_ptr() } else { ptr::null_mut() },
         ev_t: if ne > 0 { ev_t.as_mut_ptr() } else { ptr::null_mut() }, ev_y: if ne > 0 { ev_y.as_mut_ptr() } else { ptr::null_mut() },
+        n_seg: ptr::null_mut(), seg_x: ptr::null_mut(), seg_cont: ptr::null_mut(),   // the dense log stays on the device
     };
     let rc = unsafe { sys::ivpb_solve_batch(ctx.raw, f.handle, &o, big_n as i64, t0, tf, y0.as_ptr(),
                                             if f.p > 0 { params.as_ptr() } else { ptr::null() }, &out) };

@@ -155,6 +155,43 @@ static void backward_integration_works() {
   }
 }
 
+// ---- tests/ivp.rs:106-149, tests/backward_and_bounds.rs:6-31 (dense output) -------------------------------
+static void dense_output_tests() {
+  Problem sho = Problem::builtin("sho");
+  for (Method m : {Method::RK23, Method::DOPRI5, Method::DOP853, Method::RADAU}) {
+    Options o = Options::builder().method(m).rtol(1e-8).atol(1e-10).dense_output(true).build();
+    Solution sol = solve_ivp(sho, 0.0, 2.0, {1.0, 0.0}, o);
+    CHECK(sol.sol_span().has_value(), "%s: span exists", name(m));
+    auto ys = sol.sol_many(sol.t);
+    CHECK(ys.size() == sol.y.size(), "%s", name(m));
+    for (size_t k = 0; k < ys.size(); ++k)
+      for (size_t c = 0; c < ys[k].size(); ++c) CHECK(std::fabs(ys[k][c] - sol.y[k][c]) <= 1e-8, "dense vs stored mismatch (%s)", name(m));
+  }
+  {
+    Solution sol = solve_ivp(sho, 0.0, 1.0, {1.0, 0.0}, Options::builder().method(Method::DOPRI5).rtol(1e-9).atol(1e-9).dense_output(true).build());
+    auto span = *sol.sol_span();
+    int errs = 0;
+    try { sol.sol(span.first - 0.1); } catch (const InterpolationError&) { ++errs; }
+    try { sol.sol(span.second + 0.1); } catch (const InterpolationError&) { ++errs; }
+    CHECK(errs == 2, "out-of-range dense evaluation is an error");
+    Solution plain = solve_ivp(sho, 0.0, 1.0, {1.0, 0.0}, default_opts(Method::DOPRI5));
+    bool threw = false;
+    try { plain.sol(0.5); } catch (const InterpolationError&) { threw = true; }
+    CHECK(threw && !plain.sol_span(), "dense output disabled => NotEnabled");
+  }
+  const double x0 = 2.0 * std::acos(-1.0);
+  for (Method m : all_methods()) {
+    Solution sol = solve_ivp(sho, x0, 0.0, {1.0, 0.0}, Options::builder().method(m).rtol(1e-9).atol(1e-9).dense_output(true).build());
+    auto span = sol.sol_span();
+    CHECK(span && span->first > span->second, "%s: backward span", name(m));
+    if (span) {
+      const double mid = 0.5 * (span->first + span->second);
+      auto y = sol.sol(mid);
+      CHECK(std::fabs(y[0] - std::cos(mid)) < 1e-6 && std::fabs(y[1] + std::sin(mid)) < 1e-6, "%s: dense mid point", name(m));
+    }
+  }
+}
+
 // ---- examples/bouncing_ball.rs, examples/van_der_pol.rs, examples/cr3bp.rs as batches ----------------------
 static void example_programs_as_batches() {
   const size_t N = 1000;
@@ -213,6 +250,7 @@ int main(int argc, char** argv) {
     vector_rtol_componentwise_control();
     harmonic_accuracy_and_t_eval();
     backward_integration_works();
+    dense_output_tests();
     example_programs_as_batches();
   }
   std::printf("%d checks, %d failed\n", g_checks, g_fail);

@@ -561,3 +561,68 @@ def test_nvrtc_user_problem_implicit(oracle, method, jac_mode):
     g = ib.solve_ivp_batch(user, t0, tf, y0, par, opts)
     o = oracle.solve_batch(PROBLEMS[prob], t0, tf, y0, par, opts, nthreads=8)
     exact(g, o)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dense_output: per-trajectory segment log on the device + Solution::sol / sol_many / sol_span
+
+@pytest.mark.parametrize("method", [Method.RK23, Method.DOPRI5, Method.DOP853, Method.RK4, Method.RADAU, Method.BDF])
+@pytest.mark.parametrize("backward", [False, True])
+def test_dense_output_segments_and_sol_match_oracle(oracle, method, backward):
+    N = 65
+    y0 = np.tile([1.0, 0.0], (N, 1)) * (1.0 + 0.01 * np.arange(N))[:, None]
+    t0, tf = (0.0, 2.0) if not backward else (2.0, 0.0)
+    # RK4: default h = (tf - t0) / 100 (solve_ivp.rs:185); an explicit negative first_step would trigger the
+    # reference's `x0 + direction * first_step` output quirk (solout.rs:392-421) and sample outside the span
+    kw = {} if method == Method.RK4 else dict(rtol=1e-8, atol=1e-10)
+    opts = Options(method=method, dense_output=True, max_segments=512, max_out=512, flags=IVPB_FLAG_STRICT_FP, **kw)
+    want = ["status", "counters", "t_final", "y_final", "n_out", "t_out", "y_out", "n_seg", "seg_x", "seg_cont"]
+    g = ib.solve_ivp_batch("sho", t0, tf, y0, None, opts, want=want)
+    o = oracle.solve_batch(PROBLEMS["sho"], t0, tf, y0, None, opts, want=want)
+    # the segment log is the reference's ContinuousOutput, bit for bit (strict build)
+    assert np.array_equal(g.n_seg, o.n_seg) and np.all(g.n_seg == g.naccpt if method != Method.RK4 else g.n_seg == g.nstep)
+    valid = np.arange(512)[None, :] < g.n_seg[:, None]        # slots past n_seg are not initialised on the device
+    assert np.array_equal(g.seg_x[valid], o.seg_x[valid]) and np.array_equal(g.seg_cont[valid], o.seg_cont[valid])
+    # reference tests/ivp.rs:106-136: dense evaluation at the stored sample times reproduces the samples
+    for i in (0, 17, N - 1):
+        m = int(g.n_out[i])
+        y, ok = g.sol_many([i] * m, g.t_out[i, :m])
+        assert ok.all() and np.abs(y - g.y_out[i, :m]).max() <= 1e-8
+        span = g.sol_span(i)
+        assert span is not None and ((span[0] > span[1]) == backward)        # tests/backward_and_bounds.rs:17-19
+        ys, oks, ospan = oracle.dense_eval(PROBLEMS["sho"], t0, tf, y0[i], None, opts, np.linspace(t0, tf, 41))
+        yg, okg = g.sol_many([i] * 41, np.linspace(t0, tf, 41))
+        assert np.array_equal(okg, oks) and np.array_equal(yg[okg], ys[oks]) and span == ospan
+        mid = 0.5 * (t0 + tf)
+        assert np.abs(g.sol(i, mid) - (1.0 + 0.01 * i) * np.array([np.cos(mid - t0), -np.sin(mid - t0)])).max() < 1e-6
+        # tests/ivp.rs:138-149: outside the span is an error
+        lo, hi = min(span), max(span)
+        for bad in (lo - 0.1, hi + 0.1):
+            with pytest.raises(ib.InterpolationError):
+                g.sol(i, bad)
+
+
+def test_dense_output_fma_build_truncation_and_zero_interval(oracle):
+    prob, y0, par, t0, tf = synth.ensemble("vdp", 300)
+    opts = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, dense_output=True, max_segments=1024)
+    g = ib.solve_ivp_batch(prob, t0, 20.0, y0, par, opts, want=["status", "counters", "t_final", "y_final", "n_seg"])
+    assert np.array_equal(g.n_seg, g.naccpt)
+    q = np.repeat(np.arange(300), 5)
+    ts = np.tile(np.linspace(0.5, 19.5, 5), 300)
+    y, ok = g.sol_many(q, ts)
+    assert ok.all()
+    for i in (0, 123, 299):          # against the oracle's own dense output, within the north-star tolerance
+        ys, oks, _ = oracle.dense_eval(PROBLEMS[prob], t0, 20.0, y0[i], par[i], opts, np.linspace(0.5, 19.5, 5))
+        assert close(y[q == i], ys, 1e-8, 1e-8).all()
+    # capacity exceeded: n_seg reports the true count, queries beyond the stored segments answer ok = 0
+    small = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, dense_output=True, max_segments=8)
+    h = ib.solve_ivp_batch(prob, t0, 20.0, y0[:4], par[:4], small, want=["status", "counters", "t_final", "y_final", "n_seg"])
+    assert np.all(h.n_seg > 8)
+    _, ok2 = h.sol_many([0, 0], [1e-3, 19.0])
+    assert ok2[0] and not ok2[1]
+    # zero interval: ContinuousOutput::constant (cont.rs:32-64)
+    z = ib.solve_ivp_batch("sho", 1.5, 1.5, np.array([[2.0, 3.0]]), None, Options(method=Method.BDF, dense_output=True, max_segments=4))
+    yz, okz = z.sol_many([0], [1.5])
+    assert okz[0] and np.array_equal(yz[0], [2.0, 3.0])
+    with pytest.raises(ib.ConfigError):
+        ib.solve_ivp_batch("sho", 0.0, 1.0, np.array([[1.0, 0.0]]), None, Options(dense_output=True))   # max_segments missing

@@ -203,7 +203,7 @@ def test_vdp_against_scipy(oracle, method, scipy_name):
 
 def test_abi_struct_sizes():
     import ctypes
-    assert ctypes.sizeof(_abi.IvpbOutputs) == 11 * 8
+    assert ctypes.sizeof(_abi.IvpbOutputs) == 14 * 8
 
 
 # ----------------------------------------------------------------------------------------------
