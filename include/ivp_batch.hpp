@@ -221,10 +221,10 @@ class Context {
 class Problem {
  public:
   // Built-in problems (ivpb_builtin in ivpb.h): "decay", "vdp_eps", "vdp_mu", "lorenz", "cr3bp",
-  // "bouncing_ball", "robertson", "sho", "zero3", "exp2", "rational", "cannon".
+  // "bouncing_ball", "robertson", "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64".
   static Problem builtin(const std::string& name) {
     static const char* names[] = {"decay", "vdp_eps", "vdp_mu", "lorenz", "cr3bp", "bouncing_ball", "robertson",
-                                  "sho", "zero3", "exp2", "rational", "cannon"};
+                                  "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64"};
     for (int i = 0; i < IVPB_P_BUILTIN_COUNT; ++i)
       if (name == names[i]) {
         Problem p;

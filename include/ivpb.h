@@ -54,7 +54,9 @@ typedef enum {
   IVPB_P_EXP2 = 9,       /* y' = y          n=2 p=0                         reference tests/ivp.rs:291-297 */
   IVPB_P_RATIONAL = 10,  /* n=2 p=0                                         reference tests/test_helpers.py:23-25 */
   IVPB_P_CANNON = 11,    /* y' = [y1, -9.80665] n=2 p=0; event y[0], terminal, negative  reference tests/test_ivp.py:153-160 */
-  IVPB_P_BUILTIN_COUNT = 12
+  IVPB_P_LINEAR100 = 12, /* y' = -y         n=100 p=0 (warp-per-trajectory kernels)     reference benches/benchmark.py:39-41,137-146 */
+  IVPB_P_MEDAKZO64 = 13, /* MEDAKZO on 32 grid points  n=64 p=0                      reference tests/test_ivp.py:77-101 */
+  IVPB_P_BUILTIN_COUNT = 14
 } ivpb_builtin;
 
 /* Mirrors `Options` (reference src/solve/options.rs:75-123) plus the per-event `EventConfig`

@@ -24,7 +24,7 @@ _lib = None
 #: Built-in problems (include/ivpb.h `ivpb_builtin`).
 PROBLEMS = {
     "decay": 0, "vdp_eps": 1, "vdp_mu": 2, "lorenz": 3, "cr3bp": 4, "bouncing_ball": 5, "robertson": 6,
-    "sho": 7, "zero3": 8, "exp2": 9, "rational": 10, "cannon": 11,
+    "sho": 7, "zero3": 8, "exp2": 9, "rational": 10, "cannon": 11, "linear100": 12, "medakzo64": 13,
 }
 
 IVPB_FLAG_STRICT_FP = 1

@@ -31,6 +31,8 @@ struct KArgs {
   const double* params;  // [N][p] row-major (may be null when p == 0)
   u64* queue;            // work-queue head (atomicAdd), zeroed before launch
   double rtol[MAX_N], atol[MAX_N];   // scalar tolerances are broadcast by the host
+  const double* rtol_ext;            // n > MAX_N with Tolerance::Vector: device arrays [n] (else null: rtol[0])
+  const double* atol_ext;
   double first_step, max_step, min_step;
   int has_first_step, has_max_step, has_min_step, static_sched;
   u64 max_steps;         // usize::MAX when Options.max_steps is None

@@ -114,35 +114,118 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Layout policies: how a state vector is spread over threads.
+//   ThreadLayout  one trajectory per thread, every vector a register array of N (n <= 32).
+//   WarpLayout    one trajectory per warp (n > 32): component i lives in lane i % 32, slot i / 32; the RHS sees
+//                 the full state through a per-warp shared-memory row, norms are reduced with shuffles (fast
+//                 build) or summed in index order from shared memory (strict build: the reference's sequential
+//                 `err += q * q`, bit for bit).  All control flow is warp-uniform.
+// The step code below is written once against this interface; with ThreadLayout everything folds away.
+template <class Prob>
+struct ThreadLayout {
+  static constexpr int N = Prob::N, NL = Prob::N;
+  static constexpr bool WARP = false;
+  static __device__ __forceinline__ int gi(int i) { return i; }
+  static __device__ __forceinline__ bool valid(int) { return true; }
+  static __device__ __forceinline__ bool leader() { return true; }
+  static __device__ __forceinline__ double rtol(const KArgs& a, int i) { return a.rtol[i]; }
+  static __device__ __forceinline__ double atol(const KArgs& a, int i) { return a.atol[i]; }
+  static __device__ __forceinline__ double sumsq(const double (&q)[NL]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) acc = IVPB_MA(q[i], q[i], acc);
+    return acc;
+  }
+  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { Prob::ode(t, y, p, d); }
+  static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { Prob::events(t, y, p, g); }
+};
+
+template <class Prob>
+struct WarpLayout {
+  static constexpr int N = Prob::N, NL = (Prob::N + 31) / 32;
+  static constexpr bool WARP = true;
+  static constexpr int SMEM_DOUBLES_PER_WARP = 2 * Prob::N;      // full state row + reduction scratch
+  static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+  static __device__ __forceinline__ int gi(int i) { return lane() + 32 * i; }
+  static __device__ __forceinline__ bool valid(int i) { return gi(i) < N; }
+  static __device__ __forceinline__ bool leader() { return lane() == 0; }
+  static __device__ __forceinline__ double* row() {
+    extern __shared__ double ivpb_smem[];
+    return ivpb_smem + (threadIdx.x >> 5) * SMEM_DOUBLES_PER_WARP;
+  }
+  static __device__ __forceinline__ double rtol(const KArgs& a, int i) { return a.rtol_ext ? a.rtol_ext[valid(i) ? gi(i) : 0] : a.rtol[0]; }
+  static __device__ __forceinline__ double atol(const KArgs& a, int i) { return a.atol_ext ? a.atol_ext[valid(i) ? gi(i) : 0] : a.atol[0]; }
+  static __device__ __forceinline__ double sumsq(const double (&q)[NL]) {
+#ifdef IVPB_STRICT
+    double* sc = row() + N;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) if (valid(i)) sc[gi(i)] = q[i] * q[i];
+    __syncwarp();
+    double acc = 0.0;
+    for (int i = 0; i < N; ++i) acc = acc + sc[i];
+    __syncwarp();
+    return acc;
+#else
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) if (valid(i)) acc = fma(q[i], q[i], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    return acc;
+#endif
+  }
+  // publish a distributed vector as a full row in shared memory
+  static __device__ __forceinline__ const double* full(const double* y) {
+    double* r = row();
+#pragma unroll
+    for (int i = 0; i < NL; ++i) if (valid(i)) r[gi(i)] = y[i];
+    __syncwarp();
+    return r;
+  }
+  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) {
+    const double* ys = full(y);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) d[i] = valid(i) ? Prob::ode_i(t, ys, p, gi(i)) : 0.0;
+    __syncwarp();
+  }
+  static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) {
+    const double* ys = full(y);
+    Prob::events(t, ys, p, g);
+    __syncwarp();
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // hinit -- reference src/methods/mod.rs:217-281 (initial step guess; one extra RHS call; the final
 // min(|h|, 100|h|, h1, hmax) keeps the reference's extra |h| term, mod.rs:279)
-template <class Prob, int IORD>
+template <class Prob, int IORD, class L = ThreadLayout<Prob>>
 __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const double* y, const double* f0,
                                             const double* p, double posneg, double hmax) {
-  constexpr int N = Prob::N;
-  double dnf = 0.0, dny = 0.0;
+  constexpr int N = L::NL;
+  double qf[N], qy[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double sk = IVPB_MA(a.rtol[i], fabs(y[i]), a.atol[i]);
-    const double qf = f0[i] / sk, qy = y[i] / sk;
-    dnf = IVPB_MA(qf, qf, dnf);
-    dny = IVPB_MA(qy, qy, dny);
+    const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
+    qf[i] = L::valid(i) ? f0[i] / sk : 0.0;
+    qy[i] = L::valid(i) ? y[i] / sk : 0.0;
   }
+  // interleaved in the reference (dnf, dny in one loop); the two sums are independent
+  const double dnf = L::sumsq(qf), dny = L::sumsq(qy);
   double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
   if (hh > fabs(hmax)) hh = fabs(hmax);
   hh = fabs(hh) * signum(posneg);
   double y1[N], f1[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) y1[i] = IVPB_MA(hh, f0[i], y[i]);
-  Prob::ode(x + hh, y1, p, f1);
-  double der2 = 0.0;
+  L::ode(x + hh, y1, p, f1);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double sk = IVPB_MA(a.rtol[i], fabs(y[i]), a.atol[i]);
-    const double df = (f1[i] - f0[i]) / sk;
-    der2 = IVPB_MA(df, df, der2);
+    const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
+    qf[i] = L::valid(i) ? (f1[i] - f0[i]) / sk : 0.0;
   }
+  double der2 = L::sumsq(qf);
   der2 = sqrt(der2) / fabs(hh);
   const double der12 = fmax(fabs(der2), sqrt(dnf));
   const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(0.01 / der12, 1.0 / (double)IORD);
@@ -152,9 +235,10 @@ __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const doub
 
 // ---------------------------------------------------------------------------------------------
 // Device DefaultSolOut (reference src/solve/solout.rs:15-432), state kept per thread.
-template <class Prob, int METHOD, int FEAT>
+template <class Prob, int METHOD, int FEAT, class L = ThreadLayout<Prob>>
 struct SolOutDev {
-  static constexpr int N = Prob::N;
+  static constexpr int N = L::NL;          // local slice of the state (== Prob::N for ThreadLayout)
+  static constexpr int NG = Prob::N;       // global state size
   static constexpr int NEV = (FEAT & K_EVENTS) ? Prob::NEV : 0;
   static constexpr int NEVS = NEV > 0 ? NEV : 1;
   static constexpr int NC = MethodTraits<METHOD>::NC;
@@ -176,10 +260,10 @@ struct SolOutDev {
   __device__ __forceinline__ void push(const KArgs& a, i64 idx, double t, const double* yv) {
     if (n_out < a.out_cap) {
       const i64 o = idx * (i64)a.out_cap + n_out;
-      if (a.t_out) a.t_out[o] = t;
+      if (a.t_out && L::leader()) a.t_out[o] = t;
       if (a.y_out) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) a.y_out[o * N + i] = yv[i];
+        for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_out[o * NG + L::gi(i)] = yv[i];
       }
     }
     last_t = t;
@@ -203,22 +287,22 @@ struct SolOutDev {
     if (a.seg_cap > 0 && !first && x != xold && hstep != 0.0) {
       if (n_seg < a.seg_cap) {
         const i64 sg = idx * (i64)a.seg_cap + n_seg;
-        a.seg_x[2 * sg] = ixold;
-        a.seg_x[2 * sg + 1] = hstep;
+        if (L::leader()) { a.seg_x[2 * sg] = ixold; a.seg_x[2 * sg + 1] = hstep; }
         double* dst = a.seg_cont + sg * (i64)a.n_cont;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            if constexpr (METHOD == M_BDF) dst[i * NC + c] = cont[c][i];      // state-major (bdf.rs:506-514)
-            else dst[c * N + i] = cont[c][i];                                 // coefficient-major
+            if (!L::valid(i)) continue;
+            if constexpr (METHOD == M_BDF) dst[L::gi(i) * NC + c] = cont[c][i];      // state-major (bdf.rs:506-514)
+            else dst[c * NG + L::gi(i)] = cont[c][i];                                // coefficient-major
           }
       }
       ++n_seg;
     }
     if constexpr (NEV > 0) {
       double g[NEV];
-      Prob::events(x, y, p, g);
+      L::events(x, y, p, g);
       if (!have_prev) {            // solout.rs:163-164 (yold.is_empty())
 #pragma unroll
         for (int e = 0; e < NEV; ++e) prev_g[e] = g[e];
@@ -267,7 +351,7 @@ struct SolOutDev {
               if (fabs(d) > tol1) b += d;
               else b += (xm > 0.0 ? tol1 : -tol1);
               erk_interp<METHOD, N>(b, ey, cont, ixold, hstep);
-              Prob::events(b, ey, p, gm);
+              L::events(b, ey, p, gm);
               fb = gm[e];
             }
             erk_interp<METHOD, N>(b, ey, cont, ixold, hstep);
@@ -308,10 +392,10 @@ struct SolOutDev {
             if (det_i[j] != e) continue;
             if (hits[e] < a.max_events) {
               const i64 o = (idx * NEV + e) * (i64)a.max_events + hits[e];
-              if (a.ev_t) a.ev_t[o] = det_t[j];
+              if (a.ev_t && L::leader()) a.ev_t[o] = det_t[j];
               if (a.ev_y) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) a.ev_y[o * N + i] = det_y[j][i];
+                for (int i = 0; i < N; ++i) if (L::valid(i)) a.ev_y[o * NG + L::gi(i)] = det_y[j][i];
               }
             }
             hits[e] += 1;
@@ -382,13 +466,13 @@ struct SolOutDev {
 
 // ---------------------------------------------------------------------------------------------
 // Per-thread trajectory state + the step loops.
-template <class Prob, int METHOD, int FEAT>
+template <class Prob, int METHOD, int FEAT, class L = ThreadLayout<Prob>>
 struct ErkTraj {
-  static constexpr int N = Prob::N, P = Prob::P;
+  static constexpr int N = L::NL, NG = Prob::N, P = Prob::P;     // N: local slice (== NG for ThreadLayout)
   static constexpr int PS = P > 0 ? P : 1;
   static constexpr bool DENSE = FEAT != 0;
   static constexpr int NC = MethodTraits<METHOD>::NC;
-  using Out = SolOutDev<Prob, METHOD, FEAT>;
+  using Out = SolOutDev<Prob, METHOD, FEAT, L>;
 
   i64 idx;
   double x, h;
@@ -404,11 +488,11 @@ struct ErkTraj {
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = yev[i];
   }
-  __device__ __forceinline__ double rt(const KArgs& a, int i) const { return a.rtol[i]; }
-  __device__ __forceinline__ double at(const KArgs& a, int i) const { return a.atol[i]; }
+  __device__ __forceinline__ double rt(const KArgs& a, int i) const { return L::rtol(a, i); }
+  __device__ __forceinline__ double at(const KArgs& a, int i) const { return L::atol(a, i); }
 
   __device__ __forceinline__ double hinit(const KArgs& a, double posneg, double hmax) {
-    return hinit_dev<Prob, MethodTraits<METHOD>::IORD>(a, x, y, k1, p, posneg, hmax);
+    return hinit_dev<Prob, MethodTraits<METHOD>::IORD, L>(a, x, y, k1, p, posneg, hmax);
   }
 
   __device__ __forceinline__ double hmax_of(const KArgs& a) const {
@@ -422,7 +506,7 @@ struct ErkTraj {
     idx = index;
     x = a.t0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = a.y0[index * N + i];
+    for (int i = 0; i < N; ++i) y[i] = L::valid(i) ? a.y0[index * NG + L::gi(i)] : 0.0;
     if constexpr (P > 0) {
 #pragma unroll
       for (int i = 0; i < P; ++i) p[i] = a.params[index * P + i];
@@ -438,7 +522,7 @@ struct ErkTraj {
     last = false; reject = false;
     so.reset();
     const double posneg = signum(a.tf - a.t0);
-    Prob::ode(x, y, p, k1);
+    L::ode(x, y, p, k1);
     if constexpr (METHOD == M_RK4) {
       h = a.has_first_step ? a.first_step : (a.tf - a.t0) / 100.0;    // solve_ivp.rs:185; rk4.rs:116 (not counted)
     } else {
@@ -461,16 +545,17 @@ struct ErkTraj {
   // Write the per-trajectory results.  (x, y) is the integrator's last accepted point, or the event point
   // when a terminal event interrupted the integration (step() moves it there).
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if (a.y_final) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_final[idx * NG + L::gi(i)] = y[i];
+    }
+    if (!L::leader()) return;                 // per-trajectory scalars: one writer
     if (a.status) a.status[idx] = status;
     if (a.counters) {
       u32* c = a.counters + idx * 6;
       c[0] = nfev; c[1] = 0u; c[2] = 0u; c[3] = nstep; c[4] = naccpt; c[5] = nrejct;
     }
     if (a.t_final) a.t_final[idx] = x;
-    if (a.y_final) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) a.y_final[idx * N + i] = y[i];
-    }
     if (a.h_next) a.h_next[idx] = h;
     if (a.n_out) a.n_out[idx] = a.out_cap > 0 ? so.n_out : 0;
     if (a.seg_n) a.seg_n[idx] = so.n_seg;
@@ -491,8 +576,8 @@ struct ErkTraj {
   double acc = (COEF)[0] * (KARR)[(SLOT)[0]][i];                                  \
   _Pragma("unroll") for (int j_ = 1; j_ < 9; ++j_) if (j_ < (LEN)) acc = IVPB_MA((COEF)[j_], (KARR)[(SLOT)[j_]][i], acc);
 
-template <class Prob, int METHOD, int FEAT>
-__device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a) {
+template <class Prob, int METHOD, int FEAT, class L>
+__device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs& a) {
   const double xend = a.tf;
   const double posneg = signum(a.tf - a.t0);
   double tev = 0.0, yev[N];
@@ -524,7 +609,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         }
       }
       const double ts = (s == 10) ? (x + h) : IVPB_MA(D853_STG_C[s], h, x);
-      Prob::ode(ts, y1, p, k[STG_OUT[s]]);
+      L::ode(ts, y1, p, k[STG_OUT[s]]);
     }
     const double xph = x + h;
     nfev += 11;
@@ -535,7 +620,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       k[3][i] = acc;
       k[4][i] = IVPB_MA(h, acc, y[i]);
     }
-    double err = 0.0, err2 = 0.0;
+    double qe1[N], qe2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #ifdef IVPB_STRICT
@@ -552,13 +637,14 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       const double rsk = fm::rcp(sk);                      // one reciprocal shared by both norms
       const double q2 = erri * rsk, q1 = e8 * rsk;
 #endif
-      err2 = IVPB_MA(q2, q2, err2);
-      err = IVPB_MA(q1, q1, err);
+      qe2[i] = L::valid(i) ? q2 : 0.0;
+      qe1[i] = L::valid(i) ? q1 : 0.0;
     }
+    double err2 = L::sumsq(qe2), err = L::sumsq(qe1);
     double deno = IVPB_MA(0.01, err2, err);
     if (deno <= 0.0) deno = 1.0;
 #ifdef IVPB_STRICT
-    err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
+    err = fabs(h) * err * sqrt(1.0 / ((double)NG * deno));
     const double fac11 = ivpb_libm_pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
     // facold^beta == 1 exactly (beta = 0), so fac = fac11 (dop853.rs:434)
     const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
@@ -567,7 +653,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #else
     // Same controller written with the reciprocal step factor 1/fac = safe * err^(-1/8), which needs
     // multiplications only (see ivpb_fastmath.cuh): hnew = h * clamp(safe/fac11, 1/facc1, 1/facc2).
-    err = fabs(h) * err * fm::rsqrt((double)N * deno);
+    err = fabs(h) * err * fm::rsqrt((double)NG * deno);
     const double ratio = safe * fm::rroot8(err);
     double hnew = h * fm::minsel(fm::maxsel(ratio, 0.333), 6.0);
     const double hrej = h * fm::maxsel(ratio, 0.333);
@@ -577,15 +663,13 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     if (err <= 1.0) {
       facold = fmax(err, 1.0e-4);
       naccpt += 1;
-      Prob::ode(xph, k[4], p, k[3]);
+      L::ode(xph, k[4], p, k[3]);
       nfev += 1;
       if ((naccpt % 1000u == 0u) || (iasti > 0)) {            // stiffness detection, dop853.rs:447-472
-        double stnum = 0.0, stden = 0.0;
+        double sd1[N], sd2[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const double d1 = k[3][i] - k[2][i], d2 = k[4][i] - y1[i];
-          stnum = IVPB_MA(d1, d1, stnum); stden = IVPB_MA(d2, d2, stden);
-        }
+        for (int i = 0; i < N; ++i) { sd1[i] = k[3][i] - k[2][i]; sd2[i] = k[4][i] - y1[i]; }
+        const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 6.1) {
           nonstiff = 0; iasti += 1;
@@ -621,7 +705,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
             IVPB_LINCOMB(acc, DSTG_LEN[s], DSTG_SLOT[s], D853_DSTG_COEF[s], k, i)
             y1[i] = IVPB_MA(h, acc, y[i]);
           }
-          Prob::ode(IVPB_MA(D853_DSTG_C[s], h, x), y1, p, k[DSTG_OUT[s]]);
+          L::ode(IVPB_MA(D853_DSTG_C[s], h, x), y1, p, k[DSTG_OUT[s]]);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -689,7 +773,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         }
       }
       const double ts = (s >= 4) ? xph : IVPB_MA(D5_S_C[s], h, x);
-      Prob::ode(ts, y1, p, k[S_OUT[s]]);
+      L::ode(ts, y1, p, k[S_OUT[s]]);
     }
     nfev += 6;
     double cont[NC][N];
@@ -702,7 +786,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
         cont[4][i] = h * acc;
       }
     }
-    double err = 0.0;
+    double qe[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {                                // k4 <- scaled error vector, dopri5.rs:337-340
       double acc = D5_E_COEF[0] * k[ED_SLOT[0]][i];
@@ -712,15 +796,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
       const double q = k[3][i] / sk;
-      err += q * q;
 #else
       const double sk = fma(rt(a, i), fm::maxsel(fabs(y[i]), fabs(y1[i])), at(a, i));
       const double q = k[3][i] * fm::rcp(sk);
-      err = fma(q, q, err);
 #endif
+      qe[i] = L::valid(i) ? q : 0.0;
     }
+    double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = sqrt(err / (double)N);
+    err = sqrt(err / (double)NG);
     const double fac11 = ivpb_libm_pow(err, expo1);
     double fac = fac11 / ivpb_libm_pow(facold, beta);
     fac = fmax(facc2, fmin(facc1, fac / safe));
@@ -729,7 +813,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #else
     // Same PI controller in log space: err = sqrt(e2), so log(err) = log(e2)/2 needs no square root, and
     // log(facold) is carried from the previous accepted step (facold holds log(max(err, 1e-4)) in this build).
-    const double e2 = err * (1.0 / (double)N);
+    const double e2 = err * (1.0 / (double)NG);
     const double lerr = 0.5 * log(e2);
     double hnew = h * fm::minsel(fm::maxsel(safe * exp(fma(beta, facold, -(expo1 * lerr))), 0.2), 10.0);
     const bool accept = e2 <= 1.0;
@@ -744,17 +828,17 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #endif
       naccpt += 1;
       if ((naccpt % 1000u == 0u) || (iasti > 0)) {              // dopri5.rs:364-391 (uses overwritten k4: quirk kept)
-        double stnum = 0.0, stden = 0.0;
+        double sd1[N], sd2[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const double d1 = k[1][i] - k[5][i];
+          sd1[i] = k[1][i] - k[5][i];
           double sacc = D5_S_COEF[4][0] * k[0][i];
 #pragma unroll
           for (int j = 1; j < 5; ++j) sacc = IVPB_MA(D5_S_COEF[4][j], k[j][i], sacc);
           const double ysti = IVPB_MA(h, sacc, y[i]);
-          const double d2 = y1[i] - ysti;
-          stnum = IVPB_MA(d1, d1, stnum); stden = IVPB_MA(d2, d2, stden);
+          sd2[i] = y1[i] - ysti;
         }
+        const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
         if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
         if (hlamb > 3.25) {
           nonstiff = 0; iasti += 1;
@@ -813,15 +897,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k1[i], y[i]);
-    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k2);
+    L::ode(IVPB_MA(0.5, h, x), yt, p, k2);
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.75, k2[i], y[i]);
-    Prob::ode(IVPB_MA(0.75, h, x), yt, p, k3);
+    L::ode(IVPB_MA(0.75, h, x), yt, p, k3);
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h, IVPB_MA(b3, k3[i], IVPB_MA(b2, k2[i], b1 * k1[i])), y[i]);
-    Prob::ode(x + h, yt, p, k4);
+    L::ode(x + h, yt, p, k4);
     nfev += 3;
-    double err = 0.0;
+    double qe[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double ye = h * IVPB_MA(e4, k4[i], IVPB_MA(e3, k3[i], IVPB_MA(e2, k2[i], e1 * k1[i])));
@@ -831,14 +915,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
 #else
       const double q = ye * fm::rcp(tol);
 #endif
-      err = IVPB_MA(q, q, err);
+      qe[i] = L::valid(i) ? q : 0.0;
     }
+    double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = sqrt(err / (double)N);
+    err = sqrt(err / (double)NG);
     const double sfac = safe * ivpb_libm_pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
     const bool accept = err <= 1.0;
 #else
-    const double errsq = err * (1.0 / (double)N);              // err^2; err^(-1/3) = cbrt(1/sqrt(err^2))
+    const double errsq = err * (1.0 / (double)NG);              // err^2; err^(-1/3) = cbrt(1/sqrt(err^2))
     const double sfac = safe * cbrt(fm::rsqrt(errsq));
     const bool accept = errsq <= 1.0;
     (void)expo;
@@ -881,13 +966,13 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
     double k2[N], k3[N], k4[N], yt[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k1[i], y[i]);
-    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k2);
+    L::ode(IVPB_MA(0.5, h, x), yt, p, k2);
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 0.5, k2[i], y[i]);
-    Prob::ode(IVPB_MA(0.5, h, x), yt, p, k3);
+    L::ode(IVPB_MA(0.5, h, x), yt, p, k3);
 #pragma unroll
     for (int i = 0; i < N; ++i) yt[i] = IVPB_MA(h * 1.0, k3[i], y[i]);
-    Prob::ode(IVPB_MA(1.0, h, x), yt, p, k4);
+    L::ode(IVPB_MA(1.0, h, x), yt, p, k4);
     const double xold = x;
     double cont[NC][N];
     x += h;
@@ -896,7 +981,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT>::step(const KArgs& a
       if constexpr (DENSE) { cont[0][i] = y[i]; cont[1][i] = k4[i]; }
       y[i] = IVPB_MA(h, IVPB_MA(1.0 / 6.0, k4[i], IVPB_MA(1.0 / 3.0, k3[i], IVPB_MA(1.0 / 3.0, k2[i], (1.0 / 6.0) * k1[i]))), y[i]);
     }
-    Prob::ode(x, y, p, k1);
+    L::ode(x, y, p, k1);
     nfev += 4;
     nstep += 1;
     if constexpr (DENSE) {
@@ -965,6 +1050,40 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
 template <class Prob, int METHOD, int FEAT>
 __device__ __forceinline__ void erk_body(const KArgs& a) {
   run_schedule<ErkTraj<Prob, METHOD, FEAT>>(a);
+}
+
+// Warp-per-trajectory scheduler: every warp owns one trajectory at a time and pulls the next index from the
+// same global queue (one atomic per trajectory, by the leader lane); `static_sched` maps warp w of the grid to
+// trajectory w.  Control flow is warp-uniform throughout.
+template <class Traj>
+__device__ __forceinline__ void run_schedule_warp(const KArgs& a) {
+  Traj T;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const i64 warp_global = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  bool first = true;
+  for (;;) {
+    i64 idx;
+    if (a.static_sched) {
+      if (!first) break;
+      idx = warp_global;
+    } else {
+      u64 base = 0;
+      if (lane == 0) base = atomicAdd(a.queue, 1ull);
+      idx = (i64)__shfl_sync(FULL, base, 0);
+    }
+    first = false;
+    if (idx >= a.N) break;
+    if (!T.init(a, idx)) {
+      while (!T.step(a)) {}
+    }
+    T.finish(a);
+  }
+}
+
+template <class Prob, int METHOD, int FEAT>
+__device__ __forceinline__ void erk_warp_body(const KArgs& a) {
+  run_schedule_warp<ErkTraj<Prob, METHOD, FEAT, WarpLayout<Prob>>>(a);
 }
 
 }  // namespace ivpb

@@ -30,13 +30,35 @@ __host__ inline const void* erk_lookup_feat(int feat) {
   }
 }
 
+// Warp-per-trajectory variant for n > 32 (WarpLayout, ivpb_erk.cuh): 4 warps per block, dynamic shared memory
+// IVPB_BLOCK / 32 * WarpLayout::SMEM_DOUBLES_PER_WARP doubles.
+template <class Prob, int METHOD, int FEAT>
+__global__ void __launch_bounds__(IVPB_BLOCK, 1) erk_warp_kernel(const __grid_constant__ KArgs a) {
+  erk_warp_body<Prob, METHOD, FEAT>(a);
+}
+
+template <class Prob, int METHOD>
+__host__ inline const void* erk_lookup_feat_any(int feat) {
+  if constexpr (Prob::N <= MAX_N) return erk_lookup_feat<Prob, METHOD>(feat);
+  else {
+    switch (feat) {
+      case 0: return (const void*)&erk_warp_kernel<Prob, METHOD, 0>;
+      case K_OUT: return (const void*)&erk_warp_kernel<Prob, METHOD, K_OUT>;
+      case K_OUT | K_EVENTS:
+        if constexpr (Prob::NEV > 0) return (const void*)&erk_warp_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
+        else return nullptr;
+      default: return nullptr;
+    }
+  }
+}
+
 template <class Prob>
 __host__ inline const void* erk_lookup(int method, int feat) {
   switch (method) {
-    case M_RK23: return erk_lookup_feat<Prob, M_RK23>(feat);
-    case M_DOPRI5: return erk_lookup_feat<Prob, M_DOPRI5>(feat);
-    case M_DOP853: return erk_lookup_feat<Prob, M_DOP853>(feat);
-    case M_RK4: return erk_lookup_feat<Prob, M_RK4>(feat);
+    case M_RK23: return erk_lookup_feat_any<Prob, M_RK23>(feat);
+    case M_DOPRI5: return erk_lookup_feat_any<Prob, M_DOPRI5>(feat);
+    case M_DOP853: return erk_lookup_feat_any<Prob, M_DOP853>(feat);
+    case M_RK4: return erk_lookup_feat_any<Prob, M_RK4>(feat);
     default: return nullptr;
   }
 }

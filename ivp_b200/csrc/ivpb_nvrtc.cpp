@@ -98,7 +98,10 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
   s += "\n// ---- adaptor ----\n";
   s += "struct PUser : ivpb::ProblemDefaults<" + std::to_string(up.n) + ", " + std::to_string(up.p) + ", " +
        std::to_string(up.n_events) + "> {\n";
-  s += "  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { ivp_ode(t, y, p, d); }\n";
+  if (up.n > 32)
+    s += "  static __device__ __forceinline__ double ode_i(double t, const double* y, const double* p, int i) { return ivp_ode_i(t, y, p, i); }\n";
+  else
+    s += "  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { ivp_ode(t, y, p, d); }\n";
   if (up.n_events > 0)
     s += "  static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { ivp_events(t, y, p, g); }\n";
   if (up.has_jac) {
@@ -112,7 +115,8 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
     s += "  ivpb::implicit_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
   } else {
     s += "extern \"C\" __global__ void __launch_bounds__(IVPB_BLOCK) ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
-    s += "  ivpb::erk_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
+    s += up.n > 32 ? "  ivpb::erk_warp_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n"
+                   : "  ivpb::erk_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
   }
   return s;
 }
@@ -197,11 +201,20 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
       if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
     }
   }
+  long long units_per_block = block;
+  if (method < 4 && up.n > 32) {       // one trajectory per warp: WarpLayout needs 2 n doubles of shared memory per warp
+    smem = (size_t)(block / 32) * 2 * up.n * 8;
+    units_per_block = block / 32;
+    if (smem > 48 * 1024) {
+      CUresult ar = A.FuncSetAttribute(it->second.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+      if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
+    }
+  }
   int occ = 1;
   A.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, it->second.fn, block, smem);
   if (occ < 1) occ = 1;
   long long grid = (long long)sms * occ;
-  const long long need = (N + block - 1) / block;
+  const long long need = (N + units_per_block - 1) / units_per_block;
   if (static_sched || need < grid) grid = need;
   std::vector<char> copy((const char*)kargs, (const char*)kargs + kargs_bytes);
   void* params[] = {copy.data()};

@@ -141,4 +141,30 @@ struct PCannon : ProblemDefaults<2, 0, 1> {     // reference tests/test_ivp.py:1
   IVPB_HD i64 default_term(int) { return 1; }
 };
 
+// ---- large systems: one trajectory per warp (WarpLayout), the RHS is given per component ----
+struct PLinear100 : ProblemDefaults<100, 0, 0> {  // reference benches/benchmark.py:39-41,137-146 (dy/dt = -y, N = 100)
+  IVPB_DEV double ode_i(double, const double* y, const double*, int i) { return -y[i]; }
+};
+
+// MEDAKZO (reference tests/test_ivp.py:77-101 `fun_medazko`) on 32 grid points: n = 64, stiff reaction-diffusion.
+struct PMedakzo64 : ProblemDefaults<64, 0, 0> {
+  IVPB_DEV double z(double t, const double* y, int m) {      // y padded as hstack((phi, 0, y, y[-2]))
+    if (m == 0) return t <= 5.0 ? 2.0 : 0.0;
+    if (m == 1) return 0.0;
+    if (m == 2 * 32 + 2) return y[2 * 32 - 2];
+    return y[m - 2];
+  }
+  IVPB_DEV double ode_i(double t, const double* y, const double*, int i) {
+    constexpr int NG = 32;
+    const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+    const int j = i / 2 + 1;
+    const double u = z(t, y, 2 * j), v = z(t, y, 2 * j + 1);
+    if (i & 1) return -k * v * u;
+    const double w = (double)j * d - 1.0;
+    const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+    const double zp = z(t, y, 2 * j + 2), zm = z(t, y, 2 * j - 2);
+    return alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
+  }
+};
+
 }  // namespace ivpb

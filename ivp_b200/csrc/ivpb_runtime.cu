@@ -32,12 +32,12 @@ typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* sme
   extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*);             \
   extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
-DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon)
+DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64)
 #undef DECL
 #define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag}
 static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
-    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64)};
 #undef ROW
 // dense-output evaluation kernels (ivpb_dense.cu)
 extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
@@ -49,7 +49,7 @@ extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const d
 #define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag}
 static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
-    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon)};
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64)};
 #undef ROW
 
 namespace {
@@ -80,7 +80,7 @@ struct Device {
   cudaStream_t stream = nullptr;
   u64* queue = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
-  Buf y0, params, t_eval, out[OUT_FIELDS];
+  Buf y0, params, t_eval, tol_ext, out[OUT_FIELDS];
 };
 
 // bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
@@ -168,7 +168,6 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
   if (!o) return fail(ctx, IVPB_ERR_CONFIG, "options is null");
   if (N < 0) return fail(ctx, IVPB_ERR_CONFIG, "N must be >= 0");
   if (o->method < IVPB_RK23 || o->method > IVPB_BDF) return fail(ctx, IVPB_ERR_CONFIG, "unknown method");
-  if (pi.n > ivpb::MAX_N) return fail(ctx, IVPB_ERR_CONFIG, "state size exceeds the thread-per-trajectory limit (32)");
   if (!o->rtol || !o->atol) return fail(ctx, IVPB_ERR_CONFIG, "rtol/atol must be given");
   // Tolerance::Vector length mismatch panics in the reference (src/methods/mod.rs:156-161)
   if (!(o->n_rtol == 1 || o->n_rtol == pi.n)) return fail(ctx, IVPB_ERR_CONFIG, "rtol length must be 1 or n");
@@ -300,7 +299,7 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
     // bdf.rs:174-184
     const double eps = std::numeric_limits<double>::epsilon();
     double rtol_min = std::numeric_limits<double>::infinity();
-    for (int i = 0; i < pi.n; ++i) rtol_min = std::fmin(rtol_min, a.rtol[i]);
+    for (int i = 0; i < pi.n && i < ivpb::MAX_N; ++i) rtol_min = std::fmin(rtol_min, a.rtol[i]);
     rtol_min = std::fmax(rtol_min, eps);
     a.newton_tol = std::fmax(10.0 * eps / rtol_min, std::fmin(std::sqrt(rtol_min), 0.03));
     if (a.newton_tol <= 0.0) a.newton_tol = 1e-9;
@@ -332,8 +331,18 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     CK(cudaMemcpyAsync(dev.t_eval.p, o->t_eval, sizeof(double) * o->n_t_eval, cudaMemcpyHostToDevice, stream));
     a.t_eval = (const double*)dev.t_eval.p;
   }
+  if (pi.n > ivpb::MAX_N && (o->n_rtol > 1 || o->n_atol > 1)) {
+    // Tolerance::Vector for a warp-per-trajectory problem: per-component arrays in device memory
+    std::vector<double> tol(2 * (size_t)pi.n);
+    for (int i = 0; i < pi.n; ++i) { tol[i] = o->rtol[o->n_rtol == 1 ? 0 : i]; tol[pi.n + i] = o->atol[o->n_atol == 1 ? 0 : i]; }
+    CK(dev.tol_ext.ensure(sizeof(double) * tol.size()));
+    CK(cudaMemcpyAsync(dev.tol_ext.p, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
+    a.rtol_ext = (const double*)dev.tol_ext.p; a.atol_ext = a.rtol_ext + pi.n;
+  }
   const int strict = (o->flags & IVPB_FLAG_STRICT_FP) ? 1 : 0;
   const int block = 128;
+  const bool warp_mode = pi.n > ivpb::MAX_N;      // one trajectory per warp (WarpLayout, ivpb_erk.cuh)
 
   if (std::fabs(tf - t0) < 1e-15) {
     const int grid = (int)((N + block - 1) / block);
@@ -362,6 +371,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
 
   if (pi.user) {
+    if (warp_mode && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
+      return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
     int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, strict, &a, sizeof(a), N,
                                a.static_sched, stream);
     if (rc) return rc;
@@ -378,12 +389,17 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   } else {
     kern = BUILTIN[problem][strict](o->method, feat, nullptr);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
+    if (warp_mode) {
+      ksmem = (kblock / 32) * 2 * pi.n * (int)sizeof(double);
+      if (ksmem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
+    }
   }
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kblock, ksmem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)dev.sms * occ;
-  const int64_t need = (N + kblock - 1) / kblock;
+  const int64_t units_per_block = warp_mode && !(o->method == IVPB_RADAU || o->method == IVPB_BDF) ? kblock / 32 : kblock;
+  const int64_t need = (N + units_per_block - 1) / units_per_block;
   if (a.static_sched || need < grid) grid = need;
   void* kargs[] = {&a};
   CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kblock), kargs, ksmem, stream));
@@ -440,7 +456,7 @@ void ivpb_destroy(ivpb_ctx* ctx) {
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
-    d.y0.release(); d.params.release(); d.t_eval.release();
+    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release();
     for (auto& b : d.out) b.release();
     cudaFree(d.queue);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
@@ -468,7 +484,7 @@ int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_e
 
 int ivpb_nvrtc_problem(ivpb_ctx* ctx, const char* cuda_src, int n, int p, int n_events, int has_jac, int* handle) {
   if (!ctx || !cuda_src || !handle) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
-  if (n < 1 || n > ivpb::MAX_N) return fail(ctx, IVPB_ERR_CONFIG, "n must be in 1..32");
+  if (n < 1 || n > 1024) return fail(ctx, IVPB_ERR_CONFIG, "n must be in 1..1024 (n > 32 runs one trajectory per warp and needs ivp_ode_i)");
   if (p < 0 || n_events < 0 || n_events > ivpb::MAX_EVENTS_FN) return fail(ctx, IVPB_ERR_CONFIG, "bad p / n_events");
   ivpb_user_problem up;
   up.n = n; up.p = p; up.n_events = n_events; up.has_jac = has_jac; up.src = cuda_src;

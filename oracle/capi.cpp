@@ -157,6 +157,7 @@ int oracle_problem_dims(int problem, int* n, int* p, int* ne) {
     case IVPB_P_LORENZ: DIMS(Lorenz) case IVPB_P_CR3BP: DIMS(Cr3bp) case IVPB_P_BALL: DIMS(Ball)
     case IVPB_P_ROBERTSON: DIMS(Robertson) case IVPB_P_SHO: DIMS(Sho) case IVPB_P_ZERO3: DIMS(Zero3)
     case IVPB_P_EXP2: DIMS(Exp2) case IVPB_P_RATIONAL: DIMS(Rational) case IVPB_P_CANNON: DIMS(Cannon)
+    case IVPB_P_LINEAR100: DIMS(Linear100) case IVPB_P_MEDAKZO64: DIMS(Medakzo64)
     default: return 1;
   }
 }
@@ -169,6 +170,7 @@ int oracle_solve_batch(int problem, const ivpb_options* o, int64_t N, double t0,
     case IVPB_P_LORENZ: return RB(Lorenz); case IVPB_P_CR3BP: return RB(Cr3bp); case IVPB_P_BALL: return RB(Ball);
     case IVPB_P_ROBERTSON: return RB(Robertson); case IVPB_P_SHO: return RB(Sho); case IVPB_P_ZERO3: return RB(Zero3);
     case IVPB_P_EXP2: return RB(Exp2); case IVPB_P_RATIONAL: return RB(Rational); case IVPB_P_CANNON: return RB(Cannon);
+    case IVPB_P_LINEAR100: return RB(Linear100); case IVPB_P_MEDAKZO64: return RB(Medakzo64);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -183,6 +185,7 @@ int oracle_dense_eval(int problem, const ivpb_options* o, double t0, double tf, 
     case IVPB_P_LORENZ: return DE(Lorenz); case IVPB_P_CR3BP: return DE(Cr3bp); case IVPB_P_BALL: return DE(Ball);
     case IVPB_P_ROBERTSON: return DE(Robertson); case IVPB_P_SHO: return DE(Sho); case IVPB_P_ZERO3: return DE(Zero3);
     case IVPB_P_EXP2: return DE(Exp2); case IVPB_P_RATIONAL: return DE(Rational); case IVPB_P_CANNON: return DE(Cannon);
+    case IVPB_P_LINEAR100: return DE(Linear100); case IVPB_P_MEDAKZO64: return DE(Medakzo64);
     default: g_err = "unknown problem id"; return 1;
   }
 }

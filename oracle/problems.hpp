@@ -121,4 +121,30 @@ struct Cannon : ProblemBase<Cannon, 2, 0, 1> {        // tests/test_ivp.py:153-1
   EventConfig default_event_config(int) const { EventConfig c; c.terminal_count = 1; c.direction = Direction::Negative; return c; }
 };
 
+struct Linear100 : ProblemBase<Linear100, 100, 0, 0> {  // benches/benchmark.py:39-41,137-146
+  void ode(double, const double* y, double* d) const { for (int i = 0; i < 100; ++i) d[i] = -y[i]; }
+};
+
+struct Medakzo64 : ProblemBase<Medakzo64, 64, 0, 0> {   // tests/test_ivp.py:77-101 (fun_medazko), 32 grid points
+  static double z(double t, const double* y, int m) {
+    if (m == 0) return t <= 5.0 ? 2.0 : 0.0;
+    if (m == 1) return 0.0;
+    if (m == 2 * 32 + 2) return y[2 * 32 - 2];
+    return y[m - 2];
+  }
+  void ode(double t, const double* y, double* f) const {
+    const int NG = 32;
+    const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+    for (int i = 0; i < 64; ++i) {
+      const int j = i / 2 + 1;
+      const double u = z(t, y, 2 * j), v = z(t, y, 2 * j + 1);
+      if (i & 1) { f[i] = -k * v * u; continue; }
+      const double w = (double)j * d - 1.0;
+      const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+      const double zp = z(t, y, 2 * j + 2), zm = z(t, y, 2 * j - 2);
+      f[i] = alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
+    }
+  }
+};
+
 }  // namespace oracle

@@ -626,3 +626,88 @@ def test_dense_output_fma_build_truncation_and_zero_interval(oracle):
     assert okz[0] and np.array_equal(yz[0], [2.0, 3.0])
     with pytest.raises(ib.ConfigError):
         ib.solve_ivp_batch("sho", 0.0, 1.0, np.array([[1.0, 0.0]]), None, Options(dense_output=True))   # max_segments missing
+
+
+# ---------------------------------------------------------------------------------------------------------
+# n > 32: one trajectory per warp (WarpLayout): state distributed over lanes, RHS per component from a
+# shared-memory row, norms by shuffle reduction (fast) or in index order (strict, bit-exact).
+
+def medakzo_y0(N):
+    y0 = np.zeros((N, 64))
+    y0[:, 1::2] = 1.0 + 0.001 * np.arange(N)[:, None]      # tests/test_ivp.py:247-249 (v0 = 1), spread per trajectory
+    return y0
+
+
+@pytest.mark.parametrize("method", [Method.RK23, Method.DOPRI5, Method.DOP853, Method.RK4])
+def test_warp_per_trajectory_strict_bit_exact(oracle, method):
+    N = 75                                              # not a multiple of the 4 warps per block
+    y0 = np.ones((N, 100)) * (1.0 + 0.01 * np.arange(N))[:, None] * np.linspace(0.5, 1.5, 100)[None, :]
+    te = np.linspace(0.0, 10.0, 7)
+    kw = dict(first_step=0.05) if method == Method.RK4 else dict(rtol=1e-6, atol=1e-8)
+    for extra in ({}, {"t_eval": te}):
+        opts = Options(method=method, flags=IVPB_FLAG_STRICT_FP, **kw, **extra)
+        g = ib.solve_ivp_batch("linear100", 0.0, 10.0, y0, None, opts)
+        o = oracle.solve_batch(PROBLEMS["linear100"], 0.0, 10.0, y0, None, opts, nthreads=8)
+        exact(g, o)
+        if extra:
+            exact(g, o, ("n_out", "t_out", "y_out"))
+    np.testing.assert_allclose(g.y_final, y0 * np.exp(-10.0), rtol=2e-3)
+    # coupled system (neighbours read through the shared-memory row), static schedule too
+    ym = medakzo_y0(33)
+    for flags in (IVPB_FLAG_STRICT_FP, IVPB_FLAG_STRICT_FP | IVPB_FLAG_NO_REFILL):
+        kw2 = dict(first_step=1e-3) if method == Method.RK4 else dict(rtol=1e-6, atol=1e-8)
+        opts = Options(method=method, flags=flags, **kw2)
+        g = ib.solve_ivp_batch("medakzo64", 0.0, 0.5, ym, None, opts)
+        o = oracle.solve_batch(PROBLEMS["medakzo64"], 0.0, 0.5, ym, None, opts, nthreads=8)
+        exact(g, o)
+
+
+def test_warp_per_trajectory_fma_build_vector_tolerances_dense(oracle):
+    N = 200
+    ym = medakzo_y0(N)
+    rt = np.full(64, 1e-6); rt[::2] = 1e-7
+    opts = Options(method=Method.DOP853, rtol=rt, atol=1e-9, dense_output=True, max_segments=512)
+    g = ib.solve_ivp_batch("medakzo64", 0.0, 0.5, ym, None, opts)
+    o = oracle.solve_batch(PROBLEMS["medakzo64"], 0.0, 0.5, ym, None, opts, nthreads=8)
+    assert np.array_equal(g.status, o.status)
+    check_counts(g, o, 0.97)
+    assert close(g.y_final, o.y_final, 1e-6, 1e-9).all()
+    ys, oks, _ = oracle.dense_eval(PROBLEMS["medakzo64"], 0.0, 0.5, ym[7], None, opts, np.linspace(0.0, 0.5, 9))
+    yg, okg = g.sol_many([7] * 9, np.linspace(0.0, 0.5, 9))
+    assert okg.all() and oks.all() and close(yg, ys, 1e-6, 1e-9).all()
+
+
+USER_CHAIN48 = r"""
+// 48 coupled oscillators on a ring: y[2j] position, y[2j+1] velocity
+__device__ double ivp_ode_i(double t, const double* y, const double* p, int i) {
+  const int j = i >> 1, jl = (j + 23) % 24, jr = (j + 1) % 24;
+  if ((i & 1) == 0) return y[i + 1];
+  return -y[2 * j] + p[0] * (y[2 * jl] - 2.0 * y[2 * j] + y[2 * jr]);
+}
+__device__ void ivp_events(double t, const double* y, const double* p, double* g) { g[0] = y[0]; }
+"""
+
+
+def test_nvrtc_user_problem_warp_mode():
+    from ivp_b200 import api
+    user = api.Problem.from_cuda_source(USER_CHAIN48, n=48, p=1, n_events=1)
+    N = 50
+    y0 = np.zeros((N, 48)); y0[:, 0] = 1.0 + 0.01 * np.arange(N)
+    par = np.full((N, 1), 0.3)
+    opts = Options(method=Method.DOP853, rtol=1e-9, atol=1e-9, max_events=8, t_eval=np.linspace(0, 10, 11),
+                   event_config=[EventConfig(Direction.All, None)])
+    g = ib.solve_ivp_batch(user, 0.0, 10.0, y0, par, opts)
+    assert np.all(g.status == Status.Success) and np.all(g.n_out == 11)
+    # energy of the linear ring is conserved; events are the zeros of y[0]
+    def energy(y):
+        q, v = y[..., 0::2], y[..., 1::2]
+        return 0.5 * (v ** 2).sum(-1) + 0.5 * (q ** 2).sum(-1) + 0.5 * 0.3 * ((np.roll(q, -1, -1) - q) ** 2).sum(-1)
+    e = energy(g.y_out[:, :11])
+    assert np.abs(e / e[:, :1] - 1.0).max() < 1e-7
+    assert np.all(g.ev_count[:, 0] >= 2) and np.abs(g.ev_y[:, 0, 0, 0]).max() < 1e-8
+    import scipy.integrate as si
+    def rhs(t, y):
+        q, v = y[0::2], y[1::2]
+        d = np.empty_like(y); d[0::2] = v; d[1::2] = -q + 0.3 * (np.roll(q, 1) - 2 * q + np.roll(q, -1)); return d
+    ref = si.solve_ivp(rhs, (0, 10), y0[3], method="DOP853", rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(g.y_final[3], ref.y[:, -1], rtol=0, atol=1e-7)
