@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--static", action="store_true", help="disable work-queue refill (A/B)")
     ap.add_argument("--strict", action="store_true", help="-fmad=false kernel variant (A/B)")
+    ap.add_argument("--no-zerocopy", action="store_true", help="e2e arm: staged H2D/D2H copies instead of mapped pinned buffers (A/B)")
     ap.add_argument("--jac-mode", type=int, default=0, help="implicit workloads: 0 finite differences, 1 analytic")
     args = ap.parse_args()
     from ivp_b200.dist import dist_env, reduce_time_and_count, weak_offset
@@ -214,7 +215,8 @@ def main():
     Nper = args.trajectories
     prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=weak_offset(Nper, rank))
     problem = api.Problem.builtin(prob_name)
-    flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0)
+    flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0) | \
+        (api.IVPB_FLAG_NO_ZEROCOPY if args.no_zerocopy else 0)
     n_te = N_T_EVAL.get(args.workload, 0)
     opts = workload_options(args.workload, t0, tf, flags, args.jac_mode)
     mo = _abi.MarshalledOptions(opts, problem.n, problem.n_events)
@@ -377,7 +379,8 @@ def main():
             "accepted_steps_per_step": acc_all, "rejected_steps_rank0": int(nrejct.sum()),
             "status_success_frac_rank0": float(np.mean(status == 0)),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s_max / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers)"},
+                    "ms_per_step": e2e_s_max / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers" + (", staged copies)" if args.no_zerocopy else
+                                                                  ", kernel reads/writes them over PCIe while integrating; sample blocks staged)")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))
     if use_dist:

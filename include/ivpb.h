@@ -87,6 +87,9 @@ typedef struct {
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
                                   the reference's rounding, no FMA contraction) */
 #define IVPB_FLAG_NO_REFILL 2u /* static one-trajectory-per-thread schedule (debug / A-B measurements) */
+#define IVPB_FLAG_NO_ZEROCOPY 4u /* ivpb_solve_batch: always stage through device buffers, even when the caller's
+                                    buffers are page-locked (default: pinned y0 / params / per-trajectory results are
+                                    read and written by the kernel directly over PCIe, overlapping the solve) */
 
 /* Per-trajectory outputs.  Any pointer may be NULL (= not wanted).  In ivpb_solve_batch they are
  * HOST pointers, in ivpb_solve_batch_device DEVICE pointers.
@@ -162,8 +165,9 @@ int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const d
  * (src/solve/cont.rs:67-76); n_seg = segments stored (0 => no span). */
 int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg);
 
-/* Pinned host memory for y0 / params / outputs, so the H2D / D2H copies of ivpb_solve_batch run at full
- * PCIe rate and asynchronously (pageable buffers work too, but are staged by the driver). */
+/* Pinned host memory for y0 / params / outputs: ivpb_solve_batch maps such buffers into the kernel (zero-copy,
+ * see IVPB_FLAG_NO_ZEROCOPY) or, for the staged fields, copies at full PCIe rate.  Pageable buffers work too,
+ * through staging copies. */
 void* ivpb_host_alloc(size_t bytes);
 void ivpb_host_free(void* p);
 

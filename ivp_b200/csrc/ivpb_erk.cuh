@@ -590,8 +590,18 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0;      // beta = 0 => facold^beta == 1 exactly
     const double h_max = hmax_of(a);
     if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
+#ifdef IVPB_STRICT
     if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
     if ((IVPB_MA(1.01, h, x) - xend) * posneg > 0.0) { h = xend - x; last = true; }
+#else
+    // same two tests with fewer fp64 operations: (a - xend) * (+-1) > 0 is a comparison of a with xend, and the
+    // factor 0.1 moves into the constant
+    if (fabs(h) <= fabs(x) * (10.0 * uround)) { status = ST_SMALL; return true; }
+    {
+      const double xa = fma(1.01, h, x);
+      if (posneg > 0.0 ? (xa > xend) : (xa < xend)) { h = xend - x; last = true; }
+    }
+#endif
     nstep += 1;
 
     double k[10][N], y1[N];
@@ -751,8 +761,18 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     const double expo1 = 0.2 - beta * 0.75;
     const double h_max = hmax_of(a);
     if ((u64)nstep > a.max_steps) { status = ST_NMAX; return true; }
+#ifdef IVPB_STRICT
     if (0.1 * fabs(h) <= fabs(x) * uround) { status = ST_SMALL; return true; }
     if ((IVPB_MA(1.01, h, x) - xend) * posneg > 0.0) { h = xend - x; last = true; }
+#else
+    // same two tests with fewer fp64 operations: (a - xend) * (+-1) > 0 is a comparison of a with xend, and the
+    // factor 0.1 moves into the constant
+    if (fabs(h) <= fabs(x) * (10.0 * uround)) { status = ST_SMALL; return true; }
+    {
+      const double xa = fma(1.01, h, x);
+      if (posneg > 0.0 ? (xa > xend) : (xa < xend)) { h = xend - x; last = true; }
+    }
+#endif
     nstep += 1;
 
     double k[6][N], y1[N];

@@ -17,27 +17,24 @@ __device__ __forceinline__ bool in_range(double x) {
   return hi - 0x03000000u < 0x7a000000u;      // roughly 1e-293 < |x| < 1e280
 }
 
-// 1/x: MUFU.RCP64H seed (~2^-20) + two Newton steps
+// 1/x: MUFU.RCP64H seed r (relative error e ~ 2^-20), then one third-order step r (1 + e + e^2) with
+// e = 1 - x r: remaining error e^3 ~ 2^-60, i.e. rounding-limited, in 3 dependent DFMAs.
 __device__ __forceinline__ double rcp(double x) {
   if (!in_range(x)) return 1.0 / x;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 }
 
-// 1/sqrt(x), x > 0: MUFU.RSQ64H seed + two Newton steps
+// 1/sqrt(x), x > 0: MUFU.RSQ64H seed r (e = 1 - x r^2 ~ 2^-19), then one third-order step
+// r (1 + e/2 + 3 e^2 / 8): remaining error ~ (5/16) e^3 ~ 2^-59.
 __device__ __forceinline__ double rsqrt(double x) {
   if (!in_range(x) || x < 0.0) return ::rsqrt(x);
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  const double hx = 0.5 * x;
-  double e = fma(-hx * r, r, 0.5);
-  r = fma(r, e, r);
-  e = fma(-hx * r, r, 0.5);
-  return fma(r, e, r);
+  const double e = fma(-(x * r), r, 1.0);
+  return fma(r * e, fma(0.375, e, 0.5), r);
 }
 
 // Comparison-select max/min: 3 instructions instead of the ~7 of IEEE fmax/fmin on doubles.  A NaN in `a`
@@ -45,26 +42,25 @@ __device__ __forceinline__ double rsqrt(double x) {
 __device__ __forceinline__ double maxsel(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double minsel(double a, double b) { return a < b ? a : b; }
 
-// x^(-1/8) for x >= 0.  fp32 seed through MUFU lg2/ex2 on the argument clamped to [1e-30, 1e30] (rel. error
-// ~2e-6), then two Newton steps on f(u) = u^-8 - x, u <- u + u (1 - x u^8) / 8, which need multiplications only
-// (error 4.5 e^2 per step).  Below 1e-30 (and for 0) the iteration just grows u a little from the clamped seed
-// 5.6e3; at or above 1e30, and for inf / NaN, the result is forced to 0.  Callers clamp the step factor to
-// [0.333, 6] (or [0.2, 10]) with maxsel/minsel, so both ends land on the bound the reference's controller
-// reaches for such an error (growth by scale_max for err -> 0, shrink by scale_min for err -> inf / NaN).
+// x^(-1/8) for x >= 0.  fp32 seed u through MUFU lg2/ex2 on the argument clamped to [1e-30, 1e30] (relative error
+// below ~1e-5), then ONE step of the binomial series of (1 - r)^(-1/8) with r = 1 - x u^8:
+//   u (1 + r/8 + 9 r^2/128 + 51 r^3/1024),   truncation error ~ 0.04 r^4 < 1e-17 for |r| < 1e-4,
+// which needs multiplications and FMAs only.  Below 1e-30 (and for 0) the step just grows u a little from the
+// clamped seed 5.6e3; at or above 1e30, and for inf / NaN, the result is forced to 0.  Callers clamp the step
+// factor to [0.333, 6] (or [0.2, 10]) with maxsel/minsel, so both ends land on the bound the reference's
+// controller reaches for such an error (growth by scale_max for err -> 0, shrink by scale_min for err -> inf / NaN).
 __device__ __forceinline__ double rroot8(double x) {
   const float xr = (float)x;
   float xf = fminf(fmaxf(xr, 1e-30f), 1e30f), lf, uf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lf) : "f"(xf));
   lf *= -0.125f;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(uf) : "f"(lf));
-  double u = (double)uf;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
-    const double r = fma(-x, u8, 1.0);
-    u = fma(0.125 * u, r, u);
-  }
-  return (xr < 1e30f) ? u : 0.0;
+  const double u = (double)uf;
+  const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
+  const double r = fma(-x, u8, 1.0);
+  const double pl = fma(fma(0.0498046875, r, 0.0703125), r, 0.125) * r;
+  const double v = fma(u, pl, u);
+  return (xr < 1e30f) ? v : 0.0;
 }
 
 }  // namespace fm

@@ -711,3 +711,45 @@ def test_nvrtc_user_problem_warp_mode():
         d = np.empty_like(y); d[0::2] = v; d[1::2] = -q + 0.3 * (np.roll(q, 1) - 2 * q + np.roll(q, -1)); return d
     ref = si.solve_ivp(rhs, (0, 10), y0[3], method="DOP853", rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(g.y_final[3], ref.y[:, -1], rtol=0, atol=1e-7)
+
+
+def test_zero_copy_pinned_buffers_match_staged_copies():
+    """ivpb_solve_batch with page-locked caller buffers: the kernel reads y0/params and writes the per-trajectory
+    results straight over PCIe (no staging copies); identical to the staged path."""
+    import ctypes as C
+    from ivp_b200 import _abi, api
+    from ivp_b200.api import IVPB_FLAG_NO_ZEROCOPY
+    lib = api.load_library()
+    N = 20011
+    prob, y0, par, t0, tf = synth.ensemble("vdp", N)
+    problem = api.Problem.builtin(prob)
+    ctx = api.default_context()
+
+    def pinned(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib.ivpb_host_alloc(nbytes)
+        assert p
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (nbytes,)).view(dtype).reshape(shape), p
+
+    bufs = {}
+    y0_p, bufs["y0"] = pinned((N, 2), np.float64)
+    par_p, bufs["par"] = pinned((N, 1), np.float64)
+    y0_p[:] = y0; par_p[:] = par
+    res = {}
+    for flags in (0, IVPB_FLAG_NO_ZEROCOPY):
+        st_p, b1 = pinned((N,), np.int32); cn_p, b2 = pinned((N, 6), np.uint32)
+        tf_p, b3 = pinned((N,), np.float64); yf_p, b4 = pinned((N, 2), np.float64)
+        st_p[:] = -7; cn_p[:] = 0; yf_p[:] = np.nan
+        mo = _abi.MarshalledOptions(Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, flags=flags), 2, 0)
+        st = _abi.IvpbOutputs()
+        st.status, st.counters, st.t_final, st.y_final = _abi.ptr(st_p), _abi.ptr(cn_p), _abi.ptr(tf_p), _abi.ptr(yf_p)
+        ctx.solve_host(problem, t0, 25.0, y0_p, par_p, mo, st)
+        res[flags] = (st_p.copy(), cn_p.copy(), tf_p.copy(), yf_p.copy())
+        for b in (b1, b2, b3, b4):
+            lib.ivpb_host_free(b)
+    for a, b in zip(res[0], res[IVPB_FLAG_NO_ZEROCOPY]):
+        assert np.array_equal(a, b)
+    assert np.all(res[0][0] == 0) and np.all(res[0][2] == 25.0)
+    ref = ib.solve_ivp_batch(prob, t0, 25.0, y0, par, Options(method=Method.DOP853, rtol=1e-8, atol=1e-8))   # pageable => staged
+    assert np.array_equal(ref.y_final, res[0][3]) and np.array_equal(ref.counters, res[0][1])
+    lib.ivpb_host_free(bufs["y0"]); lib.ivpb_host_free(bufs["par"])
