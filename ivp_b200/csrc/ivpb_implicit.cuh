@@ -292,6 +292,7 @@ struct RadauTraj {
   static constexpr int N = Prob::N, P = Prob::P;
   static constexpr int PS = P > 0 ? P : 1;
   static constexpr int SMEM_MATS = REG ? 0 : 4;
+  static constexpr int SMEM_DOUBLES_PER_THREAD = SMEM_MATS * N * N;
   using Out = SolOutDev<Prob, M_RADAU, FEAT>;
   using Mat = typename std_conditional<REG, RegMat<N>, SmemMat<N, BLK>>::type;
 
@@ -599,51 +600,76 @@ namespace bdf_c {
 static constexpr int MAX_ORDER = 5;
 static constexpr double MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, SAFETY = 0.9;
 static constexpr double EPS = 2.220446049250313e-16, MINPOS = 2.2250738585072014e-308;
-__device__ __forceinline__ double kappa(int k) {     // bdf.rs:15
+static __host__ __device__ constexpr double kappa_c(int k) {     // bdf.rs:15
   return k == 1 ? -0.1850 : k == 2 ? -1.0 / 9.0 : k == 3 ? -0.0823 : k == 4 ? -0.0415 : 0.0;
 }
-__device__ __forceinline__ double gamma(int k) {     // cumulative, left to right as bdf.rs:160-163
+static __host__ __device__ constexpr double gamma_c(int k) {     // cumulative, left to right as bdf.rs:160-163
   double g = 0.0;
-#pragma unroll
-  for (int j = 1; j <= MAX_ORDER; ++j) if (j <= k) g = g + 1.0 / (double)j;
+  for (int j = 1; j <= k; ++j) g = g + 1.0 / (double)j;
   return g;
 }
-__device__ __forceinline__ double alpha(int k) { return (1.0 - kappa(k)) * gamma(k); }
-__device__ __forceinline__ double error_const(int k) { return kappa(k) * gamma(k) + 1.0 / ((double)k + 1.0); }
-}  // namespace bdf_c
-
-// c ? a : b through an opaque selp: keeps "slot k of a register array, chosen by a run-time order" as a chain
-// of selects.  Written as a plain ternary, LLVM folds the chain back into one dynamically indexed load / store,
-// which forces the whole trajectory state out of registers into local memory (measured: 528 B stack frame).
-__device__ __forceinline__ double opaque_sel(bool c, double a, double b) {
-  double r;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+static __host__ __device__ constexpr double alpha_c(int k) { return (1.0 - kappa_c(k)) * gamma_c(k); }
+static __host__ __device__ constexpr double error_const_c(int k) { return kappa_c(k) * gamma_c(k) + 1.0 / ((double)k + 1.0); }
+// compute_r(order, 1.0)[i][j] (bdf.rs:694-713); the order only selects the leading block.  Upper triangular.
+static __host__ __device__ constexpr double u_entry(int i, int j) {
+  if (i == 0) return 1.0;
+  if (j == 0) return 0.0;
+  double r = 1.0;
+  for (int l = 1; l <= i; ++l) r = r * (((double)l - 1.0 - 1.0 * (double)j) / (double)l);
   return r;
 }
+#define IVPB_U_ROW(i) {u_entry(i, 0), u_entry(i, 1), u_entry(i, 2), u_entry(i, 3), u_entry(i, 4), u_entry(i, 5)}
+static __constant__ double BDF_U[6][6] = {IVPB_U_ROW(0), IVPB_U_ROW(1), IVPB_U_ROW(2), IVPB_U_ROW(3), IVPB_U_ROW(4), IVPB_U_ROW(5)};
+#undef IVPB_U_ROW
+static __constant__ double BDF_GAMMA[6] = {gamma_c(0), gamma_c(1), gamma_c(2), gamma_c(3), gamma_c(4), gamma_c(5)};
+static __constant__ double BDF_ALPHA[6] = {alpha_c(0), alpha_c(1), alpha_c(2), alpha_c(3), alpha_c(4), alpha_c(5)};
+static __constant__ double BDF_ERRC[6] = {error_const_c(0), error_const_c(1), error_const_c(2), error_const_c(3),
+                                          error_const_c(4), error_const_c(5)};
+}  // namespace bdf_c
 
+// One shared copy of the transcribed pow per kernel instead of one per call site: the implicit kernels are
+// instruction-cache bound (ncu: "no instruction" is their top stall), and pow sits on rarely taken paths.
+static __device__ __noinline__ double ivpb_pow_call(double x, double y) { return ivpb_libm_pow(x, y); }
+
+// BDF trajectory.  The difference table D (MAX_ORDER + 3 rows of n), change_d's scratch rows and the Jacobian
+// evaluation point live in shared memory, [row][component][thread]: every row index depends on the run-time
+// order, and shared memory takes dynamic indices where a register array cannot (LLVM folds select chains over
+// register slots back into one indexed access, which demotes the whole state to local memory).  The compact
+// loops this allows also keep the kernel small.
 template <class Prob, int FEAT, bool REG, int BLK>
 struct BdfTraj {
   static constexpr int N = Prob::N, P = Prob::P;
   static constexpr int PS = P > 0 ? P : 1;
+  static constexpr int ND = bdf_c::MAX_ORDER + 3, NS = bdf_c::MAX_ORDER + 1;
+  static constexpr int SMEM_VEC_ROWS = ND + NS + 1;                     // D, scratch, Jacobian point
   static constexpr int SMEM_MATS = REG ? 0 : 2;
-  static constexpr int ND = bdf_c::MAX_ORDER + 3;
+  static constexpr int SMEM_DOUBLES_PER_THREAD = SMEM_VEC_ROWS * N + SMEM_MATS * N * N;
   using Out = SolOutDev<Prob, M_BDF, FEAT>;
   using Mat = typename std_conditional<REG, RegMat<N>, SmemMat<N, BLK>>::type;
 
   i64 idx;
   double x, current_h;
   double y[N], p[PS];
-  double d[ND][N];
+  double* sm;                   // this thread's column of the block's shared memory
   Mat jac, lu;
   int pivot[N];
-  double current_c, pend;       // pend: change_d factor owed to d by the previous pass (1.0 = none)
+  double current_c, pend, jx;   // pend: change_d factor owed to D by the previous pass (1.0 = none)
   u32 nfev, njev, nlu, nstep, naccpt, nrejct;
   int order, n_equal_steps, status;
-  bool lu_is_current;
+  bool lu_is_current, jac_pending;
   Out so;
 
+  __device__ __forceinline__ double& D(int k, int i) { return sm[(k * N + i) * BLK]; }
+  __device__ __forceinline__ double& S(int k, int i) { return sm[((ND + k) * N + i) * BLK]; }
+  __device__ __forceinline__ double& JY(int i) { return sm[((ND + NS) * N + i) * BLK]; }
+
   __device__ __forceinline__ void bind_storage() {
-    if constexpr (!REG) { jac = smem_mat<N, BLK>(0); lu = smem_mat<N, BLK>(1); }
+    extern __shared__ double ivpb_smem[];
+    sm = ivpb_smem + threadIdx.x;
+    if constexpr (!REG) {
+      jac.b = ivpb_smem + (size_t)SMEM_VEC_ROWS * N * BLK + threadIdx.x;
+      lu.b = jac.b + (size_t)N * N * BLK;
+    }
   }
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
     x = tev;
@@ -662,70 +688,42 @@ struct BdfTraj {
     return sqrt(sum / (double)N);
   }
 
-  // change_d (bdf.rs:669-713): D <- (R(order, factor) U(order, 1))^T D on rows 0..order, where
-  // compute_r(order, f)[i][j] = prod_{l=1..i} (l - 1 - f j) / l  (row 0 = 1, column 0 = 0 below row 0) and the
-  // order only selects the leading (order+1) x (order+1) block.  The reference forms RU = R U first (matmul,
-  // zero R entries skipped) and then accumulates scratch[row] += RU[k][row] * D[k] over k ascending; the loop
-  // below walks k once, carrying row k of R in six registers, which performs the same operations in the same
-  // order per output element.  U is a compile-time constant (u_entry), upper triangular.
-  static __host__ __device__ constexpr double u_entry(int i, int j) {      // compute_r(order, 1.0)[i][j]
-    if (i == 0) return 1.0;
-    if (j == 0) return 0.0;
-    double r = 1.0;
-    for (int l = 1; l <= i; ++l) r = r * (((double)l - 1.0 - 1.0 * (double)j) / (double)l);
-    return r;
-  }
-  __device__ __forceinline__ void change_d(double factor) {
-    constexpr int S = bdf_c::MAX_ORDER + 1;
+  // change_d (bdf.rs:669-713): D <- (R(order, factor) U(order, 1))^T D on rows 0..order, with
+  // compute_r(order, f)[i][j] = prod_{l=1..i} (l - 1 - f j) / l (row 0 = 1, column 0 = 0 below row 0).  The
+  // reference forms RU = R U first (matmul) and then accumulates scratch[row] += RU[k][row] * D[k] over k
+  // ascending; the loop below walks k once, carrying row k of R in six registers, which performs the same
+  // operations in the same order per output element.
+  __device__ __noinline__ void change_d(double factor) {
+    using namespace bdf_c;
     if (factor == 1.0) return;
-    const int ord = order < bdf_c::MAX_ORDER ? order : bdf_c::MAX_ORDER;
-    double scratch[S][N];
+    const int ord = order < MAX_ORDER ? order : MAX_ORDER;
+    for (int row = 0; row <= ord; ++row)
 #pragma unroll
-    for (int row = 0; row < S; ++row)
+      for (int i = 0; i < N; ++i) S(row, i) = 0.0;
+    double rk[NS];
 #pragma unroll
-      for (int i = 0; i < N; ++i) scratch[row][i] = 0.0;
-    double rk[S];                      // row k of R
-#pragma unroll
-    for (int j = 0; j < S; ++j) rk[j] = 1.0;
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
+    for (int j = 0; j < NS; ++j) rk[j] = 1.0;
+    for (int k = 0; k <= ord; ++k) {
       if (k > 0) {
+        const double kd = (double)k;
         rk[0] = rk[0] * 0.0;           // m[k][0] is never written (stays 0), bdf.rs:698-703
 #pragma unroll
-        for (int j = 1; j < S; ++j) rk[j] = rk[j] * (((double)k - 1.0 - factor * (double)j) / (double)k);
+        for (int j = 1; j < NS; ++j) rk[j] = rk[j] * ((kd - 1.0 - factor * (double)j) / kd);
       }
-      if (k <= ord) {
+      for (int row = 0; row <= ord; ++row) {
+        double coeff = 0.0;            // RU[k][row] = sum_{m <= ord} R[k][m] U[m][row], zero R entries skipped
 #pragma unroll
-        for (int row = 0; row < S; ++row) {
-          if (row <= ord) {
-            double coeff = 0.0;        // RU[k][row] = sum_m R[k][m] U[m][row]
+        for (int m = 0; m < NS; ++m)
+          if (m <= ord && rk[m] != 0.0) coeff += rk[m] * BDF_U[m][row];
+        if (coeff != 0.0) {
 #pragma unroll
-            for (int m = 0; m < S; ++m) {
-              // U is upper triangular (u_entry(m, row) == 0 for m > row): those terms add an exact zero in the
-              // reference and are skipped here at compile time; m <= row <= ord holds for the rest.
-              if (u_entry(m, row) != 0.0) {
-                const double um = u_entry(m, row);
-#ifdef IVPB_STRICT
-                if (rk[m] != 0.0) coeff += rk[m] * um;     // matmul skips zero R entries (bdf.rs:722-725)
-#else
-                coeff = fma(rk[m], um, coeff);
-#endif
-              }
-            }
-            if (coeff != 0.0) {
-#pragma unroll
-              for (int i = 0; i < N; ++i) scratch[row][i] += coeff * d[k][i];
-            }
-          }
+          for (int i = 0; i < N; ++i) S(row, i) += coeff * D(k, i);
         }
       }
     }
+    for (int row = 0; row <= ord; ++row)
 #pragma unroll
-    for (int row = 0; row < S; ++row)
-      if (row <= ord) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) d[row][i] = scratch[row][i];
-      }
+      for (int i = 0; i < N; ++i) D(row, i) = S(row, i);
   }
 
   __device__ __forceinline__ bool init(const KArgs& a, i64 index) {
@@ -746,8 +744,10 @@ struct BdfTraj {
     double f0[N];
     Prob::ode(x, y, p, f0);
     nfev = 1;
-    eval_jac<Prob>(a, x, y, p, jac);
-    njev = 1;
+    // f.jac(x, y) (bdf.rs:151-153): evaluated by the single Jacobian site at the top of the first pass
+    jx = x; jac_pending = true; njev = 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) JY(i) = y[i];
     double h_abs;
     if (a.has_first_step) {
       h_abs = fabs(a.first_step);
@@ -759,12 +759,11 @@ struct BdfTraj {
     }
     h_abs = fmin(h_abs, fmax(hmax, bdf_c::MINPOS));
     current_h = h_abs;
+    for (int k = 2; k < ND; ++k)
 #pragma unroll
-    for (int k = 0; k < ND; ++k)
+      for (int i = 0; i < N; ++i) D(k, i) = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) d[k][i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { d[0][i] = y[i]; d[1][i] = f0[i] * current_h * direction; }
+    for (int i = 0; i < N; ++i) { D(0, i) = y[i]; D(1, i) = f0[i] * current_h * direction; }
     if constexpr (FEAT != 0) {
       double cont[7][N];
 #pragma unroll
@@ -814,12 +813,23 @@ struct BdfTraj {
     const int newton_maxiter = 4;
     const double newton_tol = a.newton_tol;
 
+    // The single Jacobian site.  The reference evaluates f.jac at three places -- before the loop (x0, y0),
+    // after a failed Newton iteration (x_new, y_predict; bdf.rs:450) and after an order change (x, y;
+    // bdf.rs:604-607) -- always as the last use of the old Jacobian before the next factorisation, so
+    // evaluating it here, at the top of the following trip, from the saved point is equivalent.
+    if (jac_pending) {
+      double jy[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) jy[i] = JY(i);
+      eval_jac<Prob>(a, jx, jy, p, jac);
+      jac_pending = false;
+    }
     if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
     if (current_h < MINPOS) { status = ST_SMALL; return true; }
     double h_try = current_h, h_signed = 0.0, x_new = x;
     const double x_start = x;
     // The reference calls change_d at up to three places before the step and once at the end of the previous
-    // trip; here the four calls run through ONE inlined copy of change_d (stage 0 = the owed one).
+    // trip; here the four calls run through ONE call site (stage 0 = the owed one).
     for (int stage = 0; stage < 4; ++stage) {
       double factor = 1.0;
       if (stage == 0) { factor = pend; pend = 1.0; }
@@ -847,20 +857,19 @@ struct BdfTraj {
     nstep += 1;
 
     double y_predict[N], scale[N], psi[N];
+    const double alpha_o = BDF_ALPHA[order];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double sum = 0.0;
-#pragma unroll
-      for (int k = 0; k <= MAX_ORDER; ++k) if (k <= order) sum += d[k][i];
+      for (int k = 0; k <= order; ++k) sum += D(k, i);
       y_predict[i] = sum;
       scale[i] = a.atol[i] + a.rtol[i] * fabs(sum);
       if (scale[i] == 0.0) scale[i] = EPS;
       double s = 0.0;
-#pragma unroll
-      for (int j = 1; j <= MAX_ORDER; ++j) if (j <= order) s += gamma(j) * d[j][i];
-      psi[i] = s / alpha(order);
+      for (int j = 1; j <= order; ++j) s += BDF_GAMMA[j] * D(j, i);
+      psi[i] = s / alpha_o;
     }
-    const double c = h_signed / alpha(order);
+    const double c = h_signed / alpha_o;
     if (!lu_is_current || fabs(c - current_c) / fmax(fabs(c), 1.0) > 0.1) {
 #pragma unroll
       for (int r = 0; r < N; ++r)
@@ -892,7 +901,7 @@ struct BdfTraj {
         if (rate >= 1.0) rate_condition = true;
         else {
           const double remaining = (double)(newton_maxiter - iters);
-          const double estimate = ivpb_libm_pow(rate, remaining) / (1.0 - rate) * dy_norm;
+          const double estimate = ivpb_pow_call(rate, remaining) / (1.0 - rate) * dy_norm;
           if (estimate > newton_tol) rate_condition = true;
         }
       }
@@ -908,22 +917,24 @@ struct BdfTraj {
       iters += 1;
     }
     if (!converged) {
-      eval_jac<Prob>(a, x_new, y_predict, p, jac);           // bdf.rs:450
-      njev += 1;
+      jx = x_new; jac_pending = true; njev += 1;             // f.jac(x_new, y_predict), bdf.rs:450
+#pragma unroll
+      for (int i = 0; i < N; ++i) JY(i) = y_predict[i];
       lu_is_current = false;
       retry(0.5);
       return false;
     }
     const double safety = SAFETY * (2.0 * (double)newton_maxiter + 1.0) / (2.0 * (double)newton_maxiter + (double)(iters + 1));
+    const double errc = BDF_ERRC[order];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       scale[i] = a.atol[i] + a.rtol[i] * fabs(y_new[i]);
       if (scale[i] == 0.0) scale[i] = EPS;
-      rhs[i] = error_const(order) * delta[i];
+      rhs[i] = errc * delta[i];
     }
     const double error_norm = wrms(rhs, scale);
     if (error_norm > 1.0) {
-      double factor = safety * ivpb_libm_pow(error_norm, -1.0 / ((double)order + 1.0));
+      double factor = safety * ivpb_pow_call(error_norm, -1.0 / ((double)order + 1.0));
       factor = fmax(factor, MIN_FACTOR);
       retry(factor);                                         // lu_is_current is NOT cleared (bdf.rs:481-489)
       return false;
@@ -934,21 +945,17 @@ struct BdfTraj {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       y[i] = y_new[i];
-#pragma unroll
-      for (int k = 2; k < ND; ++k)         // d[order+2] = delta - d[order+1]; d[order+1] = delta
-        d[k][i] = opaque_sel(k == order + 2, delta[i] - d[k - 1][i], d[k][i]);
-#pragma unroll
-      for (int k = 1; k < ND; ++k) d[k][i] = opaque_sel(k == order + 1, delta[i], d[k][i]);
-#pragma unroll
-      for (int k = MAX_ORDER; k >= 0; --k) d[k][i] = opaque_sel(k <= order, d[k][i] + d[k + 1][i], d[k][i]);
+      D(order + 2, i) = delta[i] - D(order + 1, i);
+      D(order + 1, i) = delta[i];
+      for (int k = order; k >= 0; --k) D(k, i) += D(k + 1, i);
     }
     if constexpr (FEAT != 0) {
       double cont[7][N];                    // D0, D1..D5 (zero above the order), order marker (bdf.rs:506-514)
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        cont[0][i] = d[0][i];
+        cont[0][i] = D(0, i);
 #pragma unroll
-        for (int k = 0; k < MAX_ORDER; ++k) cont[1 + k][i] = (k + 1 <= order) ? d[k + 1][i] : 0.0;
+        for (int k = 0; k < MAX_ORDER; ++k) cont[1 + k][i] = (k + 1 <= order) ? D(k + 1, i) : 0.0;
         cont[6][i] = (double)order;
       }
       double tev, yev[N];
@@ -961,37 +968,30 @@ struct BdfTraj {
       const double INF = __longlong_as_double(0x7ff0000000000000LL);
       double err_m = INF, err_p = INF;
       if (order > 1) {
+        const double ec = BDF_ERRC[order - 1];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double dv = 0.0;
-#pragma unroll
-          for (int k = 2; k <= MAX_ORDER; ++k) dv = opaque_sel(k == order, d[k][i], dv);
-          rhs[i] = error_const(order - 1) * dv;
-        }
+        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order, i);
         err_m = wrms(rhs, scale);
       }
       if (order < MAX_ORDER) {
+        const double ec = BDF_ERRC[order + 1];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          double dv = 0.0;
-#pragma unroll
-          for (int k = 3; k < ND; ++k) dv = opaque_sel(k == order + 2, d[k][i], dv);
-          rhs[i] = error_const(order + 1) * dv;
-        }
+        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order + 2, i);
         err_p = wrms(rhs, scale);
       }
-      const double f0 = ivpb_libm_pow(err_m, -1.0 / ((double)order + 0.0));
-      const double f1 = ivpb_libm_pow(error_norm, -1.0 / ((double)order + 1.0));
-      const double f2 = ivpb_libm_pow(err_p, -1.0 / ((double)order + 2.0));
-      // Iterator::max_by keeps the LAST maximal element (bdf.rs:577-583)
+      // factors[idx] = errors[idx]^(-1 / (order + idx)); Iterator::max_by keeps the LAST maximal element
+      // (bdf.rs:577-583)
+      double fbest = 0.0, max_factor = 0.0;
       int best = 0;
-      double fb = f0;
-      if (!(f1 < fb)) { best = 1; fb = f1; }
-      if (!(f2 < fb)) { best = 2; fb = f2; }
+      for (int k = 0; k < 3; ++k) {
+        const double e = k == 0 ? err_m : (k == 1 ? error_norm : err_p);
+        const double f = ivpb_pow_call(e, -1.0 / ((double)order + (double)k));
+        if (k == 0 || !(f < fbest)) { best = k; fbest = f; }
+        max_factor = fmax(max_factor, f);
+      }
       int new_order = order;
       if (best == 0 && order > 1) new_order -= 1;
       else if (best == 2 && order < MAX_ORDER) new_order += 1;
-      const double max_factor = fmax(fmax(fmax(0.0, f0), f1), f2);
       const double step_factor = fmin(safety * max_factor, MAX_FACTOR);
       const int old_order = order;
       order = new_order;
@@ -999,7 +999,11 @@ struct BdfTraj {
       current_h *= step_factor;
       n_equal_steps = 0;
       lu_is_current = false;
-      if (new_order != old_order) { eval_jac<Prob>(a, x, y, p, jac); njev += 1; }
+      if (new_order != old_order) {                          // f.jac(x, y), bdf.rs:604-607
+        jx = x; jac_pending = true; njev += 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) JY(i) = y[i];
+      }
     }
     return false;
   }
@@ -1010,7 +1014,7 @@ struct ImplicitSel {
   static constexpr bool REG = MatSel<Prob::N>::REG;
   static constexpr int BLK = MatSel<Prob::N>::BLK;
   using Traj = typename std_conditional<METHOD == M_RADAU, RadauTraj<Prob, FEAT, REG, BLK>, BdfTraj<Prob, FEAT, REG, BLK>>::type;
-  static constexpr int SMEM_BYTES = Traj::SMEM_MATS * Prob::N * Prob::N * BLK * 8;
+  static constexpr int SMEM_BYTES = Traj::SMEM_DOUBLES_PER_THREAD * BLK * 8;
 };
 
 template <class Prob, int METHOD, int FEAT>

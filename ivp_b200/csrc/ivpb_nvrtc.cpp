@@ -194,8 +194,12 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   int block = 128;
   size_t smem = 0;
   if (method >= 4) {
+    // must match ivpb::MatSel / RadauTraj / BdfTraj::SMEM_DOUBLES_PER_THREAD (ivpb_implicit.cuh)
     block = up.n <= 6 ? 128 : 64;
-    if (up.n > 3) smem = (size_t)(method == 4 ? 4 : 2) * up.n * up.n * block * 8;
+    size_t doubles = 0;
+    if (up.n > 3) doubles += (size_t)(method == 4 ? 4 : 2) * up.n * up.n;   // Jacobian + iteration matrices
+    if (method == 5) doubles += (size_t)15 * up.n;                          // BDF: D (8 rows), scratch (6), Jacobian point
+    smem = doubles * block * 8;
     if (smem > 0) {
       CUresult ar = A.FuncSetAttribute(it->second.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
       if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
