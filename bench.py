@@ -49,6 +49,9 @@ WORKLOADS = {
     "robertson_bdf": ("robertson", "BDF", 1e-6, 1e-6, 13, 3),
     "vdpstiff_radau": ("vdp_stiff", "RADAU", 1e-4, 1e-6, 5, 2),
     "vdpstiff_bdf": ("vdp_stiff", "BDF", 1e-4, 1e-6, 5, 2),
+    "linear100_dopri5": ("linear100", "DOPRI5", 1e-6, 1e-8, 100, 100),       # warp-per-trajectory kernels (n > 32)
+    "medakzo_radau": ("medakzo", "RADAU", 1e-5, 1e-7, 900, 64),              # warp-cooperative LU, n = 64
+    "medakzo_bdf": ("medakzo", "BDF", 1e-5, 1e-7, 900, 64),
 }
 N_T_EVAL = {"cr3bp_dop853_teval": 101}
 NOMINAL_FP64_TFLOPS = 37.0   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz

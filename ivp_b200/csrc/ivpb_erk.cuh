@@ -138,15 +138,22 @@ struct ThreadLayout {
     for (int i = 0; i < NL; ++i) acc = IVPB_MA(q[i], q[i], acc);
     return acc;
   }
+  static __device__ __forceinline__ double sum(const double (&t)[NL]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) acc += t[i];
+    return acc;
+  }
   static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { Prob::ode(t, y, p, d); }
   static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { Prob::events(t, y, p, g); }
 };
 
-template <class Prob>
+template <class Prob, int EXTRA = 0>
 struct WarpLayout {
   static constexpr int N = Prob::N, NL = (Prob::N + 31) / 32;
   static constexpr bool WARP = true;
-  static constexpr int SMEM_DOUBLES_PER_WARP = 2 * Prob::N;      // full state row + reduction scratch
+  // full state row + reduction scratch (+ EXTRA doubles the implicit kernels keep per warp behind them)
+  static constexpr int SMEM_DOUBLES_PER_WARP = 2 * Prob::N + EXTRA;
   static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
   static __device__ __forceinline__ int gi(int i) { return lane() + 32 * i; }
   static __device__ __forceinline__ bool valid(int i) { return gi(i) < N; }
@@ -176,6 +183,39 @@ struct WarpLayout {
     return acc;
 #endif
   }
+  // sum of per-component terms in index order (strict) / by shuffle reduction (fast)
+  static __device__ __forceinline__ double sum(const double (&t)[NL]) {
+#ifdef IVPB_STRICT
+    double* sc = row() + N;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) if (valid(i)) sc[gi(i)] = t[i];
+    __syncwarp();
+    double acc = 0.0;
+    for (int i = 0; i < N; ++i) acc = acc + sc[i];
+    __syncwarp();
+    return acc;
+#else
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) if (valid(i)) acc += t[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    return acc;
+#endif
+  }
+  // component i of the RHS from the full state `ys`: the problem's ode_i, or -- for problems that only define
+  // the whole-vector ode (n <= 32) -- the whole RHS evaluated by every lane (correct, but n-fold redundant)
+  static __device__ __forceinline__ double ode_comp(double t, const double* ys, const double* p, int i) {
+    if constexpr (Prob::HAS_ODE_I) return Prob::ode_i(t, ys, p, i);
+    else {
+      double tmp[N];
+      Prob::ode(t, ys, p, tmp);
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) r = (k == i) ? tmp[k] : r;
+      return r;
+    }
+  }
   // publish a distributed vector as a full row in shared memory
   static __device__ __forceinline__ const double* full(const double* y) {
     double* r = row();
@@ -187,7 +227,7 @@ struct WarpLayout {
   static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) {
     const double* ys = full(y);
 #pragma unroll
-    for (int i = 0; i < NL; ++i) d[i] = valid(i) ? Prob::ode_i(t, ys, p, gi(i)) : 0.0;
+    for (int i = 0; i < NL; ++i) d[i] = valid(i) ? ode_comp(t, ys, p, gi(i)) : 0.0;
     __syncwarp();
   }
   static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) {

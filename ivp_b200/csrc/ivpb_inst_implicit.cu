@@ -15,6 +15,6 @@
 #define IVPB_SYM(tag) IVPB_CAT(ivpb_lookup_impl_, tag)
 #endif
 
-extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, int* block, int* smem) {
-  return ivpb::implicit_lookup<ivpb::IVPB_PROBLEM>(method, feat, block, smem);
+extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, int* block, int* smem, int* units) {
+  return ivpb::implicit_lookup<ivpb::IVPB_PROBLEM>(method, feat, block, smem, units);
 }

@@ -5,6 +5,7 @@
 #include "ivpb_erk.cuh"
 #ifdef IVPB_WITH_IMPLICIT
 #include "ivpb_implicit.cuh"
+#include "ivpb_implicit_warp.cuh"
 #endif
 
 namespace ivpb {
@@ -72,12 +73,34 @@ __global__ void __launch_bounds__(ImplicitSel<Prob, METHOD, FEAT>::BLK, 1) impli
   implicit_body<Prob, METHOD, FEAT>(a);
 }
 
+// n > IMPLICIT_MAX_N: one trajectory per warp, matrices in the warp's shared memory (ivpb_implicit_warp.cuh)
+template <class Prob, int METHOD, int FEAT>
+__global__ void __launch_bounds__(ImplicitWarpSel<Prob, METHOD, FEAT>::BLK, 1) implicit_warp_kernel(const __grid_constant__ KArgs a) {
+  implicit_warp_body<Prob, METHOD, FEAT>(a);
+}
+
 template <class Prob, int METHOD>
-__host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem) {
-  if constexpr (Prob::N > IMPLICIT_MAX_N) return nullptr;
-  else {
+__host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem, int* units) {
+  if constexpr (Prob::N > IMPLICIT_MAX_N) {
+    using Sel = ImplicitWarpSel<Prob, METHOD, 0>;
+    if constexpr (!Sel::FITS) return nullptr;
+    else {
+      if (block) *block = Sel::BLK;
+      if (smem) *smem = Sel::SMEM_BYTES;
+      if (units) *units = Sel::WARPS;
+      switch (feat) {
+        case 0: return (const void*)&implicit_warp_kernel<Prob, METHOD, 0>;
+        case K_OUT: return (const void*)&implicit_warp_kernel<Prob, METHOD, K_OUT>;
+        case K_OUT | K_EVENTS:
+          if constexpr (Prob::NEV > 0) return (const void*)&implicit_warp_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
+          else return nullptr;
+        default: return nullptr;
+      }
+    }
+  } else {
     if (block) *block = ImplicitSel<Prob, METHOD, 0>::BLK;
     if (smem) *smem = ImplicitSel<Prob, METHOD, 0>::SMEM_BYTES;
+    if (units) *units = ImplicitSel<Prob, METHOD, 0>::BLK;
     switch (feat) {
       case 0: return (const void*)&implicit_kernel<Prob, METHOD, 0>;
       case K_OUT: return (const void*)&implicit_kernel<Prob, METHOD, K_OUT>;
@@ -90,10 +113,10 @@ __host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem
 }
 
 template <class Prob>
-__host__ inline const void* implicit_lookup(int method, int feat, int* block, int* smem) {
+__host__ inline const void* implicit_lookup(int method, int feat, int* block, int* smem, int* units) {
   switch (method) {
-    case M_RADAU: return implicit_lookup_feat<Prob, M_RADAU>(feat, block, smem);
-    case M_BDF: return implicit_lookup_feat<Prob, M_BDF>(feat, block, smem);
+    case M_RADAU: return implicit_lookup_feat<Prob, M_RADAU>(feat, block, smem, units);
+    case M_BDF: return implicit_lookup_feat<Prob, M_BDF>(feat, block, smem, units);
     default: return nullptr;
   }
 }

@@ -92,14 +92,15 @@ std::string drv_err(CUresult r) {
 std::string program_source(const ivpb_user_problem& up, bool implicit) {
   std::string s;
   s += "#include \"ivpb_problems_min.cuh\"\n";
-  s += implicit ? "#include \"ivpb_implicit.cuh\"\n" : "#include \"ivpb_erk.cuh\"\n";
+  s += implicit ? "#include \"ivpb_implicit_warp.cuh\"\n" : "#include \"ivpb_erk.cuh\"\n";
   s += "// ---- user source ----\n";
   s += up.src;
   s += "\n// ---- adaptor ----\n";
   s += "struct PUser : ivpb::ProblemDefaults<" + std::to_string(up.n) + ", " + std::to_string(up.p) + ", " +
        std::to_string(up.n_events) + "> {\n";
   if (up.n > 32)
-    s += "  static __device__ __forceinline__ double ode_i(double t, const double* y, const double* p, int i) { return ivp_ode_i(t, y, p, i); }\n";
+    s += "  static constexpr bool HAS_ODE_I = true;\n"
+         "  static __device__ __forceinline__ double ode_i(double t, const double* y, const double* p, int i) { return ivp_ode_i(t, y, p, i); }\n";
   else
     s += "  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { ivp_ode(t, y, p, d); }\n";
   if (up.n_events > 0)
@@ -109,7 +110,11 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
     s += "  static __device__ __forceinline__ void jac(double t, const double* y, const double* p, double* J) { ivp_jac(t, y, p, J); }\n";
   }
   s += "};\n";
-  if (implicit) {
+  if (implicit && up.n > 8) {
+    s += "extern \"C\" __global__ void __launch_bounds__((ivpb::ImplicitWarpSel<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>::BLK), 1) "
+         "ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
+    s += "  ivpb::implicit_warp_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
+  } else if (implicit) {
     s += "extern \"C\" __global__ void __launch_bounds__((ivpb::ImplicitSel<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>::BLK), 1) "
          "ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
     s += "  ivpb::implicit_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
@@ -176,10 +181,6 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   const int key = device * 4096 + method * 64 + feat * 2 + (strict ? 1 : 0);
   auto it = cache->mods.find(key);
   if (it == cache->mods.end()) {
-    if (method >= 4 && up.n > 8) {
-      ivpb_set_error(ctx, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
-      return IVPB_ERR_CONFIG;
-    }
     std::vector<char> cubin;
     std::string log;
     if (int rc = compile_cubin(up, method, feat, strict, cubin, log)) { ivpb_set_error(ctx, log); return rc; }
@@ -193,7 +194,18 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   // launch shape: explicit kernels 128 threads; implicit kernels follow ivpb::MatSel (ivpb_implicit.cuh)
   int block = 128;
   size_t smem = 0;
-  if (method >= 4) {
+  long long units_per_block = 0;
+  if (method >= 4 && up.n > 8) {
+    // one trajectory per warp; must match ivpb::ImplicitWarpSel (ivpb_implicit_warp.cuh)
+    const size_t n = (size_t)up.n, matd = (n | 1) * n;
+    const size_t extra = method == 4 ? 3 * n + 4 * matd + n : n + 14 * n + 2 * matd + n;
+    const size_t bytes = (2 * n + extra) * 8;
+    if (bytes > 227 * 1024) { ivpb_set_error(ctx, "implicit methods: the per-warp matrices of this state size do not fit shared memory"); return IVPB_ERR_CONFIG; }
+    const int warps = bytes * 4 <= 200 * 1024 ? 4 : (bytes * 2 <= 200 * 1024 ? 2 : 1);
+    block = 32 * warps; smem = bytes * warps; units_per_block = warps;
+    CUresult ar = A.FuncSetAttribute(it->second.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+    if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
+  } else if (method >= 4) {
     // must match ivpb::MatSel / RadauTraj / BdfTraj::SMEM_DOUBLES_PER_THREAD (ivpb_implicit.cuh)
     block = up.n <= 6 ? 128 : 64;
     size_t doubles = 0;
@@ -205,7 +217,7 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
       if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
     }
   }
-  long long units_per_block = block;
+  if (units_per_block == 0) units_per_block = block;
   if (method < 4 && up.n > 32) {       // one trajectory per warp: WarpLayout needs 2 n doubles of shared memory per warp
     smem = (size_t)(block / 32) * 2 * up.n * 8;
     units_per_block = block / 32;

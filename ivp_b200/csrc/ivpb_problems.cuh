@@ -143,11 +143,13 @@ struct PCannon : ProblemDefaults<2, 0, 1> {     // reference tests/test_ivp.py:1
 
 // ---- large systems: one trajectory per warp (WarpLayout), the RHS is given per component ----
 struct PLinear100 : ProblemDefaults<100, 0, 0> {  // reference benches/benchmark.py:39-41,137-146 (dy/dt = -y, N = 100)
+  static constexpr bool HAS_ODE_I = true;
   IVPB_DEV double ode_i(double, const double* y, const double*, int i) { return -y[i]; }
 };
 
 // MEDAKZO (reference tests/test_ivp.py:77-101 `fun_medazko`) on 32 grid points: n = 64, stiff reaction-diffusion.
 struct PMedakzo64 : ProblemDefaults<64, 0, 0> {
+  static constexpr bool HAS_ODE_I = true;
   IVPB_DEV double z(double t, const double* y, int m) {      // y padded as hstack((phi, 0, y, y[-2]))
     if (m == 0) return t <= 5.0 ? 2.0 : 0.0;
     if (m == 1) return 0.0;

@@ -13,6 +13,7 @@ template <int N_, int P_, int NEV_>
 struct ProblemDefaults {
   static constexpr int N = N_, P = P_, NEV = NEV_;
   static constexpr bool HAS_JAC = false;
+  static constexpr bool HAS_ODE_I = false;   // per-component RHS `double ode_i(t, y, p, i)` for the warp-per-trajectory kernels
   IVPB_DEV void events(double, const double*, const double*, double*) {}
   IVPB_DEV void jac(double, const double*, const double*, double*) {}
   // IVP::event_config default (src/ivp.rs:51-53 -> EventConfig::new: All, non-terminal)

@@ -25,12 +25,12 @@ using ivpb::u64;
 // ------------------------------------------------------------------------------------------------
 // Built-in kernel tables (one lookup function per problem and floating-point mode; ivpb_inst.cu)
 typedef const void* (*lookup_fn)(int method, int feat, ivpb_pinfo* info);
-typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* smem);
+typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* smem, int* units);
 #define DECL(tag)                                                                  \
   extern "C" const void* ivpb_lookup_##tag(int, int, ivpb_pinfo*);                 \
   extern "C" const void* ivpb_lookup_strict_##tag(int, int, ivpb_pinfo*);          \
-  extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*);             \
-  extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*);
+  extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*, int*);       \
+  extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
 DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64)
 #undef DECL
@@ -213,6 +213,8 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
       if (o->atol[i] < 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: negative absolute tolerance");
     if (o->has_first_step && o->first_step == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: first_step is zero");
   }
+  if (o->jac_mode == 1 && pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
+    return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1: the warp-cooperative implicit kernels (n > 8) use the finite-difference Jacobian only");
   if (o->jac_mode == 1 && !pi.has_jac && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
   return 0;
@@ -371,8 +373,6 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
 
   if (pi.user) {
-    if (warp_mode && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
-      return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
     int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, strict, &a, sizeof(a), N,
                                a.static_sched, stream);
     if (rc) return rc;
@@ -381,10 +381,10 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   }
 
   const void* kern = nullptr;
-  int kblock = block, ksmem = 0;
+  int kblock = block, ksmem = 0, kunits = 0;
   if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
-    kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem);
-    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: state size exceeds the thread-per-trajectory limit (8)");
+    kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem, &kunits);
+    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: the per-warp matrices of this state size do not fit shared memory");
     if (ksmem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
   } else {
     kern = BUILTIN[problem][strict](o->method, feat, nullptr);
@@ -398,7 +398,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kblock, ksmem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)dev.sms * occ;
-  const int64_t units_per_block = warp_mode && !(o->method == IVPB_RADAU || o->method == IVPB_BDF) ? kblock / 32 : kblock;
+  const int64_t units_per_block = kunits > 0 ? kunits : (warp_mode ? kblock / 32 : kblock);
   const int64_t need = (N + units_per_block - 1) / units_per_block;
   if (a.static_sched || need < grid) grid = need;
   void* kargs[] = {&a};

@@ -63,4 +63,12 @@ def ensemble(name: str, N: int, offset: int = 0):
         u = uniform(N, 2, offset=offset)
         y0 = np.stack([2.0 + (u[:, 0] - 0.5), u[:, 1] - 0.5], axis=1)
         return "vdp_mu", y0, np.full((N, 1), 1000.0), 0.0, 3000.0
+    if name == "linear100":      # benches/benchmark.py:137-146 (y' = -y, N = 100), y0 ~ U(0.5, 1.5)
+        u = uniform(N, 100, offset=offset)
+        return "linear100", 0.5 + u, None, 0.0, 10.0
+    if name == "medakzo":        # tests/test_ivp.py:244-269 on 32 grid points: u = 0, v = v0 ~ U(0.9, 1.1)
+        u = uniform(N, 1, offset=offset)
+        y0 = np.zeros((N, 64))
+        y0[:, 1::2] = 0.9 + 0.2 * u
+        return "medakzo64", y0, None, 0.0, 20.0
     raise KeyError(name)

@@ -753,3 +753,52 @@ def test_zero_copy_pinned_buffers_match_staged_copies():
     ref = ib.solve_ivp_batch(prob, t0, 25.0, y0, par, Options(method=Method.DOP853, rtol=1e-8, atol=1e-8))   # pageable => staged
     assert np.array_equal(ref.y_final, res[0][3]) and np.array_equal(ref.counters, res[0][1])
     lib.ivpb_host_free(bufs["y0"]); lib.ivpb_host_free(bufs["par"])
+
+
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_warp_cooperative_implicit_medakzo(oracle, method):
+    """8 < n <= 64: one trajectory per warp, Jacobian / E1 / E2 in the warp's shared memory, warp-cooperative
+    DEC / SOL / DECC / SOLC (ivpb_implicit_warp.cuh).  MEDAKZO (reference tests/test_ivp.py:77-101, 244-269) on 32
+    grid points, n = 64.  Strict build: bit-exact, including counters and t_eval samples."""
+    ym = medakzo_y0(21)
+    te = np.linspace(0.0, 7.0, 8)          # crosses the phi discontinuity at t = 5
+    for extra in ({}, {"t_eval": te}):
+        opts = Options(method=method, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_STRICT_FP, **extra)
+        g = ib.solve_ivp_batch("medakzo64", 0.0, 7.0, ym, None, opts)
+        o = oracle.solve_batch(PROBLEMS["medakzo64"], 0.0, 7.0, ym, None, opts, nthreads=8)
+        exact(g, o)
+        if extra:
+            exact(g, o, ("n_out", "t_out", "y_out"))
+    assert np.all(g.status == Status.Success) and np.all(g.njev > 0) and np.all(g.nlu > 0)
+    # default (FMA + shuffle-reduction) build: inside tolerance
+    f = ib.solve_ivp_batch("medakzo64", 0.0, 7.0, ym, None, Options(method=method, rtol=1e-5, atol=1e-7))
+    assert np.array_equal(f.status, o.status)
+    assert close(f.y_final, o.y_final, 1e-4, 1e-6).all()
+    with pytest.raises(ib.ConfigError):
+        ib.solve_ivp_batch("medakzo64", 0.0, 1.0, ym, None, Options(method=method, jac_mode=1))
+
+
+USER_DIFFUSION12 = r"""
+// stiff linear diffusion on 12 nodes, whole-vector RHS only (no ivp_ode_i): exercises the n <= 32 fallback of the
+// warp-cooperative implicit kernels
+__device__ void ivp_ode(double t, const double* y, const double* p, double* d) {
+  for (int i = 0; i < 12; ++i) {
+    const double l = i > 0 ? y[i - 1] : 0.0, r = i < 11 ? y[i + 1] : 0.0;
+    d[i] = p[0] * (l - 2.0 * y[i] + r);
+  }
+}
+"""
+
+
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_nvrtc_user_problem_warp_cooperative_implicit(method):
+    from ivp_b200 import api
+    user = api.Problem.from_cuda_source(USER_DIFFUSION12, n=12, p=1)
+    N = 40
+    y0 = np.tile(np.sin(np.pi * np.arange(1, 13) / 13.0), (N, 1))
+    par = (1000.0 + 10.0 * np.arange(N))[:, None]
+    g = ib.solve_ivp_batch(user, 0.0, 0.01, y0, par, Options(method=method, rtol=1e-7, atol=1e-10))
+    assert np.all(g.status == Status.Success)
+    lam = -2.0 * (1.0 - np.cos(np.pi / 13.0))            # sin(pi i / 13) is an eigenvector of the 1-D Laplacian
+    ref = y0 * np.exp(par * lam * 0.01)
+    np.testing.assert_allclose(g.y_final, ref, rtol=2e-5, atol=1e-9)
