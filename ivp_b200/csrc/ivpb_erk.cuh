@@ -546,7 +546,20 @@ struct ErkTraj {
     idx = index;
     x = a.t0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = L::valid(i) ? a.y0[index * NG + L::gi(i)] : 0.0;
+    for (int i = 0; i < N; ++i) y[i] = 0.0;
+    if constexpr (!L::WARP && (NG % 2 == 0)) {
+      if (a.vec_io) {                       // one row = NG/2 aligned 16-byte words
+        const double2* src = reinterpret_cast<const double2*>(a.y0 + index * NG);
+#pragma unroll
+        for (int i = 0; i < NG / 2; ++i) { const double2 v = __ldg(src + i); y[2 * i] = v.x; y[2 * i + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = a.y0[index * NG + i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = L::valid(i) ? a.y0[index * NG + L::gi(i)] : 0.0;
+    }
     if constexpr (P > 0) {
 #pragma unroll
       for (int i = 0; i < P; ++i) p[i] = a.params[index * P + i];
@@ -586,14 +599,25 @@ struct ErkTraj {
   // when a terminal event interrupted the integration (step() moves it there).
   __device__ __forceinline__ void finish(const KArgs& a) {
     if (a.y_final) {
+      if constexpr (!L::WARP && (NG % 2 == 0)) {
+        if (a.vec_io) {
+          double2* dst = reinterpret_cast<double2*>(a.y_final + idx * NG);
 #pragma unroll
-      for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_final[idx * NG + L::gi(i)] = y[i];
+          for (int i = 0; i < NG / 2; ++i) dst[i] = make_double2(y[2 * i], y[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) a.y_final[idx * NG + i] = y[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_final[idx * NG + L::gi(i)] = y[i];
+      }
     }
     if (!L::leader()) return;                 // per-trajectory scalars: one writer
     if (a.status) a.status[idx] = status;
-    if (a.counters) {
-      u32* c = a.counters + idx * 6;
-      c[0] = nfev; c[1] = 0u; c[2] = 0u; c[3] = nstep; c[4] = naccpt; c[5] = nrejct;
+    if (a.counters) {                         // 24-byte row as three 8-byte words
+      uint2* c = reinterpret_cast<uint2*>(a.counters + idx * 6);
+      c[0] = make_uint2(nfev, 0u); c[1] = make_uint2(0u, nstep); c[2] = make_uint2(naccpt, nrejct);
     }
     if (a.t_final) a.t_final[idx] = x;
     if (a.h_next) a.h_next[idx] = h;

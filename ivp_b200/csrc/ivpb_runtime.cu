@@ -324,6 +324,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   a.h_next = d->h_next; a.n_out = d->n_out; a.t_out = d->t_out; a.y_out = d->y_out;
   a.ev_count = d->ev_count; a.ev_t = d->ev_t; a.ev_y = d->ev_y;
   a.seg_n = d->n_seg; a.seg_x = d->seg_x; a.seg_cont = d->seg_cont;
+  a.vec_io = ((reinterpret_cast<uintptr_t>(d_y0) | reinterpret_cast<uintptr_t>(d->y_final)) & 15u) == 0 && (pi.n % 2 == 0);
   if (!a.seg_n || !a.seg_x || !a.seg_cont) a.seg_cap = 0;      // nowhere to log the segments
   if (a.out_cap == 0 || (!a.t_out && !a.y_out && !a.n_out)) {
     if (!o->has_t_eval) a.out_cap = 0;    // nothing to store in step mode
