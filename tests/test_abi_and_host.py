@@ -216,3 +216,23 @@ int main() {
                            "-I", os.path.join(ROOT, "ivp_b200", "csrc"), str(src), "-o", str(exe)])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout
+
+
+def test_scipy_style_front_end_argument_handling():
+    """ivp_b200.scipy_api.solve_ivp (reference src/python/solve.rs:153-222): everything that can be checked without a GPU."""
+    from ivp_b200 import scipy_api
+    with pytest.raises(TypeError, match="callable cannot run on the device"):
+        scipy_api.solve_ivp(lambda t, y: -y, (0, 1), [1.0])
+    with pytest.raises(TypeError, match="unknown options"):
+        scipy_api.solve_ivp("decay", (0, 1), [1.0], args=(0.5,), bogus=1)
+    with pytest.raises(ValueError, match="parameters"):
+        scipy_api.solve_ivp("decay", (0, 1), [1.0])
+    with pytest.raises(ValueError, match="event specs"):
+        scipy_api.solve_ivp("sho", (0, 1), [1.0, 0.0], events=[object(), object()])
+
+    class Ev:
+        terminal, direction = True, -1.0
+    cfgs, has = scipy_api._event_configs(Ev(), 1)
+    assert has and cfgs[0].terminal_count == 1 and int(cfgs[0].direction) < 0
+    cfgs, has = scipy_api._event_configs(None, 1)
+    assert not has and cfgs[0].terminal_count is None

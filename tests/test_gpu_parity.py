@@ -802,3 +802,40 @@ def test_nvrtc_user_problem_warp_cooperative_implicit(method):
     lam = -2.0 * (1.0 - np.cos(np.pi / 13.0))            # sin(pi i / 13) is an eigenvector of the 1-D Laplacian
     ref = y0 * np.exp(par * lam * 0.01)
     np.testing.assert_allclose(g.y_final, ref, rtol=2e-5, atol=1e-9)
+
+
+def test_scipy_style_front_end():
+    """the reference's Python signature / OdeResult over the device ABI (src/python/solve.rs:153-432)."""
+    from ivp_b200 import scipy_api
+    si = pytest.importorskip("scipy.integrate")
+
+    # reference tests/test_ivp.py:152-170 (cannon: terminal event y[0] = 0 going down), golden numbers from there
+    class HitGround:
+        terminal, direction = True, -1
+    sol = scipy_api.solve_ivp("cannon", [0, 100], [0.0, 30.0], method="RK45", events=HitGround(), rtol=1e-9, atol=1e-9)
+    assert sol.status == 1 and sol.success and sol.message == "UserInterrupt"
+    assert sol.y.shape[0] == 2 and sol.y.shape[1] == sol.t.size
+    np.testing.assert_allclose(sol.t_events[0], [2 * 30.0 / 9.80665], rtol=1e-9)
+    np.testing.assert_allclose(sol.y_events[0][0], [0.0, -30.0], atol=1e-7)
+
+    # Van der Pol against SciPy, every method name the binding accepts; args -> parameter row; y as (n, n_points)
+    ref = si.solve_ivp(lambda t, y, mu: [y[1], mu * (1 - y[0] ** 2) * y[1] - y[0]], (0, 10), [2.0, 0.0], args=(1.0,),
+                       method="DOP853", rtol=1e-12, atol=1e-12, dense_output=True)
+    for name in ("RK23", "RK45", "DOP853", "Radau", "BDF"):
+        te = np.linspace(0, 10, 21)
+        r = scipy_api.solve_ivp("vdp_mu", (0, 10), [2.0, 0.0], method=name, t_eval=te, args=(1.0,), rtol=1e-7, atol=1e-9,
+                                dense_output=True, jac=True if name in ("Radau", "BDF") else None)
+        assert r.status == 0 and r.y.shape == (2, 21) and np.array_equal(r.t, te)
+        np.testing.assert_allclose(r.y, ref.sol(te), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(r.sol(3.3), ref.sol(3.3), rtol=2e-4, atol=2e-5)
+        assert r.sol(np.array([1.0, 2.0])).shape == (2, 2)
+        assert (r.njev > 0) == (name in ("Radau", "BDF")) and r.nfev > 0
+    # user problem as CUDA C + batched y0: one OdeResult per row
+    src = "__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = -p[0] * y[0]; }"
+    rs = scipy_api.solve_ivp(src, (0, 4), np.array([[1.0], [2.0], [3.0]]), args=(0.5,), rtol=1e-9, atol=1e-12)
+    assert len(rs) == 3
+    for k, r in enumerate(rs):
+        assert abs(r.y[0, -1] - (k + 1) * np.exp(-2.0)) < 1e-8 and r.t[0] == 0.0 and r.t[-1] == 4.0
+    # failure status: -1
+    r = scipy_api.solve_ivp("vdp_mu", (0, 10), [2.0, 0.0], args=(1.0,), rtol=1e-10, atol=1e-12, max_steps=5)
+    assert r.status == -1 and not r.success and r.message == "NeedLargerNMax"
