@@ -44,6 +44,7 @@ WORKLOADS = {
     "lorenz_dopri5": ("lorenz", "DOPRI5", 1e-6, 1e-9, 8, 3),
     "lorenz_rk4": ("lorenz", "RK4", 1e-6, 1e-9, 8, 3),
     "cr3bp_dop853_teval": ("cr3bp", "DOP853", 1e-10, 1e-12, 48, 6),          # configs[2]: 101 t_eval samples
+    "cr3bp_dop853": ("cr3bp", "DOP853", 1e-10, 1e-12, 48, 6),                # same, final state only (A/B)
     "ball_dopri5_events": ("ball", "DOPRI5", 1e-8, 1e-10, 4, 2),             # configs[3]
     "robertson_radau": ("robertson", "RADAU", 1e-6, 1e-6, 13, 3),            # configs[4]
     "robertson_bdf": ("robertson", "BDF", 1e-6, 1e-6, 13, 3),

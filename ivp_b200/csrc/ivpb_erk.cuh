@@ -1,8 +1,9 @@
 // ivpb_erk.cuh -- persistent explicit Runge-Kutta ensemble kernel for sm_100a (fp64).
 //
-// One trajectory per thread.  All stage vectors live in registers (fully unrolled, table-driven
-// stage sums whose slot indices fold at compile time), the Butcher coefficients become constant-bank
-// operands of DFMA, and every thread runs the reference's own controller:
+// One trajectory per thread (n <= 32; ThreadLayout) or per warp (n > 32; WarpLayout) -- the step code is written
+// once against a layout policy.  All stage vectors live in registers (fully unrolled, table-driven stage sums
+// whose slot indices fold at compile time), the Butcher coefficients become constant-bank operands of DFMA, and
+// every trajectory runs the reference's own controller:
 //   DOP853  reference src/methods/dop853.rs:114-670      DOPRI5  src/methods/dopri5.rs:122-478
 //   RK23    reference src/methods/rk23.rs:81-321         RK4     src/methods/rk4.rs:64-244
 //   hinit   reference src/methods/mod.rs:217-281
