@@ -13,7 +13,7 @@ namespace ivpb {
 // Small systems leave registers to spare: asking for 5 resident blocks (96 registers/thread) costs no spills
 // for n <= 2 and measured +4 % on the north-star kernel; larger systems keep the whole register file.
 #ifndef IVPB_MB_BIG
-#define IVPB_MB_BIG 3
+#define IVPB_MB_BIG 1
 #endif
 template <class Prob, int METHOD, int FEAT>
 __global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? 5 : (Prob::N <= 4 ? 1 : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
