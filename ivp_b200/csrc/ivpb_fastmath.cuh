@@ -17,10 +17,15 @@ __device__ __forceinline__ bool in_range(double x) {
   return hi - 0x03000000u < 0x7a000000u;      // roughly 1e-293 < |x| < 1e280
 }
 
+// Out-of-range arguments (zero, subnormal, huge, inf, NaN) take the exact library routines; one shared,
+// non-inlined copy per kernel keeps the call sites small (the implicit kernels are instruction-cache bound).
+static __device__ __noinline__ double rcp_slow(double x) { return 1.0 / x; }
+static __device__ __noinline__ double rsqrt_slow(double x) { return ::rsqrt(x); }
+
 // 1/x: MUFU.RCP64H seed r (relative error e ~ 2^-20), then one third-order step r (1 + e + e^2) with
 // e = 1 - x r: remaining error e^3 ~ 2^-60, i.e. rounding-limited, in 3 dependent DFMAs.
 __device__ __forceinline__ double rcp(double x) {
-  if (!in_range(x)) return 1.0 / x;
+  if (!in_range(x)) return rcp_slow(x);
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   const double e = fma(-x, r, 1.0);
@@ -30,7 +35,7 @@ __device__ __forceinline__ double rcp(double x) {
 // 1/sqrt(x), x > 0: MUFU.RSQ64H seed r (e = 1 - x r^2 ~ 2^-19), then one third-order step
 // r (1 + e/2 + 3 e^2 / 8): remaining error ~ (5/16) e^3 ~ 2^-59.
 __device__ __forceinline__ double rsqrt(double x) {
-  if (!in_range(x) || x < 0.0) return ::rsqrt(x);
+  if (!in_range(x) || x < 0.0) return rsqrt_slow(x);
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   const double e = fma(-(x * r), r, 1.0);
