@@ -839,3 +839,21 @@ def test_scipy_style_front_end():
     # failure status: -1
     r = scipy_api.solve_ivp("vdp_mu", (0, 10), [2.0, 0.0], args=(1.0,), rtol=1e-10, atol=1e-12, max_steps=5)
     assert r.status == -1 and not r.success and r.message == "NeedLargerNMax"
+
+
+def test_strict_build_reproduces_committed_golden_vectors():
+    """The strict CUDA build against the committed fixtures of tests/golden/ (bit for bit, no oracle at run time)."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "oracle_cases.npz"))
+    import dataclasses
+    for name in mg.CASES:
+        prob, y0, par, t0, tf, opts = mg.case_inputs(name)
+        g = ib.solve_ivp_batch(prob, t0, tf, y0, par, dataclasses.replace(opts, flags=IVPB_FLAG_STRICT_FP))
+        for f in mg.FIELDS:
+            v = getattr(g, f)
+            if v is not None and f"{name}/{f}" in gold:
+                assert np.array_equal(v, gold[f"{name}/{f}"], equal_nan=v.dtype.kind == "f"), (name, f)

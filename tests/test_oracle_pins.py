@@ -297,3 +297,21 @@ def test_lu_kats(oracle):
     for m in IMPLICIT:
         s = one(oracle, P_DECAY, 0.0, 10.0, [10.0], [0.5], Options(method=m, rtol=1e-8, atol=1e-10))
         assert s.status == Status.Success and abs(s.y[-1][0] - 10.0 * math.exp(-5.0)) < 1e-5
+
+
+def test_oracle_reproduces_committed_golden_vectors(oracle):
+    """tests/golden/oracle_cases.npz (generated by tests/golden/make_golden.py from the oracle; the reference itself
+    cannot run here): the oracle must keep producing exactly these bits -- guards against drift of the checker."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "oracle_cases.npz"))
+    for name in mg.CASES:
+        prob, y0, par, t0, tf, opts = mg.case_inputs(name)
+        o = oracle.solve_batch(mg.PROBLEMS[prob], t0, tf, y0, par, opts, nthreads=4)
+        for f in mg.FIELDS:
+            v = getattr(o, f)
+            if v is not None:
+                assert np.array_equal(v, gold[f"{name}/{f}"], equal_nan=v.dtype.kind == "f"), (name, f)
