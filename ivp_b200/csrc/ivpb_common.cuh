@@ -33,6 +33,7 @@ struct KArgs {
   double rtol[MAX_N], atol[MAX_N];   // scalar tolerances are broadcast by the host
   const double* rtol_ext;            // n > MAX_N with Tolerance::Vector: device arrays [n] (else null: rtol[0])
   const double* atol_ext;
+  double* scratch;       // implicit warp kernels: one Jacobian slot (n x (n|1) doubles) per warp of the grid
   double first_step, max_step, min_step;
   int has_first_step, has_max_step, has_min_step, static_sched;
   u64 max_steps;         // usize::MAX when Options.max_steps is None

@@ -240,7 +240,9 @@ struct RadauWarpTraj {
   static constexpr int NN = Prob::N;
   static constexpr int MATD = WMat<NN>::DOUBLES;
   // per warp behind the layout's 2n: staged vectors b1, b2, b3 (3n), four matrices, two pivot arrays (n doubles)
-  static constexpr int EXTRA = 3 * NN + 4 * MATD + NN;
+  // (the Jacobian itself lives in a per-warp global-memory slot, KArgs::scratch: it is touched O(n^2) times per
+  // trip against the O(n^3) of the factorisations, and leaving it out of shared memory doubles the resident warps)
+  static constexpr int EXTRA = 3 * NN + 3 * MATD + NN;
   using B = WarpImplBase<Prob, EXTRA>;
   using L = typename B::L;
   using LA = WarpLinAlg<NN>;
@@ -260,8 +262,8 @@ struct RadauWarpTraj {
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double* b2() const { return B::extra() + NN; }
   __device__ __forceinline__ double* b3() const { return B::extra() + 2 * NN; }
-  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + 3 * NN + k * MATD; return m; }
-  __device__ __forceinline__ int* ip1() const { return (int*)(B::extra() + 3 * NN + 4 * MATD); }
+  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + 3 * NN + (k - 1) * MATD; return m; }   // k = 1..3
+  __device__ __forceinline__ int* ip1() const { return (int*)(B::extra() + 3 * NN + 3 * MATD); }
   __device__ __forceinline__ int* ip2() const { return ip1() + NN; }
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
@@ -351,7 +353,8 @@ struct RadauWarpTraj {
     const double hmax = a.has_max_step ? a.max_step : fabs(a.tf - a.t0);
     const double hmin = a.has_min_step ? a.min_step : 0.0;
     const double newton_tol = a.newton_tol;
-    const WMat<NN> jac = mat(0), e1 = mat(1), e2r = mat(2), e2i = mat(3);
+    WMat<NN> jac; jac.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (i64)MATD;
+    const WMat<NN> e1 = mat(1), e2r = mat(2), e2i = mat(3);
 
     if (call_jac) { B::eval_jac_fd(x, y, p, jac); njev += 1; }
     if (call_decomp) {
@@ -561,7 +564,7 @@ struct BdfWarpTraj {
   static constexpr int MATD = WMat<NN>::DOUBLES;
   static constexpr int ND = bdf_c::MAX_ORDER + 3, NS = bdf_c::MAX_ORDER + 1;
   // per warp behind the layout's 2n: staging row b1 (n), D (8n), scratch (6n), two matrices, pivots (n/2 -> n)
-  static constexpr int EXTRA = NN + (ND + NS) * NN + 2 * MATD + NN;
+  static constexpr int EXTRA = NN + (ND + NS) * NN + 1 * MATD + NN;     // Jacobian in KArgs::scratch, see RadauWarpTraj
   using B = WarpImplBase<Prob, EXTRA>;
   using L = typename B::L;
   using LA = WarpLinAlg<NN>;
@@ -581,8 +584,8 @@ struct BdfWarpTraj {
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double& D(int k, int i) const { return B::extra()[NN + k * NN + L::gi(i)]; }          // local slot i
   __device__ __forceinline__ double& S(int k, int i) const { return B::extra()[NN + (ND + k) * NN + L::gi(i)]; }
-  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + NN + (ND + NS) * NN + k * MATD; return m; }
-  __device__ __forceinline__ int* pivot() const { return (int*)(B::extra() + NN + (ND + NS) * NN + 2 * MATD); }
+  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + NN + (ND + NS) * NN + (k - 1) * MATD; return m; }   // k = 1
+  __device__ __forceinline__ int* pivot() const { return (int*)(B::extra() + NN + (ND + NS) * NN + 1 * MATD); }
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
     x = tev;
@@ -716,7 +719,8 @@ struct BdfWarpTraj {
     const double hmin = fabs(a.has_min_step ? a.min_step : 0.0);
     const int newton_maxiter = 4;
     const double newton_tol = a.newton_tol;
-    const WMat<NN> jac = mat(0), lu = mat(1);
+    WMat<NN> jac; jac.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (i64)MATD;
+    const WMat<NN> lu = mat(1);
 
     if (jac_pending) { B::eval_jac_fd(jx, jy, p, jac); jac_pending = false; }
     if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
@@ -914,6 +918,7 @@ struct ImplicitWarpSel {
   static constexpr int BLK = 32 * WARPS;
   static constexpr int SMEM_BYTES = BYTES_PER_WARP * WARPS;
   static constexpr bool FITS = BYTES_PER_WARP <= 227 * 1024;
+  static constexpr int SCRATCH_DOUBLES_PER_WARP = WMat<Prob::N>::DOUBLES;     // the Jacobian slot in KArgs::scratch
 };
 
 template <class Prob, int METHOD, int FEAT>

@@ -90,7 +90,7 @@ __host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem
     else {
       if (block) *block = Sel::BLK;
       if (smem) *smem = Sel::SMEM_BYTES;
-      if (units) *units = Sel::WARPS;
+      if (units) *units = -Sel::WARPS;      // negative: warp-per-trajectory, needs KArgs::scratch (one Jacobian per warp)
       switch (feat) {
         case 0: return (const void*)&implicit_warp_kernel<Prob, METHOD, 0>;
         case K_OUT: return (const void*)&implicit_warp_kernel<Prob, METHOD, K_OUT>;

@@ -198,7 +198,7 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   if (method >= 4 && up.n > 8) {
     // one trajectory per warp; must match ivpb::ImplicitWarpSel (ivpb_implicit_warp.cuh)
     const size_t n = (size_t)up.n, matd = (n | 1) * n;
-    const size_t extra = method == 4 ? 3 * n + 4 * matd + n : n + 14 * n + 2 * matd + n;
+    const size_t extra = method == 4 ? 3 * n + 3 * matd + n : n + 14 * n + 1 * matd + n;    // Jacobian: KArgs::scratch
     const size_t bytes = (2 * n + extra) * 8;
     if (bytes > 227 * 1024) { ivpb_set_error(ctx, "implicit methods: the per-warp matrices of this state size do not fit shared memory"); return IVPB_ERR_CONFIG; }
     const int warps = bytes * 4 <= 200 * 1024 ? 4 : (bytes * 2 <= 200 * 1024 ? 2 : 1);

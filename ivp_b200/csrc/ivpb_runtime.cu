@@ -80,7 +80,7 @@ struct Device {
   cudaStream_t stream = nullptr;
   u64* queue = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
-  Buf y0, params, t_eval, tol_ext, out[OUT_FIELDS];
+  Buf y0, params, t_eval, tol_ext, scratch, out[OUT_FIELDS];
 };
 
 // bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
@@ -374,6 +374,13 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
 
   if (pi.user) {
+    if (pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF)) {
+      // warp-cooperative implicit kernels keep one Jacobian per resident warp in global memory; the launch shape is
+      // chosen inside ivpb_nvrtc_launch, so size the pool for the most warps an SM can hold (64 warps x SMs)
+      const size_t matd = (size_t)(pi.n | 1) * pi.n;
+      CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)dev.sms * 64));
+      a.scratch = (double*)dev.scratch.p;
+    }
     int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, strict, &a, sizeof(a), N,
                                a.static_sched, stream);
     if (rc) return rc;
@@ -399,9 +406,16 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kblock, ksmem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)dev.sms * occ;
+  const bool impl_warp = kunits < 0;
+  if (impl_warp) kunits = -kunits;
   const int64_t units_per_block = kunits > 0 ? kunits : (warp_mode ? kblock / 32 : kblock);
   const int64_t need = (N + units_per_block - 1) / units_per_block;
   if (a.static_sched || need < grid) grid = need;
+  if (impl_warp) {       // per-warp Jacobian slots in global memory (L2-resident: grid x warps x n (n|1) doubles)
+    const size_t matd = (size_t)(pi.n | 1) * pi.n;
+    CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)grid * (size_t)(kblock / 32)));
+    a.scratch = (double*)dev.scratch.p;
+  }
   void* kargs[] = {&a};
   CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kblock), kargs, ksmem, stream));
   ctx->launches += 1;
@@ -457,7 +471,7 @@ void ivpb_destroy(ivpb_ctx* ctx) {
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
-    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release();
+    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.scratch.release();
     for (auto& b : d.out) b.release();
     cudaFree(d.queue);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
