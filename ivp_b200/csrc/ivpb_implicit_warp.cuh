@@ -65,8 +65,18 @@ struct WarpLinAlg {
       for (int j = k + 1 + l; j < N; j += 32) {           // lanes own columns
         const double tj = A(m, j);
         if (m != k) { A(m, j) = A(k, j); A(k, j) = tj; }
-        if (tj != 0.0)
-          for (int i = k + 1; i < N; ++i) A(i, j) = IVPB_MA(A(i, k), tj, A(i, j));
+        if (tj != 0.0) {
+          // four independent updates in flight (loads issued before the stores: the compiler cannot prove that the
+          // store to column j does not alias the next load from column k, and would otherwise serialise them)
+          int i = k + 1;
+          for (; i + 3 < N; i += 4) {
+            const double m0 = A(i, k), m1 = A(i + 1, k), m2 = A(i + 2, k), m3 = A(i + 3, k);
+            const double a0 = A(i, j), a1 = A(i + 1, j), a2 = A(i + 2, j), a3 = A(i + 3, j);
+            A(i, j) = IVPB_MA(m0, tj, a0); A(i + 1, j) = IVPB_MA(m1, tj, a1);
+            A(i + 2, j) = IVPB_MA(m2, tj, a2); A(i + 3, j) = IVPB_MA(m3, tj, a3);
+          }
+          for (; i < N; ++i) A(i, j) = IVPB_MA(A(i, k), tj, A(i, j));
+        }
       }
       __syncwarp();
     }
@@ -113,7 +123,15 @@ struct WarpLinAlg {
           } else if (mr == 0.0) {
             for (int i = k + 1; i < N; ++i) { const double pr = -I(i, k) * mi, pi = R(i, k) * mi; R(i, j) += pr; I(i, j) += pi; }
           } else {
-            for (int i = k + 1; i < N; ++i) {
+            int i = k + 1;
+            for (; i + 1 < N; i += 2) {      // two independent complex updates in flight
+              const double r0 = R(i, k), i0 = I(i, k), r1 = R(i + 1, k), i1 = I(i + 1, k);
+              const double x0 = R(i, j), y0 = I(i, j), x1 = R(i + 1, j), y1 = I(i + 1, j);
+              const double pr0 = r0 * mr - i0 * mi, pi0 = i0 * mr + r0 * mi;
+              const double pr1 = r1 * mr - i1 * mi, pi1 = i1 * mr + r1 * mi;
+              R(i, j) = x0 + pr0; I(i, j) = y0 + pi0; R(i + 1, j) = x1 + pr1; I(i + 1, j) = y1 + pi1;
+            }
+            for (; i < N; ++i) {
               const double pr = R(i, k) * mr - I(i, k) * mi, pi = I(i, k) * mr + R(i, k) * mi;
               R(i, j) += pr; I(i, j) += pi;
             }
