@@ -81,6 +81,7 @@ struct Device {
   u64* queue = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
   Buf y0, params, t_eval, tol_ext, scratch, out[OUT_FIELDS];
+  Buf q_traj, q_ts, q_y, q_ok;      // ivpb_dense_eval query staging (grow-only)
 };
 
 // bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
@@ -472,6 +473,7 @@ void ivpb_destroy(ivpb_ctx* ctx) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
     d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.scratch.release();
+    d.q_traj.release(); d.q_ts.release(); d.q_y.release(); d.q_ok.release();
     for (auto& b : d.out) b.release();
     cudaFree(d.queue);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
@@ -598,8 +600,8 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   field_bytes(n, nev, cap, me, seg_cap, n_cont, per);
   void* host[OUT_FIELDS];
   out_to_array(out, host);
-  ctx->dense.valid = false;
-  if (seg_cap > 0) {
+  if (seg_cap > 0) {       // a new dense log replaces the retained one; solves without dense_output leave it alone
+    ctx->dense.valid = false;
     ctx->dense.method = opt->method; ctx->dense.n = n; ctx->dense.n_cont = n_cont; ctx->dense.cap = (int)seg_cap;
     ctx->dense.N = N; ctx->dense.lo.assign(G, 0); ctx->dense.count.assign(G, 0);
   }
@@ -698,7 +700,7 @@ int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const d
     if (L.count[g] == 0) continue;
     Device& dev = ctx->devs[g];
     CK(cudaSetDevice(dev.id));
-    Buf q_traj, q_ts, q_y, q_ok;
+    Buf &q_traj = dev.q_traj, &q_ts = dev.q_ts, &q_y = dev.q_y, &q_ok = dev.q_ok;
     cudaError_t e = q_traj.ensure(8 * M);
     if (e == cudaSuccess) e = q_ts.ensure(8 * M);
     if (e == cudaSuccess) e = q_y.ensure(8 * M * L.n);
@@ -715,7 +717,6 @@ int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const d
     if (e == cudaSuccess) e = cudaMemcpyAsync(yg.data(), q_y.p, 8 * M * L.n, cudaMemcpyDeviceToHost, dev.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(okg.data(), q_ok.p, 4 * M, cudaMemcpyDeviceToHost, dev.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(dev.stream);
-    q_traj.release(); q_ts.release(); q_y.release(); q_ok.release();
     if (e != cudaSuccess) return fail(ctx, IVPB_ERR_CUDA, std::string("ivpb_dense_eval: ") + cudaGetErrorString(e));
     for (size_t q = 0; q < M; ++q) {
       if (traj[q] < L.lo[g] || traj[q] >= L.lo[g] + L.count[g]) continue;

@@ -614,6 +614,10 @@ def test_dense_output_fma_build_truncation_and_zero_interval(oracle):
     for i in (0, 123, 299):          # against the oracle's own dense output, within the north-star tolerance
         ys, oks, _ = oracle.dense_eval(PROBLEMS[prob], t0, 20.0, y0[i], par[i], opts, np.linspace(0.5, 19.5, 5))
         assert close(y[q == i], ys, 1e-8, 1e-8).all()
+    # the retained log survives later solves that do not ask for dense output
+    ib.solve_ivp_batch(prob, t0, 5.0, y0[:8], par[:8], Options(method=Method.DOPRI5))
+    y2, ok2 = g.sol_many(q, ts)
+    assert ok2.all() and np.array_equal(y2, y)
     # capacity exceeded: n_seg reports the true count, queries beyond the stored segments answer ok = 0
     small = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, dense_output=True, max_segments=8)
     h = ib.solve_ivp_batch(prob, t0, 20.0, y0[:4], par[:4], small, want=["status", "counters", "t_final", "y_final", "n_seg"])
