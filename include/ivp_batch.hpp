@@ -116,7 +116,9 @@ struct Options {
   int max_events = 8;        // event hits stored per event function and trajectory
   int max_out = 4096;        // step-mode samples stored per trajectory when t_eval is None (0: endpoints only)
   bool analytic_jac = false; // use the problem's ivp_jac instead of the default finite differences
-  bool strict_fp = false;    // IVPB_FLAG_STRICT_FP: the reference's rounding, operation for operation
+  bool strict_fp = false;    // IVPB_FLAG_STRICT_FP: the reference's rounding, operation for operation (explicit methods;
+                             // RADAU / BDF use it by default)
+  bool fast_fp = false;      // IVPB_FLAG_FAST_FP: FMA-contracted RADAU / BDF kernels
   static OptionsBuilder builder();
 };
 class OptionsBuilder {
@@ -137,6 +139,7 @@ class OptionsBuilder {
   OptionsBuilder& max_out(int n) { o_.max_out = n; return *this; }
   OptionsBuilder& analytic_jac(bool b) { o_.analytic_jac = b; return *this; }
   OptionsBuilder& strict_fp(bool b) { o_.strict_fp = b; return *this; }
+  OptionsBuilder& fast_fp(bool b) { o_.fast_fp = b; return *this; }
   Options build() { return std::move(o_); }
  private:
   Options o_;
@@ -305,7 +308,7 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
   o.max_events = ne > 0 ? options.max_events : 0;
   o.max_out = options.max_out;
   o.jac_mode = options.analytic_jac ? 1 : 0;
-  o.flags = options.strict_fp ? IVPB_FLAG_STRICT_FP : 0u;
+  o.flags = (options.strict_fp ? IVPB_FLAG_STRICT_FP : 0u) | (options.fast_fp ? IVPB_FLAG_FAST_FP : 0u);
 
   const size_t cap = o.has_t_eval ? (size_t)o.n_t_eval + 1 : (size_t)o.max_out;
   std::vector<int32_t> status(N), n_out(N), ev_count(N * (size_t)ne);

@@ -87,6 +87,11 @@ typedef struct {
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
                                   the reference's rounding, no FMA contraction) */
 #define IVPB_FLAG_NO_REFILL 2u /* static one-trajectory-per-thread schedule (debug / A-B measurements) */
+#define IVPB_FLAG_FAST_FP 8u   /* RADAU / BDF only: run the FMA-contracted kernels.  The implicit methods default to the
+                                  strict arithmetic (bit-identical to the reference's operation sequence) because stiff
+                                  ensembles lose step-count parity under any last-bit perturbation (VdP mu=1000: 73 % RADAU,
+                                  97 % BDF with FMA) while the FMA build is only 17-29 % faster there.  The explicit methods
+                                  default to the FMA build (2x faster; north-star parity 100 %) and take IVPB_FLAG_STRICT_FP. */
 #define IVPB_FLAG_NO_ZEROCOPY 4u /* ivpb_solve_batch: always stage through device buffers, even when the caller's
                                     buffers are page-locked (default: pinned y0 / params / per-trajectory results are
                                     read and written by the kernel directly over PCIe, overlapping the solve) */

@@ -344,7 +344,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
     a.rtol_ext = (const double*)dev.tol_ext.p; a.atol_ext = a.rtol_ext + pi.n;
   }
-  const int strict = (o->flags & IVPB_FLAG_STRICT_FP) ? 1 : 0;
+  const bool implicit_method = o->method == IVPB_RADAU || o->method == IVPB_BDF;
+  const int strict = ((o->flags & IVPB_FLAG_STRICT_FP) || (implicit_method && !(o->flags & IVPB_FLAG_FAST_FP))) ? 1 : 0;
   const int block = 128;
   const bool warp_mode = pi.n > ivpb::MAX_N;      // one trajectory per warp (WarpLayout, ivpb_erk.cuh)
 

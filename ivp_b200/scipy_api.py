@@ -88,7 +88,7 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
         problem = api.Problem.builtin(fun)
     t0, tf = float(t_span[0]), float(t_span[1])
     known = {"rtol", "atol", "max_step", "min_step", "first_step", "max_steps"}          # solve.rs:290-340
-    unknown = set(options) - known - {"max_events", "max_out", "max_segments", "strict_fp"}
+    unknown = set(options) - known - {"max_events", "max_out", "max_segments", "strict_fp", "fast_fp"}
     if unknown:
         raise TypeError(f"unknown options: {sorted(unknown)}")
     cfgs, has_events = _event_configs(events, problem.n_events)
@@ -99,7 +99,8 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
                    dense_output=bool(dense_output), event_config=cfgs, max_events=int(options.get("max_events", 64)),
                    max_out=int(options.get("max_out", 4096)), max_segments=int(options.get("max_segments", 4096)) if dense_output else 0,
                    jac_mode=1 if jac in (True, "analytic") or (isinstance(jac, str) and "ivp_jac" in jac) else 0,
-                   flags=api.IVPB_FLAG_STRICT_FP if options.get("strict_fp") else 0)
+                   flags=(api.IVPB_FLAG_STRICT_FP if options.get("strict_fp") else 0) |
+                         (api.IVPB_FLAG_FAST_FP if options.get("fast_fp") else 0))
     params = None
     if problem.p > 0:
         if args is None:

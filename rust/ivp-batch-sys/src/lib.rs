@@ -64,6 +64,8 @@ pub const IVPB_ERR_CUDA: c_int = 2;
 pub const IVPB_ERR_NVRTC: c_int = 3;
 pub const IVPB_FLAG_STRICT_FP: i32 = 1;
 pub const IVPB_FLAG_NO_REFILL: i32 = 2;
+pub const IVPB_FLAG_NO_ZEROCOPY: i32 = 4;
+pub const IVPB_FLAG_FAST_FP: i32 = 8;
 
 extern "C" {
     pub fn ivpb_create(out: *mut *mut ivpb_ctx, device_ids: *const c_int, n_devices: c_int) -> c_int;

@@ -9,7 +9,7 @@ import pytest
 
 import ivp_b200 as ib
 from ivp_b200 import Direction, EventConfig, Method, Options, Status, synth
-from ivp_b200.api import IVPB_FLAG_NO_REFILL, IVPB_FLAG_STRICT_FP, PROBLEMS
+from ivp_b200.api import IVPB_FLAG_FAST_FP, IVPB_FLAG_NO_REFILL, IVPB_FLAG_STRICT_FP, PROBLEMS
 
 pytestmark = pytest.mark.gpu
 
@@ -422,12 +422,16 @@ def test_stiff_ensembles_strict_bit_exact(oracle, method, wl, rtol, atol, jac_mo
 @pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
 @pytest.mark.parametrize("wl,rtol,atol", [("robertson", 1e-6, 1e-6), ("vdp_stiff", 1e-4, 1e-6)])
 def test_stiff_ensembles_fma_build(oracle, method, wl, rtol, atol):
-    """Default (FMA) build: values inside the north-star tolerance; step counts of the stiff relaxation
+    """IVPB_FLAG_FAST_FP (FMA) build of the implicit kernels: values inside the north-star tolerance; step counts of the stiff relaxation
     oscillator are exempt (a single last-bit difference flips a Newton-convergence test a few hundred steps
     later -- 1-ulp noise on the oracle's own pow reproduces the same rates, tools/diag_implicit.py), Robertson
     keeps them exactly."""
-    opts = Options(method=method, rtol=rtol, atol=atol)
+    opts = Options(method=method, rtol=rtol, atol=atol, flags=IVPB_FLAG_FAST_FP)
     g, o = run_both(oracle, wl, 2048, opts)
+    # the DEFAULT for RADAU / BDF is the strict arithmetic: bit-exact without any flag
+    prob, y0d, pard, t0d, tfd = synth.ensemble(wl, 2048)
+    d = ib.solve_ivp_batch(prob, t0d, tfd, y0d, pard, Options(method=method, rtol=rtol, atol=atol))
+    assert np.array_equal(d.counters, o.counters) and np.array_equal(d.y_final, o.y_final)
     ok = close(g.y_final, o.y_final, rtol, atol).all(axis=1)
     if wl == "robertson":
         assert np.array_equal(g.status, o.status)
@@ -452,7 +456,7 @@ def test_vdp_eps_example_t_eval(oracle, method):
     o = oracle.solve_batch(PROBLEMS["vdp_eps"], 0.0, 2.0, y0, par, opts)
     exact(g, o, ("status", "counters", "n_out", "t_out", "y_out", "y_final"))
     assert np.all(g.n_out == 21)
-    f = ib.solve_ivp_batch("vdp_eps", 0.0, 2.0, y0, par, Options(method=method, rtol=1e-6, atol=1e-8, t_eval=te))
+    f = ib.solve_ivp_batch("vdp_eps", 0.0, 2.0, y0, par, Options(method=method, rtol=1e-6, atol=1e-8, t_eval=te, flags=IVPB_FLAG_FAST_FP))
     assert np.array_equal(f.n_out, o.n_out) and np.array_equal(f.t_out, o.t_out)
     assert close(f.y_out, o.y_out, 1e-5, 1e-7).mean() > 0.999
 
@@ -775,7 +779,7 @@ def test_warp_cooperative_implicit_medakzo(oracle, method):
             exact(g, o, ("n_out", "t_out", "y_out"))
     assert np.all(g.status == Status.Success) and np.all(g.njev > 0) and np.all(g.nlu > 0)
     # default (FMA + shuffle-reduction) build: inside tolerance
-    f = ib.solve_ivp_batch("medakzo64", 0.0, 7.0, ym, None, Options(method=method, rtol=1e-5, atol=1e-7))
+    f = ib.solve_ivp_batch("medakzo64", 0.0, 7.0, ym, None, Options(method=method, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_FAST_FP))
     assert np.array_equal(f.status, o.status)
     assert close(f.y_final, o.y_final, 1e-4, 1e-6).all()
     with pytest.raises(ib.ConfigError):

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ivp_b200 as ib
 from ivp_b200 import Method, Options, synth
-from ivp_b200.api import PROBLEMS, IVPB_FLAG_STRICT_FP
+from ivp_b200.api import PROBLEMS, IVPB_FLAG_STRICT_FP, IVPB_FLAG_FAST_FP
 from oracle import pyoracle
 
 CASES = [  # workload, method, rtol, atol, N, extra
@@ -32,7 +32,7 @@ for wl, m, rtol, atol, N, extra in CASES:
     kw = dict(extra)
     if "t_eval" in kw:
         kw["t_eval"] = np.linspace(t0, tf, kw["t_eval"])
-    for flags, name in ((0, "fma"), (IVPB_FLAG_STRICT_FP, "strict")):
+    for flags, name in ((IVPB_FLAG_FAST_FP, "fma"), (IVPB_FLAG_STRICT_FP, "strict")):
         opts = Options(method=m, rtol=rtol, atol=atol, flags=flags, max_events=2, **kw)
         g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts)
         o = pyoracle.solve_batch(PROBLEMS[prob], t0, tf, y0, par, opts, nthreads=os.cpu_count())
