@@ -512,6 +512,7 @@ struct ErkTraj {
   static constexpr int N = L::NL, NG = Prob::N, P = Prob::P;     // N: local slice (== NG for ThreadLayout)
   static constexpr int PS = P > 0 ? P : 1;
   static constexpr bool DENSE = FEAT != 0;
+  static constexpr bool BATCH_HEAVY = false;     // see run_schedule
   static constexpr int NC = MethodTraits<METHOD>::NC;
   using Out = SolOutDev<Prob, METHOD, FEAT, L>;
 
@@ -1126,7 +1127,17 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
     // the refill logic is live in here.
     bool done = false;
     do {
-      if (active) done = T.step(a);
+      bool run = active;
+      if constexpr (Traj::BATCH_HEAVY) {
+        // Trajectories whose next trip starts with rarely needed, expensive work (BDF: order selection, change_d,
+        // Jacobian, refactorisation) wait until most of the warp's lanes are in the same situation, so that code
+        // runs once for many lanes instead of on every trip for a few.  Each lane gets there within order + 2 trips,
+        // so nobody waits long; results are unaffected (only the interleaving of independent lanes changes).
+        const bool hv = active && T.heavy();
+        const int na = __popc(__ballot_sync(FULL, active)), nh = __popc(__ballot_sync(FULL, hv));
+        run = active && (!hv || nh * 4 >= na * 3);
+      }
+      if (run) done = T.step(a);
     } while (!__any_sync(FULL, done));
     if (done) { T.finish(a); active = false; }
   }

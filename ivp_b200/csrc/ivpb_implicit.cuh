@@ -309,6 +309,7 @@ struct RadauTraj {
   static constexpr int PS = P > 0 ? P : 1;
   static constexpr int SMEM_MATS = REG ? 0 : 4;
   static constexpr int SMEM_DOUBLES_PER_THREAD = SMEM_MATS * N * N;
+  static constexpr bool BATCH_HEAVY = false;
   using Out = SolOutDev<Prob, M_RADAU, FEAT>;
   using Mat = typename std_conditional<REG, RegMat<N>, SmemMat<N, BLK>>::type;
 
@@ -665,6 +666,10 @@ struct BdfTraj {
   static constexpr int SMEM_VEC_ROWS = ND + NS + 1;                     // D, scratch, Jacobian point
   static constexpr int SMEM_MATS = REG ? 0 : 2;
   static constexpr int SMEM_DOUBLES_PER_THREAD = SMEM_VEC_ROWS * N + SMEM_MATS * N * N;
+#ifndef IVPB_BDF_BATCH
+#define IVPB_BDF_BATCH 1
+#endif
+  static constexpr bool BATCH_HEAVY = IVPB_BDF_BATCH != 0;
   using Out = SolOutDev<Prob, M_BDF, FEAT>;
   using Mat = typename std_conditional<REG, RegMat<N>, SmemMat<N, BLK>>::type;
 
@@ -675,10 +680,14 @@ struct BdfTraj {
   Mat jac, lu;
   int pivot[N];
   double current_c, pend, jx;   // pend: change_d factor owed to D by the previous pass (1.0 = none)
+  double os_err, os_safety;     // order selection owed by the previous (accepted) pass
   u32 nfev, njev, nlu, nstep, naccpt, nrejct;
   int order, n_equal_steps, status;
-  bool lu_is_current, jac_pending;
+  bool lu_is_current, jac_pending, os_pending;
   Out so;
+
+  // true when the next trip starts with the expensive, rarely needed blocks (see run_schedule)
+  __device__ __forceinline__ bool heavy() const { return os_pending || jac_pending || pend != 1.0 || !lu_is_current; }
 
   __device__ __forceinline__ double& D(int k, int i) { return sm[(k * N + i) * BLK]; }
   __device__ __forceinline__ double& S(int k, int i) { return sm[((ND + k) * N + i) * BLK]; }
@@ -759,6 +768,7 @@ struct BdfTraj {
     }
     nfev = 0; njev = 0; nlu = 0; nstep = 0; naccpt = 0; nrejct = 0;
     status = ST_SUCCESS; order = 1; n_equal_steps = 0; lu_is_current = false; current_c = 0.0; pend = 1.0;
+    os_pending = false; os_err = 0.0; os_safety = 0.0;
     so.reset();
     const double direction = signum(a.tf - a.t0);
     const double hmax = fabs(a.has_max_step ? a.max_step : fabs(a.tf - a.t0));
@@ -838,6 +848,55 @@ struct BdfTraj {
     // after a failed Newton iteration (x_new, y_predict; bdf.rs:450) and after an order change (x, y;
     // bdf.rs:604-607) -- always as the last use of the old Jacobian before the next factorisation, so
     // evaluating it here, at the top of the following trip, from the saved point is equivalent.
+    if (os_pending) {
+      os_pending = false;
+      const double error_norm = os_err, safety = os_safety;
+      double scale[N], rhs[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {        // scale of the accepted state (y == y_new of that pass)
+        scale[i] = a.atol[i] + a.rtol[i] * fabs(y[i]);
+        if (scale[i] == 0.0) scale[i] = EPS;
+      }
+      const double INF = __longlong_as_double(0x7ff0000000000000LL);
+      double err_m = INF, err_p = INF;
+      if (order > 1) {
+        const double ec = BDF_ERRC[order - 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order, i);
+        err_m = wrms(rhs, scale);
+      }
+      if (order < MAX_ORDER) {
+        const double ec = BDF_ERRC[order + 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order + 2, i);
+        err_p = wrms(rhs, scale);
+      }
+      // factors[idx] = errors[idx]^(-1 / (order + idx)); Iterator::max_by keeps the LAST maximal element
+      // (bdf.rs:577-583)
+      double fbest = 0.0, max_factor = 0.0;
+      int best = 0;
+      for (int k = 0; k < 3; ++k) {
+        const double e = k == 0 ? err_m : (k == 1 ? error_norm : err_p);
+        const double f = ivpb_pow_call(e, -1.0 / ((double)order + (double)k));
+        if (k == 0 || !(f < fbest)) { best = k; fbest = f; }
+        max_factor = fmax(max_factor, f);
+      }
+      int new_order = order;
+      if (best == 0 && order > 1) new_order -= 1;
+      else if (best == 2 && order < MAX_ORDER) new_order += 1;
+      const double step_factor = fmin(safety * max_factor, MAX_FACTOR);
+      const int old_order = order;
+      order = new_order;
+      pend = step_factor;                                    // change_d(d, new_order, step_factor) next trip
+      current_h *= step_factor;
+      n_equal_steps = 0;
+      lu_is_current = false;
+      if (new_order != old_order) {                          // f.jac(x, y), bdf.rs:604-607
+        jx = x; jac_pending = true; njev += 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) JY(i) = y[i];
+      }
+    }
     if (jac_pending) {
       double jy[N];
 #pragma unroll
@@ -985,47 +1044,8 @@ struct BdfTraj {
       }
     }
     if (direction * (x - xend) >= 0.0) { status = ST_SUCCESS; return true; }
-    if (n_equal_steps >= order + 1) {
-      const double INF = __longlong_as_double(0x7ff0000000000000LL);
-      double err_m = INF, err_p = INF;
-      if (order > 1) {
-        const double ec = BDF_ERRC[order - 1];
-#pragma unroll
-        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order, i);
-        err_m = wrms(rhs, scale);
-      }
-      if (order < MAX_ORDER) {
-        const double ec = BDF_ERRC[order + 1];
-#pragma unroll
-        for (int i = 0; i < N; ++i) rhs[i] = ec * D(order + 2, i);
-        err_p = wrms(rhs, scale);
-      }
-      // factors[idx] = errors[idx]^(-1 / (order + idx)); Iterator::max_by keeps the LAST maximal element
-      // (bdf.rs:577-583)
-      double fbest = 0.0, max_factor = 0.0;
-      int best = 0;
-      for (int k = 0; k < 3; ++k) {
-        const double e = k == 0 ? err_m : (k == 1 ? error_norm : err_p);
-        const double f = ivpb_pow_call(e, -1.0 / ((double)order + (double)k));
-        if (k == 0 || !(f < fbest)) { best = k; fbest = f; }
-        max_factor = fmax(max_factor, f);
-      }
-      int new_order = order;
-      if (best == 0 && order > 1) new_order -= 1;
-      else if (best == 2 && order < MAX_ORDER) new_order += 1;
-      const double step_factor = fmin(safety * max_factor, MAX_FACTOR);
-      const int old_order = order;
-      order = new_order;
-      pend = step_factor;                                    // change_d(d, new_order, step_factor) next trip
-      current_h *= step_factor;
-      n_equal_steps = 0;
-      lu_is_current = false;
-      if (new_order != old_order) {                          // f.jac(x, y), bdf.rs:604-607
-        jx = x; jac_pending = true; njev += 1;
-#pragma unroll
-        for (int i = 0; i < N; ++i) JY(i) = y[i];
-      }
-    }
+    // order / step-size selection (bdf.rs:552-606) is owed to the next trip: it is the first thing step() does
+    if (n_equal_steps >= order + 1) { os_pending = true; os_err = error_norm; os_safety = safety; }
     return false;
   }
 };
