@@ -1089,6 +1089,10 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #define IVPB_BLOCK 128
 #endif
 
+#ifndef IVPB_BATCH_NUM
+#define IVPB_BATCH_NUM 1      // heavy lanes wait until NUM/DEN of the active lanes are heavy; measured on the BDF
+#define IVPB_BATCH_DEN 1      // ensembles: 1/2 -> 89 ms, 3/4 -> 80 ms, 1/1 -> 62 ms (Robertson, 2^18 trajectories)
+#endif
 // Generic persistent scheduler: Traj provides init(a, idx) -> done, step(a) -> done, finish(a).
 template <class Traj>
 __device__ __forceinline__ void run_schedule(const KArgs& a) {
@@ -1130,12 +1134,12 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
       bool run = active;
       if constexpr (Traj::BATCH_HEAVY) {
         // Trajectories whose next trip starts with rarely needed, expensive work (BDF: order selection, change_d,
-        // Jacobian, refactorisation) wait until most of the warp's lanes are in the same situation, so that code
+        // Jacobian, refactorisation) wait until all of the warp's active lanes are in the same situation, so that code
         // runs once for many lanes instead of on every trip for a few.  Each lane gets there within order + 2 trips,
         // so nobody waits long; results are unaffected (only the interleaving of independent lanes changes).
         const bool hv = active && T.heavy();
         const int na = __popc(__ballot_sync(FULL, active)), nh = __popc(__ballot_sync(FULL, hv));
-        run = active && (!hv || nh * 4 >= na * 3);
+        run = active && (!hv || nh * IVPB_BATCH_DEN >= na * IVPB_BATCH_NUM);
       }
       if (run) done = T.step(a);
     } while (!__any_sync(FULL, done));
