@@ -569,7 +569,7 @@ struct ErkTraj {
 #ifdef IVPB_STRICT
     facold = 1e-4;
 #else
-    facold = (METHOD == M_DOPRI5) ? -9.210340371976182 : 1e-4;    // fast DOPRI5 carries log(facold)
+    facold = (METHOD == M_DOPRI5) ? -13.287712379549449 : 1e-4;   // fast DOPRI5 carries log2(facold), facold = 1e-4
 #endif
     hlamb = 0.0;
     nfev = 0; nstep = 0; naccpt = 0; nrejct = 0;
@@ -897,11 +897,11 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     double hnew = h / fac;
     const bool accept = err <= 1.0;
 #else
-    // Same PI controller in log space: err = sqrt(e2), so log(err) = log(e2)/2 needs no square root, and
-    // log(facold) is carried from the previous accepted step (facold holds log(max(err, 1e-4)) in this build).
+    // Same PI controller in log2 space: err = sqrt(e2), so log2(err) = log2(e2)/2 needs no square root, and
+    // log2(facold) is carried from the previous accepted step (facold holds log2(max(err, 1e-4)) in this build).
     const double e2 = err * (1.0 / (double)NG);
-    const double lerr = 0.5 * log(e2);
-    double hnew = h * fm::minsel(fm::maxsel(safe * exp(fma(beta, facold, -(expo1 * lerr))), 0.2), 10.0);
+    const double lerr = 0.5 * fm::log2_fast(e2);
+    double hnew = h * fm::minsel(fm::maxsel(safe * fm::exp2_fast(fma(beta, facold, -(expo1 * lerr))), 0.2), 10.0);
     const bool accept = e2 <= 1.0;
     (void)facc1; (void)facc2;
 #endif
@@ -910,7 +910,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #ifdef IVPB_STRICT
       facold = fmax(err, 1.0e-4);
 #else
-      facold = fmax(lerr, -9.210340371976182);              // log(1e-4)
+      facold = fmax(lerr, -13.287712379549449);             // log2(1e-4)
 #endif
       naccpt += 1;
       if ((naccpt % 1000u == 0u) || (iasti > 0)) {              // dopri5.rs:364-391 (uses overwritten k4: quirk kept)
@@ -961,7 +961,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #ifdef IVPB_STRICT
       hnew = h / fmin(facc1, fac11 / safe);
 #else
-      hnew = h * fm::maxsel(safe * exp(-expo1 * lerr), 0.2);
+      hnew = h * fm::maxsel(safe * fm::exp2_fast(-expo1 * lerr), 0.2);
 #endif
       reject = true;
       if (naccpt > 1u) nrejct += 1;

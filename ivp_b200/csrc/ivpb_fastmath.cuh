@@ -68,5 +68,67 @@ __device__ __forceinline__ double rroot8(double x) {
   return (xr < 1e30f) ? v : 0.0;
 }
 
+// 1/x for arguments known to be comfortably normal (no range check)
+__device__ __forceinline__ double rcp_nc(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+
+static __device__ __noinline__ double log2_slow(double x) { return ::log2(x); }
+static __device__ __noinline__ double exp2_slow(double x) { return ::exp2(x); }
+
+// log2(x), x > 0 normal: x = 2^e m with m in [sqrt(1/2), sqrt(2)), log2(m) = (2 / ln 2) atanh(s), s = (m - 1) / (m + 1),
+// |s| <= 0.1716: twelve terms of the odd series (truncation 5e-20), branch-free; anything else -> library routine.
+// Used by the DOPRI5 / PI controller of the default build, where CUDA's log + exp cost more than the six stages.
+__device__ __forceinline__ double log2_fast(double x) {
+  if (!in_range(x) || x <= 0.0) return log2_slow(x);
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, lo);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double s = (m - 1.0) * rcp_nc(m + 1.0), s2 = s * s;
+  double p = 0.12545174268599682;
+  p = fma(p, s2, 0.1373995277037108);
+  p = fma(p, s2, 0.15186263588304877);
+  p = fma(p, s2, 0.16972882833987804);
+  p = fma(p, s2, 0.19235933878519512);
+  p = fma(p, s2, 0.22195308321368667);
+  p = fma(p, s2, 0.2623081892525388);
+  p = fma(p, s2, 0.3205988979753252);
+  p = fma(p, s2, 0.4121985831111324);
+  p = fma(p, s2, 0.5770780163555853);
+  p = fma(p, s2, 0.9617966939259756);
+  p = fma(p, s2, 2.8853900817779268);
+  return fma(p, s, (double)e);
+}
+
+// 2^t for |t| < 1000: t = k + f, |f| <= 1/2, 2^f by fourteen terms of the exponential series (truncation 4e-18),
+// scaled by constructing 2^k; anything else (inf, NaN, huge) -> library routine.
+__device__ __forceinline__ double exp2_fast(double t) {
+  if (!(fabs(t) < 1000.0)) return exp2_slow(t);
+  const double kd0 = t + 6755399441055744.0;          // 1.5 * 2^52: the low word now holds rint(t)
+  const int k = __double2loint(kd0);
+  const double f = t - (kd0 - 6755399441055744.0);
+  double p = 1.3691488853904128e-12;
+  p = fma(p, f, 2.5678435993488206e-11);
+  p = fma(p, f, 4.4455382718708116e-10);
+  p = fma(p, f, 7.054911620801123e-09);
+  p = fma(p, f, 1.01780860092397e-07);
+  p = fma(p, f, 1.321548679014431e-06);
+  p = fma(p, f, 1.5252733804059841e-05);
+  p = fma(p, f, 0.0001540353039338161);
+  p = fma(p, f, 0.0013333558146428443);
+  p = fma(p, f, 0.009618129107628477);
+  p = fma(p, f, 0.05550410866482158);
+  p = fma(p, f, 0.24022650695910072);
+  p = fma(p, f, 0.6931471805599453);
+  p = fma(p, f, 1.0);
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
 }  // namespace fm
 }  // namespace ivpb

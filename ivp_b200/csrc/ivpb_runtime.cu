@@ -821,6 +821,25 @@ extern "C" int ivpb_debug_pow(const double* x, const double* y, int n, double* r
   return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
 }
 
+namespace {
+__global__ void fastmath2_kernel(const double* x, int n, double* r_log2, double* r_exp2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  r_log2[i] = ivpb::fm::log2_fast(x[i]);
+  r_exp2[i] = ivpb::fm::exp2_fast(x[i]);
+}
+}  // namespace
+extern "C" int ivpb_debug_fastmath2(const double* x, int n, double* r_log2, double* r_exp2) {
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * 3 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;
+  cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  fastmath2_kernel<<<(n + 127) / 128, 128>>>(d, n, d + n, d + 2 * (size_t)n);
+  cudaMemcpy(r_log2, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(r_exp2, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
+}
+
 extern "C" int ivpb_debug_fastmath(const double* x, int n, double* r_rcp, double* r_rsqrt, double* r_rroot8) {
   double* d = nullptr;
   if (cudaMalloc((void**)&d, sizeof(double) * 4 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;

@@ -297,6 +297,19 @@ def test_fastmath_helpers_accuracy():
         assert np.max(np.abs(r3[mid] * x[mid] ** 0.125 - 1.0)) < 1e-14
     # controller limits: tiny / zero error => factor beyond the upper clamp; huge / inf / nan => 0
     assert np.all(r3[(x < 1e-30)] > 6.0 / 0.9) and np.all(r3[~(x < 1e30)] == 0.0)
+    # log2 / exp2 of the DOPRI5 controller: a few ulp; exact limits through the library fallbacks
+    xs = np.concatenate([10.0 ** rng.uniform(-30, 30, 20000), rng.uniform(0.5, 2.0, 20000), rng.uniform(-40, 40, 20000),
+                         [0.0, np.inf, 1.0, 2.0, 0.5, -1.0, 1e-310, 1023.5, -1080.0, np.nan]])
+    l2, e2 = np.zeros_like(xs), np.zeros_like(xs)
+    assert lib.ivpb_debug_fastmath2(_abi.ptr(xs), C.c_int(xs.size), _abi.ptr(l2), _abi.ptr(e2)) == 0
+    with np.errstate(all="ignore"):
+        pos = np.isfinite(xs) & (xs > 1e-300)
+        ref = np.log2(xs[pos])
+        assert np.max(np.abs(l2[pos] - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-15
+        small = np.abs(xs) < 700
+        assert np.max(np.abs(e2[small] / np.exp2(xs[small]) - 1.0)) < 1e-15
+    assert l2[-10] == -np.inf and l2[-9] == np.inf and l2[-8] == 0.0 and l2[-7] == 1.0 and l2[-6] == -1.0 and np.isnan(l2[-5])
+    assert e2[-8] == 2.0 and e2[-7] == 4.0 and e2[-2] == 0.0 and np.isnan(e2[-1])
 
 
 def test_multi_device_context_matches_single_device():
