@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vdp_dop853", choices=sorted(WORKLOADS))
     ap.add_argument("--trajectories", type=int, default=1 << 20, help="trajectories per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --trajectories per GPU (default, the bench contract); strong: --trajectories in total, split over the ranks")
     ap.add_argument("--cpu-sample", type=int, default=32768, help="trajectories per step of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--static", action="store_true", help="disable work-queue refill (A/B)")
@@ -217,8 +219,9 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     ens, method, rtol, atol, F, n = WORKLOADS[args.workload]
-    Nper = args.trajectories
-    prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=weak_offset(Nper, rank))
+    Nper = args.trajectories if args.scaling == "weak" else (args.trajectories * (rank + 1)) // world - (args.trajectories * rank) // world
+    offset = weak_offset(Nper, rank) if args.scaling == "weak" else (args.trajectories * rank) // world
+    prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=offset)
     problem = api.Problem.builtin(prob_name)
     flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0) | \
         (api.IVPB_FLAG_NO_ZEROCOPY if args.no_zerocopy else 0) | (api.IVPB_FLAG_FAST_FP if args.fast_implicit else 0)
@@ -374,9 +377,9 @@ def main():
         print(json.dumps({
             "metric": "accepted_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "problem": prob_name, "method": method, "rtol": rtol, "atol": atol,
-                       "t_span": [t0, tf], "trajectories_per_gpu": Nper, "trajectories_total": Nper * world,
+                       "t_span": [t0, tf], "trajectories_per_gpu": Nper, "trajectories_total": Nper * world if args.scaling == "weak" else args.trajectories,
                        "outputs": "final state + status + counters" + (f" + {n_te} t_eval samples" if n_te else "") +
                                   (" + event times" if ne else ""), "parallelism": f"trajectory-sharded x{world}",
                        "l2": "flushed between timed iterations (256 MiB write)",
