@@ -191,6 +191,16 @@ struct Solution {
     return out;
   }
   std::vector<Float> sol(Float t) const { return sol_many({t}).at(0); }
+  // ContinuousOutput::evaluate_extrapolate (cont.rs:91-150): outside the stored steps the first / last one answers
+  std::optional<std::vector<Float>> sol_extrapolate(Float t) const {
+    if (!continuous_sol) return std::nullopt;
+    const int n = continuous_sol->n;
+    std::vector<Float> y((size_t)n);
+    int32_t ok = 0;
+    const int64_t tr = continuous_sol->index;
+    if (ivpb_dense_eval_extrapolate(continuous_sol->ctx.get(), 1, &tr, &t, y.data(), &ok) != IVPB_OK || !ok) return std::nullopt;
+    return y;
+  }
   // batched-solve additions
   Float h_next = 0.0;          // IntegrationResult.h (src/methods/mod.rs:31-32)
   bool truncated = false;      // more samples / event hits than max_out / max_events allowed

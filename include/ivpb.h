@@ -166,6 +166,13 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
  * interpolated state, ok[q] = 1 if a stored segment covers ts[q] within 1e-12 (first match in step order, like
  * the reference's linear search), else 0 and y[q] is untouched.  All pointers are HOST pointers. */
 int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok);
+/* ContinuousOutput::evaluate_extrapolate (src/solve/cont.rs:91-150; what the reference's Python OdeSolution.__call__
+ * uses, src/python/solution.rs:41,116): as ivpb_dense_eval, but a time outside every stored step is answered by the
+ * FIRST segment when it lies below that segment's lower edge and by the LAST segment when it lies above that one's
+ * upper edge (the reference's rule, independent of the direction of integration).  ok[q] = 0 only for a trajectory
+ * without segments. */
+int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y,
+                                int32_t* ok);
 /* Solution::sol_span for trajectories [first, first + count): t_start = first.xold, t_end = last.xold + last.h
  * (src/solve/cont.rs:67-76); n_seg = segments stored (0 => no span). */
 int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg);

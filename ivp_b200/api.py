@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "ivpb_create", "ivpb_destroy", "ivpb_last_error", "ivpb_device_count", "ivpb_builtin_problem",
     "ivpb_nvrtc_problem", "ivpb_solve_batch", "ivpb_solve_batch_device", "ivpb_host_alloc", "ivpb_host_free",
     "ivpb_launch_count", "ivpb_measure_fp64_peak", "ivpb_version", "ivpb_dense_eval", "ivpb_dense_span",
+    "ivpb_dense_eval_extrapolate",
 ]
 
 
@@ -79,6 +80,8 @@ def load_library():
     L.ivpb_version.restype = C.c_char_p
     L.ivpb_dense_eval.restype = C.c_int
     L.ivpb_dense_eval.argtypes = [vp, C.c_int64, _abi.c_int64_p, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
+    L.ivpb_dense_eval_extrapolate.restype = C.c_int
+    L.ivpb_dense_eval_extrapolate.argtypes = L.ivpb_dense_eval.argtypes
     L.ivpb_dense_span.restype = C.c_int
     L.ivpb_dense_span.argtypes = [vp, C.c_int64, C.c_int64, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
     _lib = L
@@ -176,15 +179,17 @@ class Context:
         return v.value
 
     # -- dense output (Solution::sol on the device) ------------------------------------------------
-    def dense_eval(self, traj: np.ndarray, ts: np.ndarray, n: int):
-        """ivpb_dense_eval on the log retained by the last dense_output solve: (y[Q, n], ok[Q])."""
+    def dense_eval(self, traj: np.ndarray, ts: np.ndarray, n: int, extrapolate: bool = False):
+        """ivpb_dense_eval (or ivpb_dense_eval_extrapolate: ContinuousOutput::evaluate_extrapolate, cont.rs:91-150) on
+        the log retained by the last dense_output solve: (y[Q, n], ok[Q])."""
         traj = np.ascontiguousarray(np.asarray(traj, dtype=np.int64).reshape(-1))
         ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
         if traj.size != ts.size:
             raise ValueError("traj and ts must have the same length")
         y = np.zeros((ts.size, n))
         ok = np.zeros(ts.size, dtype=np.int32)
-        self.check(self.lib.ivpb_dense_eval(self.ptr, ts.size, _abi.ptr(traj), _abi.ptr(ts), _abi.ptr(y), _abi.ptr(ok)))
+        fn = self.lib.ivpb_dense_eval_extrapolate if extrapolate else self.lib.ivpb_dense_eval
+        self.check(fn(self.ptr, ts.size, _abi.ptr(traj), _abi.ptr(ts), _abi.ptr(y), _abi.ptr(ok)))
         return y, ok.astype(bool)
 
     def dense_span(self, first: int, count: int):

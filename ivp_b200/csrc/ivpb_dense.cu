@@ -77,7 +77,7 @@ __device__ void interp_rt(int method, int n, double xi, double* yi, const double
 // One thread per query.  [lo, lo + Ng) is the slice of the batch whose segments live on this device.
 __global__ void dense_eval_kernel(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
                                   const double* seg_cont, i64 M, const i64* traj, i64 lo, i64 Ng, const double* ts,
-                                  double* y, int* ok) {
+                                  double* y, int* ok, int extrapolate) {
   const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= M) return;
   const i64 tr = traj[q] - lo;
@@ -98,10 +98,22 @@ __global__ void dense_eval_kernel(int method, int n, int n_cont, int cap, const 
     const bool reached = fwd ? (t <= right + tol) : (t >= left - tol);
     if (reached) b = mid; else a = mid + 1;
   }
-  if (a >= m) return;
+  bool inside = false;
+  if (a < m) {
+    const double xa = sx[2 * a], ha = sx[2 * a + 1];
+    inside = t >= fmin(xa, xa + ha) - tol && t <= fmax(xa, xa + ha) + tol;
+  }
+  if (!inside) {
+    // ContinuousOutput::evaluate_extrapolate (cont.rs:91-150): outside every step, the FIRST segment answers
+    // t below its lower edge and the LAST one t above its upper edge -- whatever the direction of integration
+    if (!extrapolate) return;
+    const double first_left = fmin(sx[0], sx[0] + sx[1]);
+    const double last_right = fmax(sx[2 * (m - 1)], sx[2 * (m - 1)] + sx[2 * (m - 1) + 1]);
+    if (t < first_left) a = 0;
+    else if (t > last_right) a = m - 1;
+    else return;
+  }
   const double xo = sx[2 * a], hh = sx[2 * a + 1];
-  const double left = fmin(xo, xo + hh), right = fmax(xo, xo + hh);
-  if (!(t >= left - tol && t <= right + tol)) return;
   interp_rt(method, n, t, y + q * (i64)n, seg_cont + (tr * (i64)cap + a) * (i64)n_cont, xo, hh);
   ok[q] = 1;
 }
@@ -125,10 +137,10 @@ __global__ void dense_span_kernel(int cap, const int* seg_n, const double* seg_x
 extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n,
                                               const double* seg_x, const double* seg_cont, long long M,
                                               const long long* traj, long long lo, long long Ng, const double* ts,
-                                              double* y, int* ok, cudaStream_t stream) {
+                                              double* y, int* ok, int extrapolate, cudaStream_t stream) {
   if (M <= 0) return cudaSuccess;
   dense_eval_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(method, n, n_cont, cap, seg_n, seg_x, seg_cont, M, traj,
-                                                                     lo, Ng, ts, y, ok);
+                                                                     lo, Ng, ts, y, ok, extrapolate);
   return cudaGetLastError();
 }
 

@@ -42,7 +42,8 @@ static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
 // dense-output evaluation kernels (ivpb_dense.cu)
 extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
                                               const double* seg_cont, long long M, const long long* traj, long long lo,
-                                              long long Ng, const double* ts, double* y, int* ok, cudaStream_t stream);
+                                              long long Ng, const double* ts, double* y, int* ok, int extrapolate,
+                                              cudaStream_t stream);
 extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const double* seg_x, long long first, long long count,
                                               double* t_start, double* t_end, int* n_out, cudaStream_t stream);
 // RADAU / BDF kernels (ivpb_inst_implicit.cu)
@@ -686,7 +687,8 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   return 0;
 }
 
-int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok) {
+static int dense_eval_impl(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok,
+                           int extrapolate) {
   if (!ctx) return IVPB_ERR_CONFIG;
   const DenseLog& L = ctx->dense;
   if (!L.valid) return fail(ctx, IVPB_ERR_CONFIG, "no dense output retained: solve with dense_output = 1 first (InterpolationError::NotEnabled)");
@@ -712,7 +714,7 @@ int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const d
       e = ivpb_launch_dense_eval(L.method, L.n, L.n_cont, L.cap, (const int*)dev.out[OUT_NSEG].p,
                                  (const double*)dev.out[OUT_SEGX].p, (const double*)dev.out[OUT_SEGC].p, (long long)M,
                                  (const long long*)q_traj.p, L.lo[g], L.count[g], (const double*)q_ts.p, (double*)q_y.p,
-                                 (int*)q_ok.p, dev.stream);
+                                 (int*)q_ok.p, extrapolate, dev.stream);
     ctx->launches += 1;
     yg.resize(M * L.n); okg.resize(M);
     if (e == cudaSuccess) e = cudaMemcpyAsync(yg.data(), q_y.p, 8 * M * L.n, cudaMemcpyDeviceToHost, dev.stream);
@@ -727,6 +729,14 @@ int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const d
   }
   CK(cudaSetDevice(ctx->devs[0].id));
   return 0;
+}
+
+int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok) {
+  return dense_eval_impl(ctx, n_query, traj, ts, y, ok, 0);
+}
+int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y,
+                                int32_t* ok) {
+  return dense_eval_impl(ctx, n_query, traj, ts, y, ok, 1);
 }
 
 int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg) {

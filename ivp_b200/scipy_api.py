@@ -20,6 +20,9 @@ from . import api
 from .types import Direction, EventConfig, Method, Options, Status
 
 
+_SOURCE_PROBLEMS: dict = {}
+
+
 class OdeSolution:
     """`sol(t)`: dense output of one trajectory, evaluated on the device (src/python/solution.rs:17)."""
 
@@ -30,8 +33,10 @@ class OdeSolution:
 
     def __call__(self, t):
         ts = np.atleast_1d(np.asarray(t, dtype=np.float64))
-        y, ok = self._b.sol_many(np.full(ts.size, self._i), ts)
-        y[~ok] = np.nan                      # outside the covered span (the reference extrapolates; we do not)
+        # the reference's OdeSolution.__call__ extrapolates from the first / last step (src/python/solution.rs:41,116)
+        y, ok = self._b.sol_many(np.full(ts.size, self._i), ts, extrapolate=True)
+        if not ok.all():
+            raise ValueError("t is outside the solution range")          # solution.rs:47-50,119-121
         return y[0] if np.ndim(t) == 0 else y.T
 
 
@@ -82,8 +87,14 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
         problem = fun
     elif isinstance(fun, str) and "ivp_ode" in fun:
         p = 0 if args is None else len(np.atleast_1d(args))
-        problem = api.Problem.from_cuda_source(fun, n=Y0.shape[1], p=p, n_events=int("ivp_events" in fun),
-                                               has_jac="ivp_jac" in fun)
+        # event functions live in the source (`ivp_events` fills g[0..n_events)): their number is the number of
+        # event specs given, or `n_events=` when no specs are passed
+        ne = int(options.pop("n_events", 0)) or (len(events) if isinstance(events, (list, tuple)) else int(events is not None))
+        ne = ne if "ivp_events" in fun else 0
+        key = (fun, Y0.shape[1], p, ne)
+        if key not in _SOURCE_PROBLEMS:          # one NVRTC module cache per distinct source: repeated calls reuse it
+            _SOURCE_PROBLEMS[key] = api.Problem.from_cuda_source(fun, n=Y0.shape[1], p=p, n_events=ne, has_jac="ivp_jac" in fun)
+        problem = _SOURCE_PROBLEMS[key]
     else:
         problem = api.Problem.builtin(fun)
     t0, tf = float(t_span[0]), float(t_span[1])

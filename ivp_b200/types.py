@@ -194,9 +194,10 @@ class BatchSolution:
     extras: dict = field(default_factory=dict)
 
     # ---- Solution::sol / sol_many / sol_span (solution.rs:25-72), evaluated on the device ----
-    def sol_many(self, traj, ts):
-        """Dense output of trajectory `traj[q]` at `ts[q]`; returns (y[Q, n], ok[Q])."""
-        return self.extras["ctx"].dense_eval(np.asarray(traj), np.asarray(ts), self.n)
+    def sol_many(self, traj, ts, extrapolate: bool = False):
+        """Dense output of trajectory `traj[q]` at `ts[q]`; returns (y[Q, n], ok[Q]).  `extrapolate`: the rule of
+        ContinuousOutput::evaluate_extrapolate (cont.rs:91-150) for times outside the stored steps."""
+        return self.extras["ctx"].dense_eval(np.asarray(traj), np.asarray(ts), self.n, extrapolate)
 
     def sol(self, i: int, t: float):
         """Solution::sol for trajectory i: InterpolationError semantics of solution.rs:25-44."""

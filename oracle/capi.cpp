@@ -11,7 +11,7 @@
 #include <thread>
 
 #include "../include/ivpb.h"
-#include "problems.hpp"
+#include "test_problems.hpp"
 
 using namespace oracle;
 
@@ -130,7 +130,7 @@ int run_batch(const ivpb_options* o, int64_t N, double t0, double tf, const doub
 
 template <class P>
 int dense_eval(const ivpb_options* o, double t0, double tf, const double* y0, const double* params,
-               const double* ts, int nts, double* ys, int32_t* ok, double* span) {
+               const double* ts, int nts, double* ys, int32_t* ok, double* span, int extrapolate = 0) {
   constexpr int n = P::N;
   Options O = make_options(o, n);
   O.dense_output = true;
@@ -141,7 +141,7 @@ int dense_eval(const ivpb_options* o, double t0, double tf, const double* y0, co
     double a = 0, b = 0;
     bool has = sol_span(S, a, b);
     if (span) { span[0] = a; span[1] = b; span[2] = has ? 1.0 : 0.0; }
-    for (int k = 0; k < nts; ++k) ok[k] = sol_eval(S, ts[k], ys + (size_t)n * k) ? 1 : 0;
+    for (int k = 0; k < nts; ++k) ok[k] = (extrapolate ? sol_eval_extrapolate(S, ts[k], ys + (size_t)n * k) : sol_eval(S, ts[k], ys + (size_t)n * k)) ? 1 : 0;
   } catch (const std::exception& ex) { g_err = ex.what(); return 2; }
   return 0;
 }
@@ -158,6 +158,8 @@ int oracle_problem_dims(int problem, int* n, int* p, int* ne) {
     case IVPB_P_ROBERTSON: DIMS(Robertson) case IVPB_P_SHO: DIMS(Sho) case IVPB_P_ZERO3: DIMS(Zero3)
     case IVPB_P_EXP2: DIMS(Exp2) case IVPB_P_RATIONAL: DIMS(Rational) case IVPB_P_CANNON: DIMS(Cannon)
     case IVPB_P_LINEAR100: DIMS(Linear100) case IVPB_P_MEDAKZO64: DIMS(Medakzo64)
+    case 100: DIMS(RationalEv) case 101: DIMS(Sys3) case 102: DIMS(Scale1) case 103: DIMS(Scale2)
+    case 104: DIMS(Radial) case 105: DIMS(ConstRates)
     default: return 1;
   }
 }
@@ -171,6 +173,8 @@ int oracle_solve_batch(int problem, const ivpb_options* o, int64_t N, double t0,
     case IVPB_P_ROBERTSON: return RB(Robertson); case IVPB_P_SHO: return RB(Sho); case IVPB_P_ZERO3: return RB(Zero3);
     case IVPB_P_EXP2: return RB(Exp2); case IVPB_P_RATIONAL: return RB(Rational); case IVPB_P_CANNON: return RB(Cannon);
     case IVPB_P_LINEAR100: return RB(Linear100); case IVPB_P_MEDAKZO64: return RB(Medakzo64);
+    case 100: return RB(RationalEv); case 101: return RB(Sys3); case 102: return RB(Scale1); case 103: return RB(Scale2);
+    case 104: return RB(Radial); case 105: return RB(ConstRates);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -186,6 +190,24 @@ int oracle_dense_eval(int problem, const ivpb_options* o, double t0, double tf, 
     case IVPB_P_ROBERTSON: return DE(Robertson); case IVPB_P_SHO: return DE(Sho); case IVPB_P_ZERO3: return DE(Zero3);
     case IVPB_P_EXP2: return DE(Exp2); case IVPB_P_RATIONAL: return DE(Rational); case IVPB_P_CANNON: return DE(Cannon);
     case IVPB_P_LINEAR100: return DE(Linear100); case IVPB_P_MEDAKZO64: return DE(Medakzo64);
+    case 100: return DE(RationalEv); case 101: return DE(Sys3); case 102: return DE(Scale1); case 103: return DE(Scale2);
+    case 104: return DE(Radial); case 105: return DE(ConstRates);
+    default: g_err = "unknown problem id"; return 1;
+  }
+}
+
+// The same with ContinuousOutput::evaluate_extrapolate (src/solve/cont.rs:91-150).
+int oracle_dense_eval_extrapolate(int problem, const ivpb_options* o, double t0, double tf, const double* y0,
+                      const double* params, const double* ts, int nts, double* ys, int32_t* ok, double* span) {
+#define DX(T) dense_eval<T>(o, t0, tf, y0, params, ts, nts, ys, ok, span, 1)
+  switch (problem) {
+    case IVPB_P_DECAY: return DX(Decay); case IVPB_P_VDP_EPS: return DX(VdpEps); case IVPB_P_VDP_MU: return DX(VdpMu);
+    case IVPB_P_LORENZ: return DX(Lorenz); case IVPB_P_CR3BP: return DX(Cr3bp); case IVPB_P_BALL: return DX(Ball);
+    case IVPB_P_ROBERTSON: return DX(Robertson); case IVPB_P_SHO: return DX(Sho); case IVPB_P_ZERO3: return DX(Zero3);
+    case IVPB_P_EXP2: return DX(Exp2); case IVPB_P_RATIONAL: return DX(Rational); case IVPB_P_CANNON: return DX(Cannon);
+    case IVPB_P_LINEAR100: return DX(Linear100); case IVPB_P_MEDAKZO64: return DX(Medakzo64);
+    case 100: return DX(RationalEv); case 101: return DX(Sys3); case 102: return DX(Scale1); case 103: return DX(Scale2);
+    case 104: return DX(Radial); case 105: return DX(ConstRates);
     default: g_err = "unknown problem id"; return 1;
   }
 }

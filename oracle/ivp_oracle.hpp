@@ -922,4 +922,27 @@ inline bool sol_eval(const Solution& S, double t, double* yi) {
   return false;
 }
 
+// ContinuousOutput::evaluate_extrapolate / find_segment_extrapolate -- src/solve/cont.rs:91-150 (the rule behind the
+// reference's Python OdeSolution.__call__, src/python/solution.rs:41,116)
+inline bool sol_eval_extrapolate(const Solution& S, double t, double* yi) {
+  if (!S.has_dense || S.segs.empty()) return false;
+  const double tol = 1e-12;
+  const DenseSeg* use = nullptr;
+  for (const auto& sg : S.segs) {
+    double left = std::fmin(sg.xold, sg.xold + sg.h), right = std::fmax(sg.xold, sg.xold + sg.h);
+    if (t >= left - tol && t <= right + tol) { use = &sg; break; }
+  }
+  if (!use) {
+    const DenseSeg& first = S.segs.front();
+    const DenseSeg& last = S.segs.back();
+    const double first_left = std::fmin(first.xold, first.xold + first.h);
+    const double last_right = std::fmax(last.xold, last.xold + last.h);
+    if (t < first_left) use = &first;
+    else if (t > last_right) use = &last;
+    else return false;
+  }
+  interp_fn(S.method)(t, yi, S.n, use->cont.data(), use->xold, use->h);
+  return true;
+}
+
 }  // namespace oracle

@@ -20,7 +20,7 @@ def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
     if force or not os.path.exists(so) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-            for f in ("capi.cpp", "ivp_oracle.hpp", "ivp_oracle_implicit.hpp", "problems.hpp")):
+            for f in ("capi.cpp", "ivp_oracle.hpp", "ivp_oracle_implicit.hpp", "problems.hpp", "test_problems.hpp")):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so
 
@@ -36,6 +36,8 @@ def lib():
         L.oracle_dense_eval.argtypes = [C.c_int, C.POINTER(_abi.IvpbOptions), C.c_double, C.c_double, _abi.c_double_p,
                                         _abi.c_double_p, _abi.c_double_p, C.c_int, _abi.c_double_p, _abi.c_int32_p,
                                         _abi.c_double_p]
+        L.oracle_dense_eval_extrapolate.restype = C.c_int
+        L.oracle_dense_eval_extrapolate.argtypes = L.oracle_dense_eval.argtypes
         L.oracle_problem_dims.argtypes = [C.c_int, _abi.c_int32_p, _abi.c_int32_p, _abi.c_int32_p]
         L.oracle_last_error.restype = C.c_char_p
         L.oracle_hardware_threads.restype = C.c_int
@@ -72,8 +74,9 @@ def solve_batch(problem: int, t0: float, tf: float, y0, params, options: Options
     return BatchSolution(n=n, n_events=ne, **{k: arrays.get(k) for k in _abi.OUTPUT_FIELDS})
 
 
-def dense_eval(problem: int, t0, tf, y0, params, options: Options, ts):
-    """Solve one trajectory with dense_output=true; return (ys[len(ts), n], ok[len(ts)], span|None)."""
+def dense_eval(problem: int, t0, tf, y0, params, options: Options, ts, extrapolate: bool = False):
+    """Solve one trajectory with dense_output=true; return (ys[len(ts), n], ok[len(ts)], span|None).
+    `extrapolate`: ContinuousOutput::evaluate_extrapolate instead of Solution::sol."""
     n, p, ne = dims(problem)
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(n))
     par = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(p)) if p > 0 else None
@@ -82,7 +85,8 @@ def dense_eval(problem: int, t0, tf, y0, params, options: Options, ts):
     ok = np.zeros(ts.size, dtype=np.int32)
     span = np.zeros(3)
     mo = _abi.MarshalledOptions(options, n, ne)
-    rc = lib().oracle_dense_eval(int(problem), C.byref(mo.struct), float(t0), float(tf), _abi.ptr(y0), _abi.ptr(par),
+    fn = lib().oracle_dense_eval_extrapolate if extrapolate else lib().oracle_dense_eval
+    rc = fn(int(problem), C.byref(mo.struct), float(t0), float(tf), _abi.ptr(y0), _abi.ptr(par),
                                  _abi.ptr(ts), ts.size, _abi.ptr(ys), _abi.ptr(ok), _abi.ptr(span))
     if rc:
         raise RuntimeError(lib().oracle_last_error().decode())

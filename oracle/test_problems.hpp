@@ -1,0 +1,72 @@
+// test_problems.hpp -- oracle-only problems (ids >= 100) restating the callables of the reference's Python test
+// suite, so that tests/test_reference_pytests.py can run each of those tests against the oracle on the CPU and
+// against the CUDA path (the same right-hand sides as NVRTC user problems) on the GPU.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include "problems.hpp"
+
+namespace oracle {
+
+// fun_rational (tests/test_helpers.py:23-25) + the event functions of tests/test_events.py:13-17,103-104
+// (event_rational_1, event_rational_2, event_rational_3 with its threshold in p[0]: 7.4 there, 7 in
+// tests/test_t_eval.py:139-140)
+struct RationalEv : ProblemBase<RationalEv, 2, 1, 3> {
+  void ode(double t, const double* y, double* d) const {
+    d[0] = y[1] / t;
+    d[1] = y[1] * (y[0] + 2.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+  void events(double t, const double* y, double* g) const {
+    g[0] = y[0] - std::pow(y[1], 0.7);
+    g[1] = std::pow(y[1], 0.6) - y[0];
+    g[2] = t - p[0];
+  }
+  static constexpr bool HAS_JAC = true;                // tests/test_helpers.py:34-40
+  void jac(double t, const double* y, double* J) const {
+    J[0] = 0.0; J[1] = 1.0 / t;
+    J[2] = -2.0 * y[1] * y[1] / (t * (y[0] - 1.0) * (y[0] - 1.0));
+    J[3] = (y[0] + 4.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+  }
+};
+
+// sys3 + sys3_jac + its three events (tests/test_args.py:11-35); p = (omega, k, zfinal)
+struct Sys3 : ProblemBase<Sys3, 3, 3, 3> {
+  void ode(double, const double* w, double* d) const {
+    d[0] = -p[0] * w[1];
+    d[1] = p[0] * w[0];
+    d[2] = p[1] * w[2] * (1.0 - w[2]);
+  }
+  void events(double, const double* w, double* g) const { g[0] = w[0]; g[1] = w[1]; g[2] = w[2] - p[2]; }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* w, double* J) const {
+    J[0] = 0.0;  J[1] = -p[0]; J[2] = 0.0;
+    J[3] = p[0]; J[4] = 0.0;   J[5] = 0.0;
+    J[6] = 0.0;  J[7] = 0.0;   J[8] = p[1] * (1.0 - 2.0 * w[2]);
+  }
+};
+
+// y' = a y for each component (tests/test_args.py:73-78 fun_with_arg; test_edge_cases.py:14,53 with a = -1, 2;
+// test_step_control.py:144-145 with a = -0.001); one and two components
+struct Scale1 : ProblemBase<Scale1, 1, 1, 0> {
+  void ode(double, const double* y, double* d) const { d[0] = p[0] * y[0]; }
+};
+struct Scale2 : ProblemBase<Scale2, 2, 1, 0> {
+  void ode(double, const double* y, double* d) const { d[0] = p[0] * y[0]; d[1] = p[0] * y[1]; }
+};
+
+// tests/test_edge_cases.py:76-88 (gh-8848): radial Schroedinger-like system in r = exp(t)
+struct Radial : ProblemBase<Radial, 2, 0, 0> {
+  void ode(double t, const double* s, double* d) const {
+    const double r = std::exp(t);
+    const double V = -11.0 / r + 10.0 * r / (0.05 + r * r);
+    d[0] = r * s[1];
+    d[1] = -2.0 * r * ((-0.2 - V) * s[0] + 1.0 / r * s[1]);
+  }
+};
+
+// tests/test_edge_cases.py:104-110 (gh-9198): constant rates
+struct ConstRates : ProblemBase<ConstRates, 4, 0, 0> {
+  void ode(double, const double*, double* d) const {
+    d[0] = 1.73307544e-02; d[1] = 6.49376470e-06; d[2] = 0.0; d[3] = 0.0;
+  }
+};
+
+}  // namespace oracle

@@ -79,6 +79,7 @@ extern "C" {
     pub fn ivpb_solve_batch_device(ctx: *mut ivpb_ctx, problem: c_int, opt: *const ivpb_options, n: i64, t0: f64, tf: f64,
                                    d_y0: *const f64, d_params: *const f64, d_out: *const ivpb_outputs, stream: *mut c_void) -> c_int;
     pub fn ivpb_dense_eval(ctx: *mut ivpb_ctx, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
+    pub fn ivpb_dense_eval_extrapolate(ctx: *mut ivpb_ctx, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
     pub fn ivpb_dense_span(ctx: *mut ivpb_ctx, first: i64, count: i64, t_start: *mut f64, t_end: *mut f64, n_seg: *mut i32) -> c_int;
     pub fn ivpb_host_alloc(bytes: usize) -> *mut c_void;
     pub fn ivpb_host_free(p: *mut c_void);

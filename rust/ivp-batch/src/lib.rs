@@ -142,6 +142,13 @@ pub fn sol_many(ctx: &Context, index: usize, n: usize, ts: &[Float]) -> Result<V
     Ok(y.chunks(n).map(|c| c.to_vec()).collect())
 }
 
+/// `ContinuousOutput::evaluate_extrapolate` (reference src/solve/cont.rs:91-150) for trajectory `index`.
+pub fn sol_extrapolate(ctx: &Context, index: usize, n: usize, t: Float) -> Option<Vec<Float>> {
+    let (traj, mut y, mut ok) = (index as i64, vec![0.0; n], 0i32);
+    let rc = unsafe { sys::ivpb_dense_eval_extrapolate(ctx.raw, 1, &traj, &t, y.as_mut_ptr(), &mut ok) };
+    if rc != sys::IVPB_OK || ok == 0 { None } else { Some(y) }
+}
+
 /// `y0` is `[N x n]` row-major, `params` `[N x p]` row-major.  One `Solution` per trajectory.
 pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[Float], params: &[Float], options: Options)
                        -> Result<Vec<Solution>, Error> {

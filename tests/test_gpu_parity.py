@@ -617,6 +617,11 @@ def test_dense_output_segments_and_sol_match_oracle(oracle, method, backward):
         for bad in (lo - 0.1, hi + 0.1):
             with pytest.raises(ib.InterpolationError):
                 g.sol(i, bad)
+        # ContinuousOutput::evaluate_extrapolate (cont.rs:91-150): first / last segment answers outside the span
+        tx = np.array([lo - 0.3, lo - 1e-9, mid, hi + 1e-9, hi + 0.3])
+        yx, okx = g.sol_many([i] * tx.size, tx, extrapolate=True)
+        yo, oko, _ = oracle.dense_eval(PROBLEMS["sho"], t0, tf, y0[i], None, opts, tx, extrapolate=True)
+        assert okx.all() and oko.all() and np.array_equal(yx, yo)
 
 
 def test_dense_output_fma_build_truncation_and_zero_interval(oracle):
