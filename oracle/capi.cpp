@@ -159,7 +159,7 @@ int oracle_problem_dims(int problem, int* n, int* p, int* ne) {
     case IVPB_P_EXP2: DIMS(Exp2) case IVPB_P_RATIONAL: DIMS(Rational) case IVPB_P_CANNON: DIMS(Cannon)
     case IVPB_P_LINEAR100: DIMS(Linear100) case IVPB_P_MEDAKZO64: DIMS(Medakzo64)
     case 100: DIMS(RationalEv) case 101: DIMS(Sys3) case 102: DIMS(Scale1) case 103: DIMS(Scale2)
-    case 104: DIMS(Radial) case 105: DIMS(ConstRates)
+    case 104: DIMS(Radial) case 105: DIMS(ConstRates) case 106: DIMS(Linear2)
     default: return 1;
   }
 }
@@ -174,7 +174,7 @@ int oracle_solve_batch(int problem, const ivpb_options* o, int64_t N, double t0,
     case IVPB_P_EXP2: return RB(Exp2); case IVPB_P_RATIONAL: return RB(Rational); case IVPB_P_CANNON: return RB(Cannon);
     case IVPB_P_LINEAR100: return RB(Linear100); case IVPB_P_MEDAKZO64: return RB(Medakzo64);
     case 100: return RB(RationalEv); case 101: return RB(Sys3); case 102: return RB(Scale1); case 103: return RB(Scale2);
-    case 104: return RB(Radial); case 105: return RB(ConstRates);
+    case 104: return RB(Radial); case 105: return RB(ConstRates); case 106: return RB(Linear2);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -191,7 +191,7 @@ int oracle_dense_eval(int problem, const ivpb_options* o, double t0, double tf, 
     case IVPB_P_EXP2: return DE(Exp2); case IVPB_P_RATIONAL: return DE(Rational); case IVPB_P_CANNON: return DE(Cannon);
     case IVPB_P_LINEAR100: return DE(Linear100); case IVPB_P_MEDAKZO64: return DE(Medakzo64);
     case 100: return DE(RationalEv); case 101: return DE(Sys3); case 102: return DE(Scale1); case 103: return DE(Scale2);
-    case 104: return DE(Radial); case 105: return DE(ConstRates);
+    case 104: return DE(Radial); case 105: return DE(ConstRates); case 106: return DE(Linear2);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -207,7 +207,7 @@ int oracle_dense_eval_extrapolate(int problem, const ivpb_options* o, double t0,
     case IVPB_P_EXP2: return DX(Exp2); case IVPB_P_RATIONAL: return DX(Rational); case IVPB_P_CANNON: return DX(Cannon);
     case IVPB_P_LINEAR100: return DX(Linear100); case IVPB_P_MEDAKZO64: return DX(Medakzo64);
     case 100: return DX(RationalEv); case 101: return DX(Sys3); case 102: return DX(Scale1); case 103: return DX(Scale2);
-    case 104: return DX(Radial); case 105: return DX(ConstRates);
+    case 104: return DX(Radial); case 105: return DX(ConstRates); case 106: return DX(Linear2);
     default: g_err = "unknown problem id"; return 1;
   }
 }

@@ -69,4 +69,11 @@ struct ConstRates : ProblemBase<ConstRates, 4, 0, 0> {
   }
 };
 
+// fun_linear + jac_linear (tests/test_helpers.py:11-16), tests/test_ivp.py:272-317, tests/test_stiff.py:14-94
+struct Linear2 : ProblemBase<Linear2, 2, 0, 0> {
+  void ode(double, const double* y, double* d) const { d[0] = -y[0] - 5.0 * y[1]; d[1] = y[0] + y[1]; }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double*, double* J) const { J[0] = -1.0; J[1] = -5.0; J[2] = 1.0; J[3] = 1.0; }
+};
+
 }  // namespace oracle

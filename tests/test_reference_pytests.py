@@ -65,7 +65,12 @@ __device__ void ivp_ode(double t, const double* y, const double* p, double* d) {
   d[0] = 1.73307544e-02; d[1] = 6.49376470e-06; d[2] = 0.0; d[3] = 0.0;
 }
 """
-ORACLE_ID = {SRC_RATIONAL_EV: 100, SRC_SYS3: 101, SRC_SCALE1: 102, SRC_SCALE2: 103, SRC_RADIAL: 104, SRC_CONST: 105}
+# tests/test_helpers.py:11-16
+SRC_LINEAR = """
+__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = -y[0] - 5.0 * y[1]; d[1] = y[0] + y[1]; }
+__device__ void ivp_jac(double t, const double* y, const double* p, double* J) { J[0] = -1.0; J[1] = -5.0; J[2] = 1.0; J[3] = 1.0; }
+"""
+ORACLE_ID = {SRC_LINEAR: 106, SRC_RATIONAL_EV: 100, SRC_SYS3: 101, SRC_SCALE1: 102, SRC_SCALE2: 103, SRC_RADIAL: 104, SRC_CONST: 105}
 
 METHODS = ["RK23", "RK45", "DOP853", "Radau", "BDF"]
 
@@ -193,6 +198,29 @@ def test_integration_analytic_jacobian(solve_ivp):
         assert np.all(compute_error(res.y, sol_rational(res.t), 1e-3, 1e-6) < 5)
 
 
+@pytest.mark.parametrize("method", ["Radau", "BDF"])
+@pytest.mark.parametrize("jac", [True, None])
+def test_integration_const_jac(solve_ivp, method, jac):           # tests/test_ivp.py:272-317, tests/test_stiff.py:14-94
+    rtol, atol, t_span = 1e-3, 1e-6, [0, 2]
+    sol_linear = lambda t: np.vstack((-5 * np.sin(2 * t), 2 * np.cos(2 * t) + np.sin(2 * t)))   # test_helpers.py:19-21
+    res = solve_ivp(SRC_LINEAR, t_span, [0, 2], rtol=rtol, atol=atol, method=method, dense_output=True, jac=jac)
+    assert res.t[0] == t_span[0] and res.t_events is None and res.y_events is None
+    assert res.success and res.status == 0
+    assert res.nfev < 100
+    assert np.all(compute_error(res.y, sol_linear(res.t), rtol, atol) < 10)
+    tc = np.linspace(*t_span)
+    e = compute_error(res.sol(tc), sol_linear(tc), rtol, atol)
+    assert np.all(e < (60 if method == "BDF" else 15))            # the reference's own relaxed BDF bound
+    np.testing.assert_allclose(res.sol(res.t), res.y, rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize("method", ["Radau", "BDF"])
+def test_integration_stiff(solve_ivp, method):                    # tests/test_ivp.py:319-343, tests/test_stiff.py:97-143
+    res = solve_ivp("robertson", [0, 1e8], [1e4, 0, 0], args=(0.04, 1e4, 3e7), rtol=1e-6, atol=1e-6, method=method)
+    assert res.success and res.nfev < 5000 and res.njev < 200
+    np.testing.assert_allclose(res.y[:, -1].sum(), 1e4, rtol=1e-4)   # (mass conservation; stronger than the reference)
+
+
 # ---- tests/test_t_eval.py:10-160 ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("t_span,t_eval,check", [
     ([5, 9], np.linspace(5, 9, 10), True),                       # test_t_eval_forward
@@ -245,6 +273,44 @@ def test_events(solve_ivp, method):                               # test_events_
     assert abs(y[0] - y[1] ** 0.7) < 1e-9
     y = res.y_events[1][0]
     assert abs(y[1] ** 0.6 - y[0]) < 1e-9
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_events_directions_and_terminal(solve_ivp, method):       # tests/test_ivp.py:345-420
+    ev1 = lambda y: y[0] - y[1] ** 0.7
+    ev2 = lambda y: y[1] ** 0.6 - y[0]
+    res = rational(solve_ivp, [5, 8], events=[Ev(direction=1), Ev(direction=1), Ev()], p=100.0, method=method)
+    assert res.status == 0 and len(res.t_events[0]) == 1 and len(res.t_events[1]) == 0
+    assert 5.3 < res.t_events[0][0] < 5.7 and res.y_events[0].shape == (1, 2)
+    assert np.isclose(ev1(res.y_events[0][0]), 0, atol=1e-5)
+    res = rational(solve_ivp, [5, 8], events=[Ev(direction=-1), Ev(direction=-1), Ev()], p=100.0, method=method)
+    assert res.status == 0 and len(res.t_events[0]) == 0 and len(res.t_events[1]) == 1
+    assert 7.3 < res.t_events[1][0] < 7.7 and res.y_events[1].shape == (1, 2)
+    assert np.isclose(ev2(res.y_events[1][0]), 0, atol=1e-5)
+    res = rational(solve_ivp, [5, 8], events=[Ev(), Ev(), Ev(terminal=True)], p=7.4, method=method, dense_output=True)
+    assert res.status == 1
+    assert len(res.t_events[0]) == 1 and len(res.t_events[1]) == 0 and len(res.t_events[2]) == 1
+    assert 5.3 < res.t_events[0][0] < 5.7 and 7.3 < res.t_events[2][0] < 7.5
+    assert res.y_events[0].shape == (1, 2) and res.y_events[2].shape == (1, 2)
+    assert np.isclose(ev1(res.y_events[0][0]), 0, atol=1e-5) and np.isclose(res.t_events[2][0] - 7.4, 0, atol=1e-5)
+    # tests/test_ivp.py:429-438: termination by an event does not break the interpolants; y_event matches the solution
+    assert res.t[-1] == res.t_events[2][0]
+    tc = np.linspace(res.t[0], res.t[-1])
+    assert np.all(compute_error(res.sol(tc), sol_rational(tc), 1e-3, 1e-6) < 5)
+    assert np.allclose(sol_rational(res.t_events[0][0]), res.y_events[0][0], rtol=1e-3, atol=1e-6)
+    # tests/test_ivp.py:440-492: backward direction (crossings seen with the opposite sign of time)
+    back = dict(method=method, p=100.0)
+    res = solve_ivp(SRC_RATIONAL_EV, [8, 5], [4 / 9, 20 / 81], args=(100.0,), events=[Ev(), Ev(), Ev()], method=method)
+    assert res.status == 0 and len(res.t_events[0]) == 1 and len(res.t_events[1]) == 1
+    assert 5.3 < res.t_events[0][0] < 5.7 and 7.3 < res.t_events[1][0] < 7.7
+    assert np.isclose(ev1(res.y_events[0][0]), 0, atol=1e-5) and np.isclose(ev2(res.y_events[1][0]), 0, atol=1e-5)
+    res = solve_ivp(SRC_RATIONAL_EV, [8, 5], [4 / 9, 20 / 81], args=(100.0,), events=[Ev(direction=-1), Ev(direction=-1), Ev()],
+                    method=method)
+    assert res.status == 0 and len(res.t_events[0]) == 1 and len(res.t_events[1]) == 0
+    res = solve_ivp(SRC_RATIONAL_EV, [8, 5], [4 / 9, 20 / 81], args=(100.0,), events=[Ev(direction=1), Ev(direction=1), Ev()],
+                    method=method)
+    assert res.status == 0 and len(res.t_events[0]) == 0 and len(res.t_events[1]) == 1
+    del back
 
 
 def test_terminal_event(solve_ivp):                               # tests/test_events.py:99-113
