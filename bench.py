@@ -48,6 +48,7 @@ WORKLOADS = {
     "ball_dopri5_events": ("ball", "DOPRI5", 1e-8, 1e-10, 4, 2),             # configs[3]
     "robertson_radau": ("robertson", "RADAU", 1e-6, 1e-6, 13, 3),            # configs[4]
     "robertson_bdf": ("robertson", "BDF", 1e-6, 1e-6, 13, 3),
+    "robertson_dae_radau": ("robertson_dae", "RADAU", 1e-6, 1e-10, 14, 3),   # M y' = f, M = diag(1, 1, 0)
     "vdpstiff_radau": ("vdp_stiff", "RADAU", 1e-4, 1e-6, 5, 2),
     "vdpstiff_bdf": ("vdp_stiff", "BDF", 1e-4, 1e-6, 5, 2),
     "linear100_dopri5": ("linear100", "DOPRI5", 1e-6, 1e-8, 100, 100),       # warp-per-trajectory kernels (n > 32)
@@ -55,6 +56,7 @@ WORKLOADS = {
     "medakzo_bdf": ("medakzo", "BDF", 1e-5, 1e-7, 900, 64),
 }
 N_T_EVAL = {"cr3bp_dop853_teval": 101}
+EXTRA_OPTIONS = {"robertson_dae_radau": {"mass_storage": "Full"}}
 NOMINAL_FP64_TFLOPS = 37.0   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 
@@ -99,6 +101,7 @@ def workload_options(name: str, t0: float, tf: float, flags: int = 0, jac_mode: 
         extra["first_step"] = (tf - t0) / 1000.0
     if jac_mode:
         extra["jac_mode"] = 1
+    extra.update(EXTRA_OPTIONS.get(name, {}))
     return Options(method=Method[method], rtol=rtol, atol=atol, flags=flags, max_events=1, **extra)
 
 

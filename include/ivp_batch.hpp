@@ -109,8 +109,12 @@ struct Options {
   std::optional<Float> first_step, max_step, min_step;
   bool dense_output = false;
   int max_segments = 4096;   // dense_output: interpolant segments kept per trajectory (one per accepted step)
-  // jac_storage / mass_storage / nind1-3 of the reference select Banded / DAE variants that the device path
-  // does not implement (Full Jacobian, Identity mass, pure ODE == the values solve_ivp passes by default).
+  // mass_storage / nind1-3 (options.rs:105-122; RADAU only, solve_ivp.rs:246-258): Full => M y' = f with the problem's
+  // constant mass matrix (IVP::mass), nind2 / nind3 => index-2 / index-3 variable counts of a DAE.  jac_storage of the
+  // reference selects a Banded Jacobian layout; device Jacobians are always Full.
+  enum class MatrixStorage { Identity, Full };
+  MatrixStorage mass_storage = MatrixStorage::Identity;
+  std::optional<size_t> nind1, nind2, nind3;
   // ---- batched-solve additions (no reference equivalent) ----
   std::optional<std::vector<EventConfig>> event_config;   // overrides the problem's IVP::event_config
   int max_events = 8;        // event hits stored per event function and trajectory
@@ -134,6 +138,10 @@ class OptionsBuilder {
   OptionsBuilder& min_step(Float h) { o_.min_step = h; return *this; }
   OptionsBuilder& dense_output(bool b) { o_.dense_output = b; return *this; }
   OptionsBuilder& max_segments(int n) { o_.max_segments = n; return *this; }
+  OptionsBuilder& mass_storage(Options::MatrixStorage s) { o_.mass_storage = s; return *this; }
+  OptionsBuilder& nind1(size_t k) { o_.nind1 = k; return *this; }
+  OptionsBuilder& nind2(size_t k) { o_.nind2 = k; return *this; }
+  OptionsBuilder& nind3(size_t k) { o_.nind3 = k; return *this; }
   OptionsBuilder& event_config(std::vector<EventConfig> c) { o_.event_config = std::move(c); return *this; }
   OptionsBuilder& max_events(int n) { o_.max_events = n; return *this; }
   OptionsBuilder& max_out(int n) { o_.max_out = n; return *this; }
@@ -234,10 +242,13 @@ class Context {
 class Problem {
  public:
   // Built-in problems (ivpb_builtin in ivpb.h): "decay", "vdp_eps", "vdp_mu", "lorenz", "cr3bp",
-  // "bouncing_ball", "robertson", "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64".
+  // "bouncing_ball", "robertson", "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64",
+  // "robertson_dae", "mass_linear3" (the last two carry a mass matrix: RADAU with mass_storage = Full).
   static Problem builtin(const std::string& name) {
     static const char* names[] = {"decay", "vdp_eps", "vdp_mu", "lorenz", "cr3bp", "bouncing_ball", "robertson",
-                                  "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64"};
+                                  "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64",
+                                  "robertson_dae", "mass_linear3"};
+    static_assert(sizeof(names) / sizeof(names[0]) == IVPB_P_BUILTIN_COUNT, "one name per ivpb_builtin id");
     for (int i = 0; i < IVPB_P_BUILTIN_COUNT; ++i)
       if (name == names[i]) {
         Problem p;
@@ -250,9 +261,11 @@ class Problem {
   // `impl IVP for MyProblem` as CUDA C: the source must define
   //   __device__ void ivp_ode(double t, const double* y, const double* p, double* dydt);
   // and, if n_events > 0 / has_jac, ivp_events(t, y, p, g) / ivp_jac(t, y, p, J row-major).
-  static Problem from_cuda_source(std::string src, int n, int p = 0, int n_events = 0, bool has_jac = false) {
+  // `has_mass`: the source also defines `ivp_mass(const double* p, double* M)` (IVP::mass, row-major n x n).
+  static Problem from_cuda_source(std::string src, int n, int p = 0, int n_events = 0, bool has_jac = false,
+                                  bool has_mass = false) {
     Problem q;
-    q.src_ = std::move(src); q.n_ = n; q.p_ = p; q.n_events_ = n_events; q.has_jac_ = has_jac;
+    q.src_ = std::move(src); q.n_ = n; q.p_ = p; q.n_events_ = n_events; q.has_jac_ = (has_jac ? 1 : 0) | (has_mass ? 2 : 0);
     return q;
   }
   int n() const { return n_; }
@@ -262,14 +275,14 @@ class Problem {
     if (builtin_ >= 0) return builtin_;
     for (auto& h : handles_) if (h.first == ctx.get()) return h.second;
     int h = -1;
-    if (ivpb_nvrtc_problem(ctx.get(), src_.c_str(), n_, p_, n_events_, has_jac_ ? 1 : 0, &h) != IVPB_OK)
+    if (ivpb_nvrtc_problem(ctx.get(), src_.c_str(), n_, p_, n_events_, has_jac_, &h) != IVPB_OK)
       throw ConfigError(ivpb_last_error(ctx.get()));
     handles_.push_back({ctx.get(), h});
     return h;
   }
  private:
   int builtin_ = -1, n_ = 0, p_ = 0, n_events_ = 0;
-  bool has_jac_ = false;
+  int has_jac_ = 0;            // bit 0: ivp_jac, bit 1: ivp_mass
   std::string src_;
   mutable std::vector<std::pair<ivpb_ctx*, int>> handles_;
 };
@@ -305,6 +318,10 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
   o.t_eval = o.has_t_eval ? options.t_eval->data() : nullptr;
   o.dense_output = options.dense_output;
   o.max_segments = options.dense_output ? options.max_segments : 0;
+  o.mass_storage = options.mass_storage == Options::MatrixStorage::Full ? 1 : 0;
+  o.nind1 = options.nind1 ? (int32_t)*options.nind1 : -1;
+  o.nind2 = options.nind2 ? (int32_t)*options.nind2 : -1;
+  o.nind3 = options.nind3 ? (int32_t)*options.nind3 : -1;
   std::vector<int32_t> dirs;
   std::vector<int64_t> terms;
   if (options.event_config) {

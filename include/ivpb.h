@@ -56,7 +56,10 @@ typedef enum {
   IVPB_P_CANNON = 11,    /* y' = [y1, -9.80665] n=2 p=0; event y[0], terminal, negative  reference tests/test_ivp.py:153-160 */
   IVPB_P_LINEAR100 = 12, /* y' = -y         n=100 p=0 (warp-per-trajectory kernels)     reference benches/benchmark.py:39-41,137-146 */
   IVPB_P_MEDAKZO64 = 13, /* MEDAKZO on 32 grid points  n=64 p=0                      reference tests/test_ivp.py:77-101 */
-  IVPB_P_BUILTIN_COUNT = 14
+  IVPB_P_ROBERTSON_DAE = 14, /* Robertson as an index-1 DAE: M = diag(1, 1, 0), third row x + y + z - 1 = 0;  n=3 p=3; needs
+                                mass_storage = 1 (RADAU).  Exercises src/methods/radau.rs:375-386,525-539,626-634 */
+  IVPB_P_MASS_LINEAR3 = 15,  /* M y' = A y with a full (non-diagonal, invertible) constant M; n=3 p=1 (scales A); RADAU + mass */
+  IVPB_P_BUILTIN_COUNT = 16
 } ivpb_builtin;
 
 /* Mirrors `Options` (reference src/solve/options.rs:75-123) plus the per-event `EventConfig`
@@ -82,6 +85,11 @@ typedef struct {
   int32_t jac_mode;            /* 0 finite differences (src/ivp.rs:67-107), 1 analytic ivp_jac */
   int32_t flags;               /* IVPB_FLAG_* */
   int32_t max_segments;        /* dense_output: interpolant segments stored per trajectory (one per accepted step) */
+  /* RADAU only (src/solve/solve_ivp.rs:246-258; every other method ignores them, like the reference): */
+  int32_t mass_storage;        /* Options.mass_storage: 0 = Identity (default, y' = f), 1 = Full: M y' = f with the problem's
+                                  constant mass matrix (IVP::mass, src/ivp.rs:109-120; device hook `mass` / `ivp_mass`) */
+  int32_t nind1, nind2, nind3; /* Options.nind1..3: index-1/2/3 variable counts of a DAE, < 0 => None
+                                  (partition rules and Error::Config of src/methods/radau.rs:210-245) */
 } ivpb_options;
 
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
@@ -140,7 +148,8 @@ int ivpb_device_count(const ivpb_ctx* ctx);
 int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_events);
 /* User problem in CUDA C, compiled with NVRTC together with the solver templates.  `cuda_src` must define
  *   __device__ void ivp_ode(double t, const double* y, const double* p, double* dydt);
- * and, if n_events > 0 / has_jac,
+ * and, if n_events > 0 / has_jac (bit 0: analytic Jacobian `ivp_jac`; bit 1: constant mass matrix
+ * `__device__ void ivp_mass(const double* p, double* M)`, row-major n x n, IVP::mass of src/ivp.rs:109-120),
  *   __device__ void ivp_events(double t, const double* y, const double* p, double* g);
  *   __device__ void ivp_jac(double t, const double* y, const double* p, double* J);  // row-major n x n
  * (the IVP trait, reference src/ivp.rs:27-121, with the parameter row made explicit). */

@@ -43,6 +43,10 @@ class IvpbOptions(C.Structure):
         ("jac_mode", C.c_int32),
         ("flags", C.c_int32),
         ("max_segments", C.c_int32),
+        ("mass_storage", C.c_int32),
+        ("nind1", C.c_int32),
+        ("nind2", C.c_int32),
+        ("nind3", C.c_int32),
     ]
 
 
@@ -163,6 +167,13 @@ class MarshalledOptions:
         o.jac_mode = int(opts.jac_mode)
         o.flags = int(opts.flags)
         o.max_segments = int(getattr(opts, "max_segments", 0))
+        ms = str(getattr(opts, "mass_storage", "Identity")).lower()
+        if ms not in ("identity", "full"):
+            raise ValueError("mass_storage must be 'Identity' or 'Full' (banded mass matrices are not supported)")
+        o.mass_storage = int(ms == "full")
+        for fld in ("nind1", "nind2", "nind3"):
+            v = getattr(opts, fld, None)
+            setattr(o, fld, -1 if v is None else int(v))
 
     @property
     def seg_cap(self) -> int:

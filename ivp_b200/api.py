@@ -24,7 +24,7 @@ _lib = None
 #: Built-in problems (include/ivpb.h `ivpb_builtin`).
 PROBLEMS = {
     "decay": 0, "vdp_eps": 1, "vdp_mu": 2, "lorenz": 3, "cr3bp": 4, "bouncing_ball": 5, "robertson": 6,
-    "sho": 7, "zero3": 8, "exp2": 9, "rational": 10, "cannon": 11, "linear100": 12, "medakzo64": 13,
+    "sho": 7, "zero3": 8, "exp2": 9, "rational": 10, "cannon": 11, "linear100": 12, "medakzo64": 13, "robertson_dae": 14, "mass_linear3": 15,
 }
 
 IVPB_FLAG_STRICT_FP = 1
@@ -109,10 +109,11 @@ class Problem:
         return Problem(pid, n.value, p.value, ne.value, name)
 
     @staticmethod
-    def from_cuda_source(src: str, n: int, p: int = 0, n_events: int = 0, has_jac: bool = False) -> "Problem":
+    def from_cuda_source(src: str, n: int, p: int = 0, n_events: int = 0, has_jac: bool = False,
+                         has_mass: bool = False) -> "Problem":
         """User problem: `src` defines `__device__ void ivp_ode(double t, const double* y, const double* p,
-        double* dydt)` (+ `ivp_events`, `ivp_jac`), see include/ivpb.h."""
-        return Problem(-1, n, p, n_events, "user", cuda_src=src, has_jac=has_jac)
+        double* dydt)` (+ `ivp_events`, `ivp_jac`, `ivp_mass`), see include/ivpb.h."""
+        return Problem(-1, n, p, n_events, "user", cuda_src=src, has_jac=int(bool(has_jac)) | (2 if has_mass else 0))
 
     def resolve(self, ctx: "Context") -> int:
         if self.cuda_src is None:

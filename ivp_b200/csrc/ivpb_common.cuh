@@ -41,6 +41,7 @@ struct KArgs {
   int n_t_eval, out_cap;
   int max_events, jac_mode;
   int vec_io;            // y0 / y_final rows are 16-byte aligned: move them as double2 (LDG.128 / STG.128)
+  int nind1, nind2, nind3;   // RADAU with a mass matrix: resolved DAE partition (radau.rs:210-245); nind1 + nind2 + nind3 == n
   double newton_tol;     // implicit methods: Newton stopping tolerance (radau.rs:198-205, bdf.rs:174-184), host-computed
   int ev_dir[MAX_EVENTS_FN];
   i64 ev_term[MAX_EVENTS_FN];   // < 0: not terminal

@@ -105,7 +105,11 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
     s += "  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { ivp_ode(t, y, p, d); }\n";
   if (up.n_events > 0)
     s += "  static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { ivp_events(t, y, p, g); }\n";
-  if (up.has_jac) {
+  if (up.has_jac & 2) {
+    s += "  static constexpr bool HAS_MASS = true;\n";
+    s += "  static __device__ __forceinline__ void mass(const double* p, double* M) { ivp_mass(p, M); }\n";
+  }
+  if (up.has_jac & 1) {
     s += "  static constexpr bool HAS_JAC = true;\n";
     s += "  static __device__ __forceinline__ void jac(double t, const double* y, const double* p, double* J) { ivp_jac(t, y, p, J); }\n";
   }
@@ -209,7 +213,7 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
     // must match ivpb::MatSel / RadauTraj / BdfTraj::SMEM_DOUBLES_PER_THREAD (ivpb_implicit.cuh)
     block = up.n <= 6 ? 128 : 64;
     size_t doubles = 0;
-    if (up.n > 3) doubles += (size_t)(method == 4 ? 4 : 2) * up.n * up.n;   // Jacobian + iteration matrices
+    if (up.n > 3) doubles += (size_t)(method == 4 ? ((up.has_jac & 2) ? 5 : 4) : 2) * up.n * up.n;   // Jacobian + iteration matrices (+ RADAU mass matrix)
     if (method == 5) doubles += (size_t)15 * up.n;                          // BDF: D (8 rows), scratch (6), Jacobian point
     smem = doubles * block * 8;
     if (smem > 0) {

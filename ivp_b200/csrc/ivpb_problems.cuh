@@ -53,6 +53,51 @@ struct PLorenz : ProblemDefaults<3, 3, 0> {     // reference benches/benchmark.p
   }
 };
 
+// Robertson as an index-1 DAE, M = diag(1, 1, 0) (the third row is the conservation law x + y + z = 1): the classic
+// mass-matrix demonstration for RADAU5.  Needs Options.mass_storage = Full.
+struct PRobertsonDae : ProblemDefaults<3, 3, 0> {
+  IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
+    const double x = s[0], y = s[1], z = s[2];
+    d[0] = -p[0] * x + p[1] * y * z;
+    d[1] = p[0] * x - p[1] * y * z - p[2] * y * y;
+    d[2] = x + y + z - 1.0;
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* s, const double* p, double* J) {
+    const double y = s[1], z = s[2];
+    J[0] = -p[0];  J[1] = p[1] * z;                       J[2] = p[1] * y;
+    J[3] = p[0];   J[4] = -p[1] * z - 2.0 * p[2] * y;     J[5] = -p[1] * y;
+    J[6] = 1.0;    J[7] = 1.0;                            J[8] = 1.0;
+  }
+  static constexpr bool HAS_MASS = true;
+  IVPB_DEV void mass(const double*, double* M) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) M[k] = 0.0;
+    M[0] = 1.0; M[4] = 1.0;
+  }
+};
+
+// M y' = p0 A y with a full, invertible, non-symmetric constant M (every entry of the mass loops is exercised)
+struct PMassLinear3 : ProblemDefaults<3, 1, 0> {
+  IVPB_DEV void ode(double, const double* y, const double* p, double* d) {
+    d[0] = p[0] * (-2.0 * y[0] + 1.0 * y[1]);
+    d[1] = p[0] * (1.0 * y[0] - 2.0 * y[1] + 1.0 * y[2]);
+    d[2] = p[0] * (1.0 * y[1] - 2.0 * y[2]);
+  }
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double*, const double* p, double* J) {
+    J[0] = -2.0 * p[0]; J[1] = p[0];        J[2] = 0.0;
+    J[3] = p[0];        J[4] = -2.0 * p[0]; J[5] = p[0];
+    J[6] = 0.0;         J[7] = p[0];        J[8] = -2.0 * p[0];
+  }
+  static constexpr bool HAS_MASS = true;
+  IVPB_DEV void mass(const double*, double* M) {
+    M[0] = 2.0;  M[1] = 0.5;  M[2] = 0.0;
+    M[3] = 0.25; M[4] = 1.5;  M[5] = -0.5;
+    M[6] = 0.0;  M[7] = 0.75; M[8] = 3.0;
+  }
+};
+
 struct PCr3bp : ProblemDefaults<6, 1, 0> {      // reference examples/cr3bp.rs:24-35
   IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
     const double mu = p[0];

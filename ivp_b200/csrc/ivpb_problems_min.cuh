@@ -16,6 +16,10 @@ struct ProblemDefaults {
   static constexpr bool HAS_ODE_I = false;   // per-component RHS `double ode_i(t, y, p, i)` for the warp-per-trajectory kernels
   IVPB_DEV void events(double, const double*, const double*, double*) {}
   IVPB_DEV void jac(double, const double*, const double*, double*) {}
+  // IVP::mass (src/ivp.rs:109-120): constant mass matrix of M y' = f, row-major n x n; used by RADAU when
+  // Options.mass_storage = Full (src/methods/radau.rs:283,358-359)
+  static constexpr bool HAS_MASS = false;
+  IVPB_DEV void mass(const double*, double*) {}
   // IVP::event_config default (src/ivp.rs:51-53 -> EventConfig::new: All, non-terminal)
   IVPB_HD int default_dir(int) { return 0; }
   IVPB_HD i64 default_term(int) { return -1; }

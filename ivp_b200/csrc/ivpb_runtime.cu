@@ -32,12 +32,13 @@ typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* sme
   extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*, int*);       \
   extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
-DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64)
+DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64) DECL(robertson_dae) DECL(mass_linear3)
 #undef DECL
 #define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag}
 static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
-    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64)};
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
+    ROW(robertson_dae), ROW(mass_linear3)};
 #undef ROW
 // dense-output evaluation kernels (ivpb_dense.cu)
 extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
@@ -50,7 +51,8 @@ extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const d
 #define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag}
 static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
-    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64)};
+    ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
+    ROW(robertson_dae), ROW(mass_linear3)};
 #undef ROW
 
 namespace {
@@ -217,8 +219,26 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
   }
   if (o->jac_mode == 1 && pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1: the warp-cooperative implicit kernels (n > 8) use the finite-difference Jacobian only");
-  if (o->jac_mode == 1 && !pi.has_jac && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
+  if (o->jac_mode == 1 && !(pi.has_jac & 1) && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
+  if (o->method == IVPB_RADAU) {
+    // Options.mass_storage / nind1..3 reach RADAU only (solve_ivp.rs:246-258); DAE partition rules of radau.rs:210-245
+    const bool has_mass = (pi.has_jac & 2) != 0;
+    if (o->mass_storage != 0 && o->mass_storage != 1) return fail(ctx, IVPB_ERR_CONFIG, "mass_storage must be 0 (Identity) or 1 (Full)");
+    if (o->mass_storage == 1 && !has_mass)
+      return fail(ctx, IVPB_ERR_CONFIG, "mass_storage = Full, but the problem defines no mass matrix (IVP::mass / ivp_mass)");
+    if (o->mass_storage == 0 && has_mass)
+      return fail(ctx, IVPB_ERR_CONFIG, "the problem defines a mass matrix: RADAU needs mass_storage = Full (Identity storage cannot hold it)");
+    if (has_mass && pi.n > 8)
+      return fail(ctx, IVPB_ERR_CONFIG, "mass matrices are implemented for the thread-per-trajectory RADAU kernels (n <= 8)");
+    const int64_t k1 = o->nind1, k2 = o->nind2 < 0 ? 0 : o->nind2, k3 = o->nind3 < 0 ? 0 : o->nind3;
+    if (o->nind1 >= 0 || o->nind2 >= 0 || o->nind3 >= 0) {
+      if (o->nind1 < 0 ? (k2 + k3 > pi.n) : (k1 + k2 + k3 != pi.n))
+        return fail(ctx, IVPB_ERR_CONFIG, "RADAU: invalid DAE partition (ConfigError::InvalidDAEPartition: nind1 + nind2 + nind3 must equal n)");
+      if ((k2 > 0 || k3 > 0) && !has_mass)
+        return fail(ctx, IVPB_ERR_CONFIG, "index-2 / index-3 variables (nind2, nind3) need a problem with a mass matrix");
+    }
+  }
   return 0;
 }
 
@@ -285,6 +305,11 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
   a.out_cap = o->has_t_eval ? o->n_t_eval + 1 : o->max_out;
   a.max_events = o->max_events;
   a.jac_mode = o->jac_mode;
+  {   // resolved DAE partition (radau.rs:210-245; validated above)
+    const int k2 = o->nind2 < 0 ? 0 : o->nind2, k3 = o->nind3 < 0 ? 0 : o->nind3;
+    a.nind2 = k2; a.nind3 = k3;
+    a.nind1 = (o->nind1 < 0 && o->nind2 < 0 && o->nind3 < 0) ? pi.n : (o->nind1 < 0 ? pi.n - k2 - k3 : o->nind1);
+  }
   a.seg_cap = o->dense_output ? o->max_segments : 0;
   a.n_cont = coeffs_per_state(o->method) * pi.n;
   if (o->method == IVPB_RADAU) {

@@ -93,12 +93,14 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
         ne = ne if "ivp_events" in fun else 0
         key = (fun, Y0.shape[1], p, ne)
         if key not in _SOURCE_PROBLEMS:          # one NVRTC module cache per distinct source: repeated calls reuse it
-            _SOURCE_PROBLEMS[key] = api.Problem.from_cuda_source(fun, n=Y0.shape[1], p=p, n_events=ne, has_jac="ivp_jac" in fun)
+            _SOURCE_PROBLEMS[key] = api.Problem.from_cuda_source(fun, n=Y0.shape[1], p=p, n_events=ne, has_jac="ivp_jac" in fun,
+                                                                   has_mass="ivp_mass" in fun)
         problem = _SOURCE_PROBLEMS[key]
     else:
         problem = api.Problem.builtin(fun)
     t0, tf = float(t_span[0]), float(t_span[1])
-    known = {"rtol", "atol", "max_step", "min_step", "first_step", "max_steps"}          # solve.rs:290-340
+    known = {"rtol", "atol", "max_step", "min_step", "first_step", "max_steps",          # solve.rs:290-340
+             "mass_storage", "nind1", "nind2", "nind3"}                                  # Options of the Rust crate (RADAU)
     unknown = set(options) - known - {"max_events", "max_out", "max_segments", "strict_fp", "fast_fp"}
     if unknown:
         raise TypeError(f"unknown options: {sorted(unknown)}")
@@ -109,6 +111,8 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
                    first_step=options.get("first_step"), max_step=options.get("max_step"), min_step=options.get("min_step"),
                    dense_output=bool(dense_output), event_config=cfgs, max_events=int(options.get("max_events", 64)),
                    max_out=int(options.get("max_out", 4096)), max_segments=int(options.get("max_segments", 4096)) if dense_output else 0,
+                   mass_storage=options.get("mass_storage", "Identity"), nind1=options.get("nind1"),
+                   nind2=options.get("nind2"), nind3=options.get("nind3"),
                    jac_mode=1 if jac in (True, "analytic") or (isinstance(jac, str) and "ivp_jac" in jac) else 0,
                    flags=(api.IVPB_FLAG_STRICT_FP if options.get("strict_fp") else 0) |
                          (api.IVPB_FLAG_FAST_FP if options.get("fast_fp") else 0))

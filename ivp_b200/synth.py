@@ -59,6 +59,13 @@ def ensemble(name: str, N: int, offset: int = 0):
         y0[:, 0] = 1e4 * (1.0 + 0.1 * (2.0 * u[:, 0] - 1.0))
         par = np.tile(np.array([[0.04, 1e4, 3e7]]), (N, 1))
         return "robertson", y0, par, 0.0, 1e8
+    if name == "robertson_dae":  # Robertson as an index-1 DAE (mass matrix diag(1, 1, 0)), x + y + z = 1
+        u = uniform(N, 1, offset=offset)
+        y0 = np.zeros((N, 3))
+        y0[:, 0] = 1.0 - 0.2 * u[:, 0]
+        y0[:, 2] = 1.0 - y0[:, 0]
+        par = np.tile(np.array([[0.04, 1e4, 3e7]]), (N, 1))
+        return "robertson_dae", y0, par, 0.0, 1e8
     if name == "vdp_stiff":      # cfg 5: mu = 1000
         u = uniform(N, 2, offset=offset)
         y0 = np.stack([2.0 + (u[:, 0] - 0.5), u[:, 1] - 0.5], axis=1)

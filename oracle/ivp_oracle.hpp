@@ -120,6 +120,9 @@ struct StepCfg {
   bool has_first_step = false; double first_step = 0.0;
   bool has_min_step = false;  double min_step = 0.0;
   size_t max_steps = std::numeric_limits<size_t>::max();
+  // RADAU only (solve_ivp.rs:246-258): Options.mass_storage == Full, Options.nind1..3 (< 0 => None)
+  bool mass_full = false;
+  long nind1 = -1, nind2 = -1, nind3 = -1;
 };
 
 // ======================================================================================
@@ -823,6 +826,8 @@ struct Options {
   bool has_max_step = false; double max_step = 0.0;
   bool has_min_step = false; double min_step = 0.0;
   bool dense_output = false;
+  bool mass_full = false;                  // options.rs:109-112 (Identity | Full)
+  long nind1 = -1, nind2 = -1, nind3 = -1; // options.rs:114-122 (None => -1)
 };
 
 inline size_t coeffs_per_state(Method m) {   // options.rs:34-43
@@ -878,6 +883,7 @@ Solution solve_ivp(const F& f, double x0, double xend, const std::vector<double>
   cfg.has_first_step = o.has_first_step; cfg.first_step = o.first_step;
   cfg.has_min_step = o.has_min_step; cfg.min_step = o.min_step;
   cfg.max_steps = o.has_max_steps ? o.max_steps : std::numeric_limits<size_t>::max();
+  cfg.mass_full = o.mass_full; cfg.nind1 = o.nind1; cfg.nind2 = o.nind2; cfg.nind3 = o.nind3;
   IntegrationResult R;
   switch (o.method) {
     case Method::RK4: {

@@ -20,6 +20,8 @@ struct ProblemBase {
   }
   static constexpr bool HAS_JAC = false;
   void jac(double, const double*, double*) const {}
+  static constexpr bool HAS_MASS = false;  // IVP::mass (src/ivp.rs:109-120): constant, row-major n x n
+  void mass(double*) const {}
 };
 
 struct Decay : ProblemBase<Decay, 1, 1, 0> {          // examples/exponential_decay.rs:10-12
@@ -119,6 +121,47 @@ struct Cannon : ProblemBase<Cannon, 2, 0, 1> {        // tests/test_ivp.py:153-1
   void ode(double, const double* y, double* d) const { d[0] = y[1]; d[1] = -9.80665; }
   void events(double, const double* y, double* g) const { g[0] = y[0]; }
   EventConfig default_event_config(int) const { EventConfig c; c.terminal_count = 1; c.direction = Direction::Negative; return c; }
+};
+
+// Robertson as an index-1 DAE (Hairer & Wanner II, the classic RADAU5 mass-matrix demonstration): the third
+// equation becomes the conservation law.  Exercises radau.rs:375-386 (E1/E2 with M), :525-539 (M F in the Newton
+// right-hand side) and :626-634 (M in the error estimate).
+struct RobertsonDae : ProblemBase<RobertsonDae, 3, 3, 0> {
+  void ode(double, const double* s, double* d) const {
+    const double x = s[0], y = s[1], z = s[2];
+    d[0] = -p[0] * x + p[1] * y * z;
+    d[1] = p[0] * x - p[1] * y * z - p[2] * y * y;
+    d[2] = x + y + z - 1.0;
+  }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* s, double* J) const {
+    const double y = s[1], z = s[2];
+    J[0] = -p[0];  J[1] = p[1] * z;                       J[2] = p[1] * y;
+    J[3] = p[0];   J[4] = -p[1] * z - 2.0 * p[2] * y;     J[5] = -p[1] * y;
+    J[6] = 1.0;    J[7] = 1.0;                            J[8] = 1.0;
+  }
+  static constexpr bool HAS_MASS = true;
+  void mass(double* M) const { for (int k = 0; k < 9; ++k) M[k] = 0.0; M[0] = 1.0; M[4] = 1.0; }
+};
+// M y' = p0 * A y with a full, invertible, non-symmetric constant M: every entry of the mass loops is exercised.
+struct MassLinear3 : ProblemBase<MassLinear3, 3, 1, 0> {
+  void ode(double, const double* y, double* d) const {
+    d[0] = p[0] * (-2.0 * y[0] + 1.0 * y[1]);
+    d[1] = p[0] * (1.0 * y[0] - 2.0 * y[1] + 1.0 * y[2]);
+    d[2] = p[0] * (1.0 * y[1] - 2.0 * y[2]);
+  }
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double*, double* J) const {
+    J[0] = -2.0 * p[0]; J[1] = p[0];        J[2] = 0.0;
+    J[3] = p[0];        J[4] = -2.0 * p[0]; J[5] = p[0];
+    J[6] = 0.0;         J[7] = p[0];        J[8] = -2.0 * p[0];
+  }
+  static constexpr bool HAS_MASS = true;
+  void mass(double* M) const {
+    M[0] = 2.0; M[1] = 0.5;  M[2] = 0.0;
+    M[3] = 0.25; M[4] = 1.5; M[5] = -0.5;
+    M[6] = 0.0; M[7] = 0.75; M[8] = 3.0;
+  }
 };
 
 struct Linear100 : ProblemBase<Linear100, 100, 0, 0> {  // benches/benchmark.py:39-41,137-146

@@ -76,4 +76,19 @@ struct Linear2 : ProblemBase<Linear2, 2, 0, 0> {
   void jac(double, const double*, double* J) const { J[0] = -1.0; J[1] = -5.0; J[2] = 1.0; J[3] = 1.0; }
 };
 
+// M y' = p0 A y, n = 4, tridiagonal A and a full constant M (the shared-memory matrix variant of the device kernels)
+struct MassLinear4 : ProblemBase<MassLinear4, 4, 1, 0> {
+  void ode(double, const double* y, double* d) const {
+    d[0] = p[0] * (-2.0 * y[0] + y[1]);
+    d[1] = p[0] * (y[0] - 2.0 * y[1] + y[2]);
+    d[2] = p[0] * (y[1] - 2.0 * y[2] + y[3]);
+    d[3] = p[0] * (y[2] - 2.0 * y[3]);
+  }
+  static constexpr bool HAS_MASS = true;
+  void mass(double* M) const {
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) M[i * 4 + j] = (i == j) ? 2.0 + 0.5 * (double)i : 0.25 / (1.0 + (double)(i > j ? i - j : j - i)) * ((i + j) % 2 ? -1.0 : 1.0);
+  }
+};
+
 }  // namespace oracle

@@ -37,6 +37,8 @@ pub struct ivpb_options {
     pub jac_mode: i32,
     pub flags: i32,
     pub max_segments: i32,
+    pub mass_storage: i32,
+    pub nind1: i32, pub nind2: i32, pub nind3: i32,
 }
 
 #[repr(C)]

@@ -66,13 +66,16 @@ pub struct Options {
     pub min_step: Option<Float>, pub dense_output: bool,
     pub event_config: Option<Vec<EventConfig>>, pub max_events: usize, pub max_out: usize,
     pub analytic_jac: bool, pub strict_fp: bool, pub max_segments: usize,
+    /// ivp `Options.mass_storage` (Identity | Full) and `nind1..3` (src/solve/options.rs:105-122); RADAU only.
+    pub mass_full: bool, pub nind1: Option<usize>, pub nind2: Option<usize>, pub nind3: Option<usize>,
 }
 impl Options { pub fn builder() -> OptionsBuilder { OptionsBuilder(Options::default()) } }
 impl Default for Options {
     fn default() -> Self {
         Options { method: Method::DOPRI5, rtol: 1e-3.into(), atol: 1e-6.into(), max_steps: None, t_eval: None,
                   first_step: None, max_step: None, min_step: None, dense_output: false, event_config: None,
-                  max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false, max_segments: 4096 }
+                  max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false, max_segments: 4096,
+                  mass_full: false, nind1: None, nind2: None, nind3: None }
     }
 }
 pub struct OptionsBuilder(Options);
@@ -124,10 +127,10 @@ impl Problem {
         if unsafe { sys::ivpb_builtin_problem(ctx.raw, id, &mut n, &mut p, &mut ne) } != sys::IVPB_OK { return Err(Error::Config(last_error(ctx.raw))); }
         Ok(Problem { handle: id, n: n as usize, p: p as usize, n_events: ne as usize })
     }
-    pub fn from_cuda_source(ctx: &Context, src: &str, n: usize, p: usize, n_events: usize, has_jac: bool) -> Result<Self, Error> {
+    pub fn from_cuda_source(ctx: &Context, src: &str, n: usize, p: usize, n_events: usize, has_jac: bool, has_mass: bool) -> Result<Self, Error> {
         let c = CString::new(src).map_err(|e| Error::Config(e.to_string()))?;
         let mut h = -1;
-        let rc = unsafe { sys::ivpb_nvrtc_problem(ctx.raw, c.as_ptr(), n as i32, p as i32, n_events as i32, has_jac as i32, &mut h) };
+        let rc = unsafe { sys::ivpb_nvrtc_problem(ctx.raw, c.as_ptr(), n as i32, p as i32, n_events as i32, (has_jac as i32) | ((has_mass as i32) << 1), &mut h) };
         if rc != sys::IVPB_OK { return Err(Error::Config(last_error(ctx.raw))); }
         Ok(Problem { handle: h, n, p, n_events })
     }
@@ -178,6 +181,9 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         max_events: if ne > 0 { options.max_events as i32 } else { 0 }, max_out: options.max_out as i32,
         jac_mode: options.analytic_jac as i32, flags: if options.strict_fp { sys::IVPB_FLAG_STRICT_FP } else { 0 },
         max_segments: if options.dense_output { options.max_segments as i32 } else { 0 },
+        mass_storage: options.mass_full as i32,
+        nind1: options.nind1.map_or(-1, |k| k as i32), nind2: options.nind2.map_or(-1, |k| k as i32),
+        nind3: options.nind3.map_or(-1, |k| k as i32),
     };
     let cap = te.map_or(options.max_out, |t| t.len() + 1);
     let me = o.max_events as usize;
