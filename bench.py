@@ -46,6 +46,7 @@ WORKLOADS = {
     "cr3bp_dop853_teval": ("cr3bp", "DOP853", 1e-10, 1e-12, 48, 6),          # configs[2]: 101 t_eval samples
     "cr3bp_dop853": ("cr3bp", "DOP853", 1e-10, 1e-12, 48, 6),                # same, final state only (A/B)
     "ball_dopri5_events": ("ball", "DOPRI5", 1e-8, 1e-10, 4, 2),             # configs[3]
+    "ball_bounce_dopri5": ("ball_bounce", "DOPRI5", 1e-8, 1e-10, 4, 2),       # SolOut hook, bounces inside the solve
     "robertson_radau": ("robertson", "RADAU", 1e-6, 1e-6, 13, 3),            # configs[4]
     "robertson_bdf": ("robertson", "BDF", 1e-6, 1e-6, 13, 3),
     "robertson_dae_radau": ("robertson_dae", "RADAU", 1e-6, 1e-10, 14, 3),   # M y' = f, M = diag(1, 1, 0)
@@ -56,7 +57,7 @@ WORKLOADS = {
     "medakzo_bdf": ("medakzo", "BDF", 1e-5, 1e-7, 900, 64),
 }
 N_T_EVAL = {"cr3bp_dop853_teval": 101}
-EXTRA_OPTIONS = {"robertson_dae_radau": {"mass_storage": "Full"}}
+EXTRA_OPTIONS = {"robertson_dae_radau": {"mass_storage": "Full"}, "ball_bounce_dopri5": {"user_solout": True}}
 NOMINAL_FP64_TFLOPS = 37.0   # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 

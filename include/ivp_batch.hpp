@@ -115,6 +115,9 @@ struct Options {
   enum class MatrixStorage { Identity, Full };
   MatrixStorage mass_storage = MatrixStorage::Identity;
   std::optional<size_t> nind1, nind2, nind3;
+  // the problem's own SolOut hook (src/solout.rs:55-63) instead of DefaultSolOut: the reference's low-level
+  // Method::solve(.., Some(&mut solout)) call.  Samples the hook emits come back in Solution::t / y.
+  bool user_solout = false;
   // ---- batched-solve additions (no reference equivalent) ----
   std::optional<std::vector<EventConfig>> event_config;   // overrides the problem's IVP::event_config
   int max_events = 8;        // event hits stored per event function and trajectory
@@ -139,6 +142,7 @@ class OptionsBuilder {
   OptionsBuilder& dense_output(bool b) { o_.dense_output = b; return *this; }
   OptionsBuilder& max_segments(int n) { o_.max_segments = n; return *this; }
   OptionsBuilder& mass_storage(Options::MatrixStorage s) { o_.mass_storage = s; return *this; }
+  OptionsBuilder& user_solout(bool b) { o_.user_solout = b; return *this; }
   OptionsBuilder& nind1(size_t k) { o_.nind1 = k; return *this; }
   OptionsBuilder& nind2(size_t k) { o_.nind2 = k; return *this; }
   OptionsBuilder& nind3(size_t k) { o_.nind3 = k; return *this; }
@@ -247,7 +251,7 @@ class Problem {
   static Problem builtin(const std::string& name) {
     static const char* names[] = {"decay", "vdp_eps", "vdp_mu", "lorenz", "cr3bp", "bouncing_ball", "robertson",
                                   "sho", "zero3", "exp2", "rational", "cannon", "linear100", "medakzo64",
-                                  "robertson_dae", "mass_linear3"};
+                                  "robertson_dae", "mass_linear3", "ball_bounce"};
     static_assert(sizeof(names) / sizeof(names[0]) == IVPB_P_BUILTIN_COUNT, "one name per ivpb_builtin id");
     for (int i = 0; i < IVPB_P_BUILTIN_COUNT; ++i)
       if (name == names[i]) {
@@ -319,6 +323,7 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
   o.dense_output = options.dense_output;
   o.max_segments = options.dense_output ? options.max_segments : 0;
   o.mass_storage = options.mass_storage == Options::MatrixStorage::Full ? 1 : 0;
+  o.user_solout = options.user_solout ? 1 : 0;
   o.nind1 = options.nind1 ? (int32_t)*options.nind1 : -1;
   o.nind2 = options.nind2 ? (int32_t)*options.nind2 : -1;
   o.nind3 = options.nind3 ? (int32_t)*options.nind3 : -1;

@@ -59,7 +59,11 @@ typedef enum {
   IVPB_P_ROBERTSON_DAE = 14, /* Robertson as an index-1 DAE: M = diag(1, 1, 0), third row x + y + z - 1 = 0;  n=3 p=3; needs
                                 mass_storage = 1 (RADAU).  Exercises src/methods/radau.rs:375-386,525-539,626-634 */
   IVPB_P_MASS_LINEAR3 = 15,  /* M y' = A y with a full (non-diagonal, invertible) constant M; n=3 p=1 (scales A); RADAU + mass */
-  IVPB_P_BUILTIN_COUNT = 16
+  IVPB_P_BALL_BOUNCE = 16,   /* bouncing ball that bounces INSIDE the solve: n=2 p=3 (g, drag, restitution); its own SolOut hook
+                                (user_solout = 1) finds each impact on the step interpolant, reverses and damps the velocity
+                                and returns ControlFlag::ModifiedSolution (src/solout.rs:18-29,73-78; the reference's
+                                examples/bouncing_ball.py:14-36 restarts solve_ivp from the host instead) */
+  IVPB_P_BUILTIN_COUNT = 17
 } ivpb_builtin;
 
 /* Mirrors `Options` (reference src/solve/options.rs:75-123) plus the per-event `EventConfig`
@@ -88,6 +92,10 @@ typedef struct {
   /* RADAU only (src/solve/solve_ivp.rs:246-258; every other method ignores them, like the reference): */
   int32_t mass_storage;        /* Options.mass_storage: 0 = Identity (default, y' = f), 1 = Full: M y' = f with the problem's
                                   constant mass matrix (IVP::mass, src/ivp.rs:109-120; device hook `mass` / `ivp_mass`) */
+  int32_t user_solout;         /* 1: the problem's own SolOut hook (`solout` / `ivp_solout`, src/solout.rs:55-63) replaces
+                                  DefaultSolOut -- the reference's low-level `Method::solve(.., Some(&mut solout))` call
+                                  (e.g. src/methods/dop853.rs:114-127): no t_eval / events / dense log; samples the hook emits
+                                  go to t_out / y_out (capacity max_out).  Explicit methods, n <= 32. */
   int32_t nind1, nind2, nind3; /* Options.nind1..3: index-1/2/3 variable counts of a DAE, < 0 => None
                                   (partition rules and Error::Config of src/methods/radau.rs:210-245) */
 } ivpb_options;
@@ -149,7 +157,10 @@ int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_e
 /* User problem in CUDA C, compiled with NVRTC together with the solver templates.  `cuda_src` must define
  *   __device__ void ivp_ode(double t, const double* y, const double* p, double* dydt);
  * and, if n_events > 0 / has_jac (bit 0: analytic Jacobian `ivp_jac`; bit 1: constant mass matrix
- * `__device__ void ivp_mass(const double* p, double* M)`, row-major n x n, IVP::mass of src/ivp.rs:109-120),
+ * `__device__ void ivp_mass(const double* p, double* M)`, row-major n x n, IVP::mass of src/ivp.rs:109-120; bit 2: own
+ * SolOut `template <class Interp, class Emit> __device__ int ivp_solout(double xold, double& x, double* y, const double* p,
+ * double* state, const Interp& dense, Emit& emit)` returning 0 Continue / 1 Interrupt / 2 ModifiedSolution, used when
+ * ivpb_options.user_solout = 1 -- dense.valid(), dense.eval(t, yi), emit(t, y), state = 4 doubles per trajectory),
  *   __device__ void ivp_events(double t, const double* y, const double* p, double* g);
  *   __device__ void ivp_jac(double t, const double* y, const double* p, double* J);  // row-major n x n
  * (the IVP trait, reference src/ivp.rs:27-121, with the parameter row made explicit). */

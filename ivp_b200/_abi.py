@@ -44,6 +44,7 @@ class IvpbOptions(C.Structure):
         ("flags", C.c_int32),
         ("max_segments", C.c_int32),
         ("mass_storage", C.c_int32),
+        ("user_solout", C.c_int32),
         ("nind1", C.c_int32),
         ("nind2", C.c_int32),
         ("nind3", C.c_int32),
@@ -171,6 +172,7 @@ class MarshalledOptions:
         if ms not in ("identity", "full"):
             raise ValueError("mass_storage must be 'Identity' or 'Full' (banded mass matrices are not supported)")
         o.mass_storage = int(ms == "full")
+        o.user_solout = int(bool(getattr(opts, "user_solout", False)))
         for fld in ("nind1", "nind2", "nind3"):
             v = getattr(opts, fld, None)
             setattr(o, fld, -1 if v is None else int(v))

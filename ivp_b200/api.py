@@ -25,6 +25,7 @@ _lib = None
 PROBLEMS = {
     "decay": 0, "vdp_eps": 1, "vdp_mu": 2, "lorenz": 3, "cr3bp": 4, "bouncing_ball": 5, "robertson": 6,
     "sho": 7, "zero3": 8, "exp2": 9, "rational": 10, "cannon": 11, "linear100": 12, "medakzo64": 13, "robertson_dae": 14, "mass_linear3": 15,
+    "ball_bounce": 16,
 }
 
 IVPB_FLAG_STRICT_FP = 1
@@ -110,10 +111,10 @@ class Problem:
 
     @staticmethod
     def from_cuda_source(src: str, n: int, p: int = 0, n_events: int = 0, has_jac: bool = False,
-                         has_mass: bool = False) -> "Problem":
+                         has_mass: bool = False, has_solout: bool = False) -> "Problem":
         """User problem: `src` defines `__device__ void ivp_ode(double t, const double* y, const double* p,
-        double* dydt)` (+ `ivp_events`, `ivp_jac`, `ivp_mass`), see include/ivpb.h."""
-        return Problem(-1, n, p, n_events, "user", cuda_src=src, has_jac=int(bool(has_jac)) | (2 if has_mass else 0))
+        double* dydt)` (+ `ivp_events`, `ivp_jac`, `ivp_mass`, `ivp_solout`), see include/ivpb.h."""
+        return Problem(-1, n, p, n_events, "user", cuda_src=src, has_jac=int(bool(has_jac)) | (2 if has_mass else 0) | (4 if has_solout else 0))
 
     def resolve(self, ctx: "Context") -> int:
         if self.cuda_src is None:

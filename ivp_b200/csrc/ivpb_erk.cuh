@@ -22,7 +22,7 @@
 
 namespace ivpb {
 
-enum { K_OUT = 1, K_EVENTS = 2 };   // kernel feature bits (template parameter FEAT)
+enum { K_OUT = 1, K_EVENTS = 2, K_USER = 4 };   // kernel feature bits (template parameter FEAT); K_USER: the problem's own SolOut
 
 // Multiply-add of the solver core.  Default build: an explicit fma, so the result does not depend on which
 // products a particular compiler run chooses to contract -- the static, work-queue and NVRTC instances of a
@@ -524,11 +524,39 @@ struct ErkTraj {
   int iasti, nonstiff, status;
   bool last, reject;
   Out so;
+  static constexpr bool USER = (FEAT & K_USER) != 0;
+  double ustate[USER ? Prob::NSTATE : 1];      // the user SolOut's own fields (Options.user_solout)
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
     x = tev;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = yev[i];
+  }
+  // What the user SolOut sees of the step (StepInterpolant, src/dense.rs:32-97) and of the output arrays
+  struct UserInterp {
+    const double (&c)[NC][N]; double xold, h; bool ok;
+    __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<METHOD, N>(t, yi, c, xold, h); }
+  };
+  struct UserEmit {
+    Out& so; const KArgs& a; i64 idx;
+    __device__ __forceinline__ void operator()(double t, const double* yv) { so.push(a, idx, t, yv); }
+  };
+  // The solver's callback slot (e.g. dop853.rs:246-268,596-624): DefaultSolOut, or the problem's own SolOut.
+  // Returns 0 Continue, 1 Interrupt (status set, (x, y) at the point to report), 2 ModifiedSolution (k1 re-evaluated).
+  __device__ __forceinline__ int callback(const KArgs& a, bool first, double xold, const double (&cont)[NC][N], double hstep) {
+    if constexpr (USER) {
+      const UserInterp ip{cont, xold, hstep, !first};
+      UserEmit em{so, a, idx};
+      const int fl = Prob::solout(xold, x, y, p, ustate, ip, em);
+      if (fl == 1) { status = ST_INTERRUPT; return 1; }
+      if (fl == 2) { L::ode(x, y, p, k1); nfev += 1; return 2; }
+      return 0;
+    } else {
+      double tev, yev[N];
+      if (so.solout(a, idx, p, first, xold, x, y, cont, hstep, xold, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return 1; }
+      return 0;
+    }
   }
   __device__ __forceinline__ double rt(const KArgs& a, int i) const { return L::rtol(a, i); }
   __device__ __forceinline__ double at(const KArgs& a, int i) const { return L::atol(a, i); }
@@ -591,8 +619,11 @@ struct ErkTraj {
       for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
-      double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if constexpr (USER) {
+#pragma unroll
+        for (int s = 0; s < Prob::NSTATE; ++s) ustate[s] = 0.0;
+      }
+      if (callback(a, true, x, cont, 0.0) == 1) return true;
     }
     return false;
   }
@@ -799,9 +830,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       for (int i = 0; i < N; ++i) { k1[i] = k[3][i]; y[i] = k[4][i]; }
       x = xph;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-        }
+        if (callback(a, false, xold, cont, h) == 1) return true;
       }
       if (last) { h = hnew; status = ST_SUCCESS; return true; }
       if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
@@ -950,9 +979,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       for (int i = 0; i < N; ++i) { k1[i] = k[1][i]; y[i] = y1[i]; }
       x = xph;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-        }
+        if (callback(a, false, xold, cont, h) == 1) return true;
       }
       if (last) { h = hnew; status = ST_SUCCESS; return true; }
       if (fabs(hnew) > fabs(h_max)) hnew = posneg * fabs(h_max);
@@ -1029,13 +1056,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
         y[i] = yt[i];
       }
       x += h;
+      int fl = 0;
       if constexpr (FEAT != 0) {
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-        }
+        fl = callback(a, false, xold, cont, h);
+        if (fl == 1) return true;
       }
+      if (fl != 2) {                     // rk23.rs:270-284: ModifiedSolution re-evaluated k1, every other flag reuses k4
 #pragma unroll
-      for (int i = 0; i < N; ++i) k1[i] = k4[i];
+        for (int i = 0; i < N; ++i) k1[i] = k4[i];
+      }
       h *= fmax(fmin(sfac, scale_max), scale_min);
       if (fabs(h) > hmax) h = hmax * posneg;
       if (x == xend) { status = ST_SUCCESS; return true; }
@@ -1075,9 +1104,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       for (int i = 0; i < N; ++i) { cont[2][i] = k1[i]; cont[3][i] = y[i]; }
     }
     if constexpr (FEAT != 0) {
-      if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-        status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-      }
+      if (callback(a, false, xold, cont, h) == 1) return true;
     }
     if (lst) { status = ST_SUCCESS; return true; }
     return false;

@@ -23,7 +23,7 @@
 extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, ivpb_pinfo* info) {
   using P = ivpb::IVPB_PROBLEM;
   if (info) {
-    info->n = P::N; info->p = P::P; info->nev = P::NEV; info->has_jac = (P::HAS_JAC ? 1 : 0) | (P::HAS_MASS ? 2 : 0);
+    info->n = P::N; info->p = P::P; info->nev = P::NEV; info->has_jac = (P::HAS_JAC ? 1 : 0) | (P::HAS_MASS ? 2 : 0) | (P::HAS_SOLOUT ? 4 : 0);
     for (int e = 0; e < 8; ++e) {
       info->ev_dir[e] = e < P::NEV ? P::default_dir(e) : 0;
       info->ev_term[e] = e < P::NEV ? (long long)P::default_term(e) : -1;

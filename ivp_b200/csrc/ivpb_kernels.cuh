@@ -30,6 +30,9 @@ __host__ inline const void* erk_lookup_feat(int feat) {
     case K_OUT | K_EVENTS:
       if constexpr (Prob::NEV > 0) return (const void*)&erk_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
       else return nullptr;
+    case K_USER:                         // Options.user_solout: the problem's own SolOut
+      if constexpr (Prob::HAS_SOLOUT) return (const void*)&erk_kernel<Prob, METHOD, K_USER>;
+      else return nullptr;
     default: return nullptr;
   }
 }

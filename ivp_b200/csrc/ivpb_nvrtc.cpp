@@ -105,6 +105,12 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
     s += "  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { ivp_ode(t, y, p, d); }\n";
   if (up.n_events > 0)
     s += "  static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { ivp_events(t, y, p, g); }\n";
+  if (up.has_jac & 4) {
+    s += "  static constexpr bool HAS_SOLOUT = true;\n";
+    s += "  template <class Interp, class Emit>\n"
+         "  static __device__ __forceinline__ int solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit) {\n"
+         "    return ivp_solout(xold, x, y, p, state, dense, emit);\n  }\n";
+  }
   if (up.has_jac & 2) {
     s += "  static constexpr bool HAS_MASS = true;\n";
     s += "  static __device__ __forceinline__ void mass(const double* p, double* M) { ivp_mass(p, M); }\n";

@@ -98,6 +98,36 @@ struct PMassLinear3 : ProblemDefaults<3, 1, 0> {
   }
 };
 
+// The bouncing ball without host round trips (oracle/problems.hpp BallBounce; reference examples/bouncing_ball.py:14-36
+// restarts solve_ivp after every terminal event, src/solout.rs:18-29 describes the in-solver alternative used here).
+struct PBallBounce : ProblemDefaults<2, 3, 0> {
+  IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
+    const double vy = s[1];
+    d[0] = vy;
+    d[1] = -p[0] - p[1] * vy * fabs(vy);
+  }
+  static constexpr bool HAS_SOLOUT = true;
+  template <class Interp, class Emit>
+  IVPB_DEV int solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit) {
+    if (!dense.valid()) { emit(x, y); return 0; }
+    if (!(y[0] < 0.0)) return 0;
+    double lo = xold, hi = x, yi[2];
+    for (int it = 0; it < 60; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      dense.eval(mid, yi);
+      if (yi[0] < 0.0) hi = mid; else lo = mid;
+    }
+    dense.eval(hi, yi);
+    x = hi;
+    y[0] = 0.0;
+    y[1] = -p[2] * yi[1];
+    state[0] += 1.0; state[1] = x;
+    emit(x, y);
+    if (fabs(y[1]) < 0.1) return 1;
+    return 2;
+  }
+};
+
 struct PCr3bp : ProblemDefaults<6, 1, 0> {      // reference examples/cr3bp.rs:24-35
   IVPB_DEV void ode(double, const double* s, const double* p, double* d) {
     const double mu = p[0];

@@ -18,6 +18,15 @@ struct ProblemDefaults {
   IVPB_DEV void jac(double, const double*, const double*, double*) {}
   // IVP::mass (src/ivp.rs:109-120): constant mass matrix of M y' = f, row-major n x n; used by RADAU when
   // Options.mass_storage = Full (src/methods/radau.rs:283,358-359)
+  // The problem's own SolOut (src/solout.rs:55-63) for Options.user_solout = 1:
+  //   template <class Interp, class Emit>
+  //   static __device__ int solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit);
+  // returns 0 Continue | 1 Interrupt | 2 ModifiedSolution (ControlFlag, src/solout.rs:73-78; XOut == Continue on the
+  // device, where the step interpolant is always built).  `state`: NSTATE doubles per trajectory, zero at the start (the
+  // SolOut struct's fields); dense.valid() is false at the initial call; dense.eval(t, yi) interpolates inside the step;
+  // emit(t, y) appends a sample to t_out / y_out.
+  static constexpr bool HAS_SOLOUT = false;
+  static constexpr int NSTATE = 4;
   static constexpr bool HAS_MASS = false;
   IVPB_DEV void mass(const double*, double*) {}
   // IVP::event_config default (src/ivp.rs:51-53 -> EventConfig::new: All, non-terminal)

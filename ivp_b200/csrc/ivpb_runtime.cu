@@ -32,13 +32,13 @@ typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* sme
   extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*, int*);       \
   extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
-DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64) DECL(robertson_dae) DECL(mass_linear3)
+DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64) DECL(robertson_dae) DECL(mass_linear3) DECL(ball_bounce)
 #undef DECL
 #define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag}
 static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
-    ROW(robertson_dae), ROW(mass_linear3)};
+    ROW(robertson_dae), ROW(mass_linear3), ROW(ball_bounce)};
 #undef ROW
 // dense-output evaluation kernels (ivpb_dense.cu)
 extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int cap, const int* seg_n, const double* seg_x,
@@ -52,7 +52,7 @@ extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const d
 static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
-    ROW(robertson_dae), ROW(mass_linear3)};
+    ROW(robertson_dae), ROW(mass_linear3), ROW(ball_bounce)};
 #undef ROW
 
 namespace {
@@ -221,6 +221,13 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1: the warp-cooperative implicit kernels (n > 8) use the finite-difference Jacobian only");
   if (o->jac_mode == 1 && !(pi.has_jac & 1) && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
+  if (o->user_solout) {
+    // Method::solve(.., Some(&mut user_solout)) (e.g. dop853.rs:114-127): DefaultSolOut's services do not exist on this path
+    if (!(pi.has_jac & 4)) return fail(ctx, IVPB_ERR_CONFIG, "user_solout = 1, but the problem defines no SolOut hook (solout / ivp_solout)");
+    if (o->method == IVPB_RADAU || o->method == IVPB_BDF) return fail(ctx, IVPB_ERR_CONFIG, "user SolOut hooks are implemented for the explicit methods");
+    if (pi.n > ivpb::MAX_N) return fail(ctx, IVPB_ERR_CONFIG, "user SolOut hooks need the thread-per-trajectory kernels (n <= 32)");
+    if (o->has_t_eval || o->dense_output) return fail(ctx, IVPB_ERR_CONFIG, "user_solout = 1: t_eval / dense_output belong to DefaultSolOut; emit samples from the hook instead");
+  }
   if (o->method == IVPB_RADAU) {
     // Options.mass_storage / nind1..3 reach RADAU only (solve_ivp.rs:246-258); DAE partition rules of radau.rs:210-245
     const bool has_mass = (pi.has_jac & 2) != 0;
@@ -396,7 +403,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   }
   const bool want_out = o->has_t_eval || a.out_cap > 0 || a.seg_cap > 0;
   int feat = 0;
-  if (pi.nev > 0) feat = 3;            // K_OUT | K_EVENTS: events always run (they can terminate)
+  if (o->user_solout) feat = 4;        // K_USER: the problem's own SolOut replaces DefaultSolOut
+  else if (pi.nev > 0) feat = 3;       // K_OUT | K_EVENTS: events always run (they can terminate)
   else if (want_out) feat = 1;         // K_OUT
 
   CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));

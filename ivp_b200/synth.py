@@ -59,6 +59,11 @@ def ensemble(name: str, N: int, offset: int = 0):
         y0[:, 0] = 1e4 * (1.0 + 0.1 * (2.0 * u[:, 0] - 1.0))
         par = np.tile(np.array([[0.04, 1e4, 3e7]]), (N, 1))
         return "robertson", y0, par, 0.0, 1e8
+    if name == "ball_bounce":    # cfg 4's ball, bouncing inside the solve (restitution ~ U(0.6, 0.9))
+        u = uniform(N, 4, offset=offset)
+        y0 = np.stack([1.0 + 19.0 * u[:, 0], -5.0 + 15.0 * u[:, 1]], axis=1)
+        par = np.stack([np.full(N, 9.81), 0.05 * u[:, 2], 0.6 + 0.3 * u[:, 3]], axis=1)
+        return "ball_bounce", y0, par, 0.0, 15.0
     if name == "robertson_dae":  # Robertson as an index-1 DAE (mass matrix diag(1, 1, 0)), x + y + z = 1
         u = uniform(N, 1, offset=offset)
         y0 = np.zeros((N, 3))

@@ -120,6 +120,7 @@ class Options:
     max_out: int = 0             # step-mode capacity of Solution.t/.y per trajectory (0 = final state only)
     jac_mode: int = 0            # 0 finite differences (ivp.rs:67-107), 1 analytic
     flags: int = 0
+    user_solout: bool = False    # the problem's own SolOut hook replaces DefaultSolOut (src/solout.rs:55-63; include/ivpb.h)
     max_segments: int = 0        # dense_output: interpolant segments kept per trajectory (one per accepted step)
 
     def __post_init__(self):

@@ -40,7 +40,7 @@ struct EventConfig {            // src/solve/event.rs:5-27
   long terminal_count = -1;     // -1 == None
 };
 // src/solout.rs:73-78 (DefaultSolOut only ever returns Continue / Interrupt)
-enum class Flag { Continue, Interrupt };
+enum class Flag { Continue, Interrupt, ModifiedSolution };   // src/solout.rs:73-78 (XOut only gates the interpolant: == Continue here)
 
 struct ConfigError : std::runtime_error { using std::runtime_error::runtime_error; };
 
@@ -172,9 +172,11 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   else { R.nfev += 1; h = hinit(f, x, y, posneg, k1, k2, y1, 8, h_max, atol, rtol); }
 
   if (so) {
-    if (so->solout(xold, x, y, nullptr) == Flag::Interrupt) {
+    const Flag fl0 = so->solout(xold, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) {
       R.h = h; R.status = Status::UserInterrupt; return R;
     }
+    if (fl0 == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // e.g. dop853.rs:258-262
   }
 
   for (;;) {
@@ -305,7 +307,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
 
       if (so) {
         StepInterp ip{cont.data(), cont.size(), xold, h, &interpolate};
-        if (so->solout(xold, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        const Flag fl = so->solout(xold, x, y, &ip);
+        if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        if (fl == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // dop853.rs:613-617, dopri5.rs:422-426
       }
       if (last) { h = hnew; R.status = Status::Success; break; }
       if (std::fabs(hnew) > std::fabs(h_max)) hnew = posneg * std::fabs(h_max);
@@ -379,9 +383,11 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   else { R.nfev += 1; h = hinit(f, x, y, posneg, k1, k2, k3, 5, h_max, atol, rtol); }
 
   if (so) {
-    if (so->solout(xold, x, y, nullptr) == Flag::Interrupt) {
+    const Flag fl0 = so->solout(xold, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) {
       R.h = h; R.status = Status::UserInterrupt; return R;
     }
+    if (fl0 == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // e.g. dop853.rs:258-262
   }
 
   for (;;) {
@@ -460,7 +466,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
       k1 = k2; y = y1; xold = x; x = xph;
       if (so) {
         StepInterp ip{cont.data(), cont.size(), xold, h, &interpolate};
-        if (so->solout(xold, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        const Flag fl = so->solout(xold, x, y, &ip);
+        if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        if (fl == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // dop853.rs:613-617, dopri5.rs:422-426
       }
       if (last) { h = hnew; R.status = Status::Success; break; }
       if (std::fabs(hnew) > std::fabs(h_max)) hnew = posneg * std::fabs(h_max);
@@ -516,9 +524,11 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   if (cfg.has_first_step) h = std::fabs(cfg.first_step) * posneg;
   else { R.nfev += 1; h = hinit(f, x, y, posneg, k1, k2, k3, 3, hmax, atol, rtol); }
   if (so) {
-    if (so->solout(xold, x, y, nullptr) == Flag::Interrupt) {
+    const Flag fl0 = so->solout(xold, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) {
       R.h = h; R.status = Status::UserInterrupt; return R;
     }
+    if (fl0 == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // e.g. dop853.rs:258-262
   }
   for (;;) {
     if (R.nstep >= nmax) { R.status = Status::NeedLargerNMax; break; }
@@ -548,8 +558,10 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
           cont[3 * n + i] = d31 * k1[i] + d32 * k2[i] + d33 * k3[i] + d34 * k4[i];
         }
         StepInterp ip{cont.data(), cont.size(), xold, h, &interpolate};
-        if (so->solout(xold, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
-        k1 = k4;  // rk23.rs:276-284 (only inside the solout branch)
+        const Flag fl = so->solout(xold, x, y, &ip);
+        if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        if (fl == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // rk23.rs:270-275
+        else k1 = k4;  // rk23.rs:276-284 (only inside the solout branch)
       }
       h *= std::fmax(std::fmin(safe * std::pow(err, error_exponent), scale_max), scale_min);
       if (std::fabs(h) > hmax) h = hmax * posneg;
@@ -597,9 +609,11 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   double xold = x;
   f.ode(x, y.data(), k1.data());   // not counted (rk4.rs:116)
   if (so) {
-    if (so->solout(xold, x, y, nullptr) == Flag::Interrupt) {
+    const Flag fl0 = so->solout(xold, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) {
       R.h = h; R.status = Status::UserInterrupt; return R;
     }
+    if (fl0 == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // e.g. dop853.rs:258-262
   }
   for (;;) {
     if (R.nstep >= nmax) { R.status = Status::NeedLargerNMax; break; }
@@ -623,7 +637,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
         cont[i] = yt[i]; cont[n + i] = k4[i]; cont[2 * n + i] = k1[i]; cont[3 * n + i] = y[i];
       }
       StepInterp ip{cont.data(), cont.size(), xold, h, &interpolate};
-      if (so->solout(xold, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+      const Flag fl = so->solout(xold, x, y, &ip);
+      if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+      if (fl == Flag::ModifiedSolution) { f.ode(x, y.data(), k1.data()); R.nfev += 1; }   // rk4.rs:206-210
     }
     if (last) break;
   }
@@ -651,6 +667,35 @@ struct Solution {
 };
 
 inline InterpFn interp_fn(Method m);
+
+// ======================================================================================
+// A problem's own SolOut (src/solout.rs:55-63) behind the solvers' callback slot.  The problem supplies
+//   int solout(xold, x&, y*, state*, interp, emit)  ->  0 Continue | 1 Interrupt | 2 ModifiedSolution
+// `state` is the SolOut struct's own fields (NSTATE doubles, zero at the start), `interp.valid()` is false at the initial
+// call (interpolant == None), `emit(t, y)` appends a sample to Solution.t / .y.
+template <class F>
+struct UserSolOut {
+  const F& f; size_t n;
+  std::vector<double> t, y, state;
+  double x_last = 0.0; std::vector<double> y_last;
+  UserSolOut(const F& f_, size_t n_) : f(f_), n(n_), state(F::NSTATE, 0.0) {}
+  struct Interp {
+    const StepInterp* ip; size_t n;
+    bool valid() const { return ip != nullptr; }
+    void eval(double tt, double* yi) const { ip->interpolate(tt, yi, n); }
+  };
+  struct Emit {
+    UserSolOut* self;
+    void operator()(double tt, const double* yy) { self->t.push_back(tt); self->y.insert(self->y.end(), yy, yy + self->n); }
+  };
+  Flag solout(double xold, double& x, std::vector<double>& yv, const StepInterp* ip) {
+    Interp in{ip, n};
+    Emit em{this};
+    const int fl = f.solout(xold, x, yv.data(), state.data(), in, em);
+    x_last = x; y_last = yv;
+    return fl == 1 ? Flag::Interrupt : (fl == 2 ? Flag::ModifiedSolution : Flag::Continue);
+  }
+};
 
 // ======================================================================================
 // DefaultSolOut -- src/solve/solout.rs:15-432
@@ -826,6 +871,7 @@ struct Options {
   bool has_max_step = false; double max_step = 0.0;
   bool has_min_step = false; double min_step = 0.0;
   bool dense_output = false;
+  bool user_solout = false;                // batch ABI: the problem's own SolOut replaces DefaultSolOut (Method::solve, e.g. dop853.rs:114-127)
   bool mass_full = false;                  // options.rs:109-112 (Identity | Full)
   long nind1 = -1, nind2 = -1, nind3 = -1; // options.rs:114-122 (None => -1)
 };
@@ -877,7 +923,6 @@ Solution solve_ivp(const F& f, double x0, double xend, const std::vector<double>
     S.has_dense = o.dense_output;
     return S;
   }
-  DefaultSolOut<F> so(f, o.has_t_eval, o.t_eval, o.dense_output, o.has_first_step, o.first_step, x0, y0.size());
   StepCfg cfg;
   cfg.has_max_step = o.has_max_step; cfg.max_step = o.max_step;
   cfg.has_first_step = o.has_first_step; cfg.first_step = o.first_step;
@@ -885,6 +930,27 @@ Solution solve_ivp(const F& f, double x0, double xend, const std::vector<double>
   cfg.max_steps = o.has_max_steps ? o.max_steps : std::numeric_limits<size_t>::max();
   cfg.mass_full = o.mass_full; cfg.nind1 = o.nind1; cfg.nind2 = o.nind2; cfg.nind3 = o.nind3;
   IntegrationResult R;
+  if constexpr (F::HAS_SOLOUT) {
+    if (o.user_solout) {
+      // The low-level entry `Method::solve(f, x0, y0, xend, rtol, atol, Some(&mut user_solout))` (dop853.rs:114-127,
+      // dopri5.rs:122-135, rk23.rs:81-94, rk4.rs:64-77) with the problem's own SolOut (src/solout.rs:55-63)
+      UserSolOut<F> us(f, y0.size());
+      switch (o.method) {
+        case Method::RK4: R = rk4::solve(f, x0, y0, xend, o.has_first_step ? o.first_step : (xend - x0) / 100.0, cfg, &us); break;
+        case Method::RK23: R = rk23::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
+        case Method::DOPRI5: R = dopri5::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
+        case Method::DOP853: R = dop853::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
+        default: throw ConfigError("user SolOut hooks are implemented for the explicit methods");
+      }
+      S.t = std::move(us.t); S.y = std::move(us.y);
+      S.nfev = R.nfev; S.nstep = R.nstep; S.naccpt = R.naccpt; S.nrejct = R.nrejct;
+      S.status = R.status; S.h_next = R.h;
+      S.x_last = us.x_last; S.y_last = std::move(us.y_last);
+      return S;
+    }
+  }
+  if (o.user_solout) throw ConfigError("user_solout = 1, but the problem defines no SolOut hook");
+  DefaultSolOut<F> so(f, o.has_t_eval, o.t_eval, o.dense_output, o.has_first_step, o.first_step, x0, y0.size());
   switch (o.method) {
     case Method::RK4: {
       double h = o.has_first_step ? o.first_step : (xend - x0) / 100.0;   // :185

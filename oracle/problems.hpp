@@ -20,6 +20,8 @@ struct ProblemBase {
   }
   static constexpr bool HAS_JAC = false;
   void jac(double, const double*, double*) const {}
+  static constexpr bool HAS_SOLOUT = false;   // the problem's own SolOut (src/solout.rs:55-63), see UserSolOut
+  static constexpr int NSTATE = 4;
   static constexpr bool HAS_MASS = false;  // IVP::mass (src/ivp.rs:109-120): constant, row-major n x n
   void mass(double*) const {}
 };
@@ -79,6 +81,38 @@ struct Ball : ProblemBase<Ball, 2, 2, 1> {            // examples/bouncing_ball.
   }
   void events(double, const double* s, double* g) const { g[0] = s[0]; }
   EventConfig default_event_config(int) const { EventConfig c; c.terminal_count = 1; c.direction = Direction::Negative; return c; }
+};
+// The bouncing ball WITHOUT host round trips (reference examples/bouncing_ball.py:14-36 restarts solve_ivp after every
+// terminal event; src/solout.rs:18-29 offers the in-solver alternative): a SolOut that finds the impact inside the step
+// with the interpolant, moves (x, y) to the impact with the velocity reversed and damped, and returns ModifiedSolution.
+// p = (g, drag, restitution).  state[0] = bounces so far, state[1] = time of the last one.  Every impact is emitted.
+struct BallBounce : ProblemBase<BallBounce, 2, 3, 0> {
+  void ode(double, const double* s, double* d) const {
+    const double vy = s[1];
+    d[0] = vy;
+    d[1] = -p[0] - p[1] * vy * std::fabs(vy);
+  }
+  static constexpr bool HAS_SOLOUT = true;
+  template <class Interp, class Emit>
+  int solout(double xold, double& x, double* y, double* state, const Interp& dense, Emit& emit) const {
+    if (!dense.valid()) { emit(x, y); return 0; }             // initial call: record the start
+    if (!(y[0] < 0.0)) return 0;                               // still above the ground at the end of the step
+    // impact inside (xold, x]: bisection on the step interpolant, 60 halvings (deterministic, direction-free)
+    double lo = xold, hi = x, yi[2];
+    for (int it = 0; it < 60; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      dense.eval(mid, yi);
+      if (yi[0] < 0.0) hi = mid; else lo = mid;
+    }
+    dense.eval(hi, yi);
+    x = hi;
+    y[0] = 0.0;
+    y[1] = -p[2] * yi[1];
+    state[0] += 1.0; state[1] = x;
+    emit(x, y);
+    if (std::fabs(y[1]) < 0.1) return 1;                       // bouncing_ball.py:33-34: too slow to matter -> stop
+    return 2;
+  }
 };
 struct Robertson : ProblemBase<Robertson, 3, 3, 0> {  // tests/test_stiff.py:104-110
   void ode(double, const double* s, double* d) const {

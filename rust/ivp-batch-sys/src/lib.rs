@@ -38,6 +38,7 @@ pub struct ivpb_options {
     pub flags: i32,
     pub max_segments: i32,
     pub mass_storage: i32,
+    pub user_solout: i32,
     pub nind1: i32, pub nind2: i32, pub nind3: i32,
 }
 

@@ -67,6 +67,8 @@ pub struct Options {
     pub event_config: Option<Vec<EventConfig>>, pub max_events: usize, pub max_out: usize,
     pub analytic_jac: bool, pub strict_fp: bool, pub max_segments: usize,
     /// ivp `Options.mass_storage` (Identity | Full) and `nind1..3` (src/solve/options.rs:105-122); RADAU only.
+    /// the problem's own SolOut hook replaces DefaultSolOut (ivp: `Method::solve(.., Some(&mut solout))`, src/solout.rs:55-63)
+    pub user_solout: bool,
     pub mass_full: bool, pub nind1: Option<usize>, pub nind2: Option<usize>, pub nind3: Option<usize>,
 }
 impl Options { pub fn builder() -> OptionsBuilder { OptionsBuilder(Options::default()) } }
@@ -75,7 +77,7 @@ impl Default for Options {
         Options { method: Method::DOPRI5, rtol: 1e-3.into(), atol: 1e-6.into(), max_steps: None, t_eval: None,
                   first_step: None, max_step: None, min_step: None, dense_output: false, event_config: None,
                   max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false, max_segments: 4096,
-                  mass_full: false, nind1: None, nind2: None, nind3: None }
+                  user_solout: false, mass_full: false, nind1: None, nind2: None, nind3: None }
     }
 }
 pub struct OptionsBuilder(Options);
@@ -181,7 +183,7 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         max_events: if ne > 0 { options.max_events as i32 } else { 0 }, max_out: options.max_out as i32,
         jac_mode: options.analytic_jac as i32, flags: if options.strict_fp { sys::IVPB_FLAG_STRICT_FP } else { 0 },
         max_segments: if options.dense_output { options.max_segments as i32 } else { 0 },
-        mass_storage: options.mass_full as i32,
+        mass_storage: options.mass_full as i32, user_solout: options.user_solout as i32,
         nind1: options.nind1.map_or(-1, |k| k as i32), nind2: options.nind2.map_or(-1, |k| k as i32),
         nind3: options.nind3.map_or(-1, |k| k as i32),
     };

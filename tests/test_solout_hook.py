@@ -1,0 +1,146 @@
+"""the solvers' SolOut callback slot with a problem-supplied hook (reference src/solout.rs:55-78) --
+ControlFlag::Interrupt / ModifiedSolution as handled by every explicit solver (dop853.rs:246-268,596-624,
+dopri5.rs:250-264,414-434, rk23.rs:172-188,258-285, rk4.rs:124-140,196-216) -- running on the device, so that
+"bounce and continue" (reference examples/bouncing_ball.py:14-36, a host loop of solve_ivp restarts) needs no host
+round trip.  Options.user_solout = 1 is the reference's low-level `Method::solve(.., Some(&mut solout))` call.
+"""
+import numpy as np
+import pytest
+
+import ivp_b200 as ib
+from ivp_b200 import Direction, EventConfig, Method, Options, Status, synth
+from ivp_b200.api import IVPB_FLAG_STRICT_FP, PROBLEMS
+
+EXPLICIT = [Method.RK23, Method.DOPRI5, Method.DOP853, Method.RK4]
+
+
+def opts_for(method, **kw):
+    base = dict(first_step=1e-3) if method == Method.RK4 else dict(rtol=1e-8, atol=1e-10)
+    return Options(method=method, user_solout=True, max_out=64, **base, **kw)
+
+
+def host_restart_chain(oracle, y0, g, drag, restitution, tf, method):
+    """reference examples/bouncing_ball.py:14-36 with the oracle as solve_ivp: terminal event, restart from the host."""
+    t_curr, state, bounces = 0.0, np.array(y0, dtype=float), []
+    kw = dict(first_step=1e-3) if method == Method.RK4 else dict(rtol=1e-8, atol=1e-10)
+    for _ in range(64):
+        s = oracle.solve_batch(PROBLEMS["bouncing_ball"], t_curr, tf, [state], [[g, drag]],
+                               Options(method=method, event_config=[EventConfig(Direction.Negative, 1)], **kw)).solution(0)
+        if len(s.t_events[0]) == 0:
+            break
+        t_curr = float(s.t_events[0][0])
+        bounces.append(t_curr)
+        v = -restitution * float(s.y_events[0][0][1])
+        if abs(v) < 0.1:
+            break
+        state = np.array([0.0, v])
+    return np.array(bounces)
+
+
+@pytest.mark.parametrize("method", EXPLICIT)
+def test_oracle_bounce_hook_matches_the_host_restart_chain(oracle, method):
+    """The in-solver bounce (SolOut + ModifiedSolution) and the reference example's host loop of terminal events find the
+    same impacts (to integration accuracy: the restart re-runs hinit, the hook carries the step size over)."""
+    y0, g, drag, e = [10.0, 5.0], 9.81, 0.02, 0.75              # the example's numbers
+    o = oracle.solve_batch(PROBLEMS["ball_bounce"], 0.0, 15.0, [y0], [[g, drag, e]], opts_for(method))
+    m = int(o.n_out[0])
+    hook_t = o.t_out[0, 1:m]                                     # sample 0 is the start point
+    chain_t = host_restart_chain(oracle, y0, g, drag, e, 15.0, method)
+    assert o.status[0] == Status.UserInterrupt                   # the hook stops once |v| < 0.1 after an impact
+    assert hook_t.size == chain_t.size >= 10
+    np.testing.assert_allclose(hook_t, chain_t, rtol=0, atol=2e-3 if method == Method.RK4 else 2e-6)
+    assert np.all(o.y_out[0, 1:m, 0] == 0.0) and np.all(o.y_out[0, 1:m, 1] > 0.0)     # emitted on the ground, moving up
+    assert o.t_final[0] == hook_t[-1] and abs(o.y_final[0, 1]) < 0.1
+    # every ModifiedSolution costs one extra RHS evaluation (e.g. dop853.rs:613-617)
+    plain = oracle.solve_batch(PROBLEMS["ball_bounce"], 0.0, 1.0, [y0], [[g, drag, e]], opts_for(method))
+    assert plain.status[0] == Status.Success and plain.n_out[0] == 1 and abs(plain.t_final[0] - 1.0) < 1e-12
+
+
+def test_oracle_hook_config_errors(oracle):
+    with pytest.raises(RuntimeError, match="no SolOut hook"):
+        oracle.solve_batch(PROBLEMS["sho"], 0.0, 1.0, [[1.0, 0.0]], None, Options(user_solout=True))
+    with pytest.raises(RuntimeError, match="explicit methods"):
+        oracle.solve_batch(PROBLEMS["ball_bounce"], 0.0, 1.0, [[1.0, 0.0]], [[9.81, 0.0, 0.5]], Options(method=Method.RADAU, user_solout=True))
+
+
+# ---- the CUDA path -----------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", EXPLICIT)
+def test_bounce_hook_strict_bit_exact_and_fma_inside_tolerance(oracle, method):
+    prob, y0, par, t0, tf = synth.ensemble("ball_bounce", 4000)
+    o = oracle.solve_batch(PROBLEMS[prob], t0, tf, y0, par, opts_for(method), nthreads=8)
+    g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts_for(method, flags=IVPB_FLAG_STRICT_FP))
+    for f in ("status", "counters", "t_final", "y_final", "h_next", "n_out", "t_out", "y_out"):
+        a, b = getattr(g, f), getattr(o, f)
+        if f in ("t_out", "y_out"):                              # slots past n_out are not initialised on the device
+            valid = np.arange(a.shape[1])[None, :] < np.minimum(g.n_out, a.shape[1])[:, None]
+            a, b = a[valid], b[valid]
+        assert np.array_equal(a, b), f
+    assert set(np.unique(g.status)) <= {int(Status.Success), int(Status.UserInterrupt)} and (g.n_out > 3).all()
+    f = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts_for(method))          # default (FMA) build
+    # same number of bounces, except where the stop rule |v| < 0.1 is decided by the last bits of an impact velocity
+    same = f.n_out == o.n_out
+    assert np.array_equal(f.status, o.status) and same.mean() >= 0.99
+    m = (np.arange(f.t_out.shape[1])[None, :] < np.minimum(f.n_out, f.t_out.shape[1])[:, None]) & same[:, None]
+    np.testing.assert_allclose(f.t_out[m], o.t_out[m], rtol=1e-6, atol=1e-6)
+    # (no step-count claim for the FMA build here: every impact time is the end of a 60-step bisection, so a last-bit
+    #  difference restarts the following arc from a slightly different point and the step sequences decouple -- measured
+    #  52 % equal counts for DOPRI5; the strict build above is bit-identical)
+
+
+USER_PRINTER = """
+__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { d[0] = y[1]; d[1] = -p[0] * y[0]; }
+// src/solout.rs:31-54 (the `Printer` example of the SolOut docs): equidistant output through the step interpolant
+template <class Interp, class Emit>
+__device__ int ivp_solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit) {
+  const double dx = 0.25;
+  if (!dense.valid()) { emit(x, y); state[0] = 1.0; return 0; }          // state[0]: index of the next output point
+  double yi[2];
+  while (state[0] * dx <= x) {
+    dense.eval(state[0] * dx, yi);
+    emit(state[0] * dx, yi);
+    state[0] += 1.0;
+  }
+  if (y[0] < -0.5) return 1;                                             // Interrupt once the oscillator swings past -0.5
+  return 0;
+}
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [Method.DOPRI5, Method.DOP853, Method.RK23])
+def test_user_printer_hook_matches_t_eval_sampling(method):
+    """A user SolOut in CUDA C (NVRTC): the docs' equidistant `Printer`, checked against DefaultSolOut's t_eval samples of
+    the same solve, plus ControlFlag::Interrupt."""
+    from ivp_b200 import api
+    N = 600
+    y0 = np.stack([1.0 + 0.001 * np.arange(N), np.zeros(N)], axis=1)
+    par = np.full((N, 1), 1.0)
+    src_plain = USER_PRINTER.split("// src/solout.rs")[0]
+    hook = api.Problem.from_cuda_source(USER_PRINTER, n=2, p=1, has_solout=True)
+    plain = api.Problem.from_cuda_source(src_plain, n=2, p=1)
+    g = ib.solve_ivp_batch(hook, 0.0, 10.0, y0, par, Options(method=method, rtol=1e-9, atol=1e-12, user_solout=True, max_out=64))
+    assert np.all(g.status == Status.UserInterrupt)                 # A cos(t) < -0.5 seen at the end of a step
+    assert np.all(g.y_final[:, 0] < -0.5) and np.all(g.t_final > np.arccos(-0.5 / y0[:, 0])) and np.all(g.t_final < 3.5)
+    te = 0.25 * np.arange(64)
+    r = ib.solve_ivp_batch(plain, 0.0, 10.0, y0, par, Options(method=method, rtol=1e-9, atol=1e-12, t_eval=te))
+    for i in (0, N // 2, N - 1):
+        m = int(g.n_out[i])
+        assert m >= 8 and np.array_equal(g.t_out[i, :m], te[:m])
+        np.testing.assert_allclose(g.y_out[i, :m], r.y_out[i, :m], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(g.y_out[i, :m, 0], y0[i, 0] * np.cos(te[:m]), atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_user_solout_config_errors():
+    y0 = np.array([[1.0, 0.0]])
+    with pytest.raises(ib.ConfigError, match="no SolOut hook"):
+        ib.solve_ivp_batch("sho", 0.0, 1.0, y0, None, Options(user_solout=True))
+    par = np.array([[9.81, 0.0, 0.5]])
+    with pytest.raises(ib.ConfigError, match="explicit methods"):
+        ib.solve_ivp_batch("ball_bounce", 0.0, 1.0, y0, par, Options(method=Method.BDF, user_solout=True))
+    with pytest.raises(ib.ConfigError, match="DefaultSolOut"):
+        ib.solve_ivp_batch("ball_bounce", 0.0, 1.0, y0, par, Options(user_solout=True, t_eval=[0.5]))
+    # without user_solout the same problem is an ordinary ODE under DefaultSolOut: the ball falls through the floor
+    g = ib.solve_ivp_batch("ball_bounce", 0.0, 3.0, np.array([[10.0, 0.0]]), par, Options(rtol=1e-8, atol=1e-10))
+    assert g.status[0] == Status.Success and g.y_final[0, 0] < 0.0
