@@ -303,12 +303,27 @@ struct SolOutDev {
       const i64 o = idx * (i64)a.out_cap + n_out;
       if (a.t_out && L::leader()) a.t_out[o] = t;
       if (a.y_out) {
+        // 8-byte stores on purpose: 16-byte ones (STG.128) measured the same on device memory and SLOWER when y_out is
+        // mapped host memory (CR3BP, 101 samples: e2e 412 ms vs 392 ms; staged copies 425 ms)
 #pragma unroll
         for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_out[o * NG + L::gi(i)] = yv[i];
       }
     }
     last_t = t;
     ++n_out;
+  }
+
+  // Zero-copy sample output (KArgs::zero_tail): define the slots this trajectory did not fill.
+  __device__ __forceinline__ void zero_tail(const KArgs& a, i64 idx) const {
+    if (!a.zero_tail) return;
+    for (int s = n_out; s < a.out_cap; ++s) {
+      const i64 o = idx * (i64)a.out_cap + s;
+      if (a.t_out && L::leader()) a.t_out[o] = 0.0;
+      if (a.y_out) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_out[o * NG + L::gi(i)] = 0.0;
+      }
+    }
   }
 
   static __device__ __forceinline__ bool crossed(double l, double r, int dir) {   // solout.rs:168-176
@@ -631,6 +646,7 @@ struct ErkTraj {
   // Write the per-trajectory results.  (x, y) is the integrator's last accepted point, or the event point
   // when a terminal event interrupted the integration (step() moves it there).
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if constexpr (FEAT != 0) so.zero_tail(a, idx);
     if (a.y_final) {
       if constexpr (!L::WARP && (NG % 2 == 0)) {
         if (a.vec_io) {

@@ -390,6 +390,7 @@ struct RadauTraj {
   }
 
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if constexpr (FEAT != 0) so.zero_tail(a, idx);
     if (a.status) a.status[idx] = status;
     if (a.counters) {
       u32* c = a.counters + idx * 6;
@@ -872,6 +873,7 @@ struct BdfTraj {
   }
 
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if constexpr (FEAT != 0) so.zero_tail(a, idx);
     if (a.status) a.status[idx] = status;
     if (a.counters) {
       u32* c = a.counters + idx * 6;

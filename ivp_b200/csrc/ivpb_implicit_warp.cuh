@@ -324,6 +324,7 @@ struct RadauWarpTraj {
   }
 
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if constexpr (FEAT != 0) so.zero_tail(a, idx);
     if (a.y_final) {
 #pragma unroll
       for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_final[idx * NN + L::gi(i)] = y[i];
@@ -704,6 +705,7 @@ struct BdfWarpTraj {
   }
 
   __device__ __forceinline__ void finish(const KArgs& a) {
+    if constexpr (FEAT != 0) so.zero_tail(a, idx);
     if (a.y_final) {
 #pragma unroll
       for (int i = 0; i < N; ++i) if (L::valid(i)) a.y_final[idx * NN + L::gi(i)] = y[i];

@@ -349,10 +349,11 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
 // Enqueue one shard on one device.  All pointers in `d` are device pointers on dev.
 static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemInfo& pi, const ivpb_options* o,
                         int64_t N, double t0, double tf, const double* d_y0, const double* d_params,
-                        const ivpb_outputs* d, cudaStream_t stream) {
+                        const ivpb_outputs* d, cudaStream_t stream, bool zero_tail = false) {
   if (N == 0) return 0;
   KArgs a;
   fill_args(a, pi, o, N, t0, tf);
+  a.zero_tail = zero_tail ? 1 : 0;
   a.y0 = d_y0; a.params = d_params; a.queue = dev.queue;
   a.status = d->status; a.counters = d->counters; a.t_final = d->t_final; a.y_final = d->y_final;
   a.h_next = d->h_next; a.n_out = d->n_out; a.t_out = d->t_out; a.y_out = d->y_out;
@@ -657,9 +658,15 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   char* zc_par = pi.p > 0 ? mapped(params) : nullptr;
   char* zc_out[OUT_FIELDS];
   for (int f = 0; f < OUT_FIELDS; ++f) {
-    const bool whole = f <= OUT_NOUT || f == OUT_EVCOUNT;      // written by every trajectory (ErkTraj::finish)
+    // written in full by every trajectory (ErkTraj::finish); the sample blocks too, once `finish` zero-fills the
+    // slots a trajectory left empty (KArgs::zero_tail) -- t_eval-heavy output (CR3BP: 4.9 KB per trajectory, 5.2 GB per
+    // 2^20) then crosses PCIe WHILE the ensemble integrates instead of as one serial copy after the kernel
+    const bool whole = f <= OUT_NOUT || f == OUT_EVCOUNT || f == OUT_TOUT || f == OUT_YOUT;
     zc_out[f] = whole ? mapped(host[f]) : nullptr;
   }
+  const bool zero_interval = std::fabs(tf - t0) < 1e-15;       // that kernel writes only the matching samples: stage it
+  if (zero_interval || (host[OUT_TOUT] && !zc_out[OUT_TOUT]) || (host[OUT_YOUT] && !zc_out[OUT_YOUT]))   // both or neither
+    zc_out[OUT_TOUT] = zc_out[OUT_YOUT] = nullptr;
   // static contiguous split [g*N/G, (g+1)*N/G) -- trajectories are independent, no exchange step
   for (int g = 0; g < G; ++g) {
     Device& dev = ctx->devs[g];
@@ -698,13 +705,14 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       CK(cudaMemsetAsync(d.n_seg, 0, per[OUT_NSEG] * Ng, dev.stream));
     }
     // sample / event slots the kernel does not touch must read as zero on the host
-    if (d.t_out) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
-    if (d.y_out) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
+    if (d.t_out && !direct[OUT_TOUT]) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
+    if (d.y_out && !direct[OUT_YOUT]) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
     if (d.ev_t) CK(cudaMemsetAsync(d.ev_t, 0, per[OUT_EVT] * Ng, dev.stream));
     if (d.ev_y) CK(cudaMemsetAsync(d.ev_y, 0, per[OUT_EVY] * Ng, dev.stream));
     if (d.ev_count && !direct[OUT_EVCOUNT]) CK(cudaMemsetAsync(d.ev_count, 0, per[OUT_EVCOUNT] * Ng, dev.stream));
     if (d.n_out && !direct[OUT_NOUT]) CK(cudaMemsetAsync(d.n_out, 0, per[OUT_NOUT] * Ng, dev.stream));
-    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, d_y0, d_par, &d, dev.stream))
+    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, d_y0, d_par, &d, dev.stream,
+                              direct[OUT_TOUT] || direct[OUT_YOUT]))
       return rc;
     for (int f = 0; f < OUT_FIELDS; ++f) {
       if (!dptr[f] || !host[f] || direct[f]) continue;

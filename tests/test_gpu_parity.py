@@ -781,6 +781,57 @@ def test_zero_copy_pinned_buffers_match_staged_copies():
     lib.ivpb_host_free(bufs["y0"]); lib.ivpb_host_free(bufs["par"])
 
 
+@pytest.mark.parametrize("case", ["t_eval", "step_mode_events", "radau_t_eval"])
+def test_zero_copy_sample_blocks_match_staged_copies(case):
+    """Page-locked t_out / y_out: every trajectory writes its samples to the caller's buffer over PCIe while it integrates
+    and zero-fills the slots it leaves empty at `finish` (KArgs::zero_tail); byte-identical to the staged path."""
+    import ctypes as C
+    from ivp_b200 import _abi, api
+    from ivp_b200.api import IVPB_FLAG_NO_ZEROCOPY
+    lib = api.load_library()
+    N = 5003
+    if case == "step_mode_events":       # terminal event: different sample counts per trajectory, ragged tails
+        prob, y0, par, t0, tf = synth.ensemble("ball", N)
+        opts = dict(method=Method.DOPRI5, rtol=1e-8, atol=1e-10, max_out=40)
+    elif case == "radau_t_eval":
+        prob, y0, par, t0, tf = synth.ensemble("robertson", N)
+        opts = dict(method=Method.RADAU, rtol=1e-6, atol=1e-6, t_eval=np.geomspace(1e-3, 1e8, 23))
+    else:                                # some samples lie outside the span: their slots stay empty
+        prob, y0, par, t0, tf = synth.ensemble("vdp", N)
+        opts = dict(method=Method.DOP853, rtol=1e-8, atol=1e-8, t_eval=np.linspace(t0, 1.5 * tf, 31))
+    problem = api.Problem.builtin(prob)
+    ctx = api.default_context()
+    n, ne = problem.n, problem.n_events
+    keep = []
+
+    def pinned(shape, dtype, fill):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib.ivpb_host_alloc(nbytes)
+        assert p
+        keep.append(p)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (nbytes,)).view(dtype).reshape(shape)
+        a[...] = fill
+        return a
+
+    res = {}
+    for flags in (0, IVPB_FLAG_NO_ZEROCOPY):
+        mo = _abi.MarshalledOptions(Options(flags=flags, **opts), n, ne)
+        cap = mo.cap
+        nout = pinned((N,), np.int32, -1)
+        tout = pinned((N, cap), np.float64, np.nan)          # poisoned: every slot must be defined afterwards
+        yout = pinned((N, cap, n), np.float64, np.nan)
+        stat = pinned((N,), np.int32, -7)
+        st = _abi.IvpbOutputs()
+        st.status, st.n_out, st.t_out, st.y_out = _abi.ptr(stat), _abi.ptr(nout), _abi.ptr(tout), _abi.ptr(yout)
+        ctx.solve_host(problem, t0, tf, np.ascontiguousarray(y0), None if par is None else np.ascontiguousarray(par), mo, st)
+        res[flags] = (stat.copy(), nout.copy(), tout.copy(), yout.copy())
+    for a, b in zip(res[0], res[IVPB_FLAG_NO_ZEROCOPY]):
+        assert not np.isnan(a).any() and np.array_equal(a, b)
+    assert (res[0][1] > 0).all() and (res[0][1] < res[0][2].shape[1]).any()      # some rows do have an empty tail
+    for p in keep:
+        lib.ivpb_host_free(p)
+
+
 @pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
 def test_warp_cooperative_implicit_medakzo(oracle, method):
     """8 < n <= 64: one trajectory per warp, Jacobian / E1 / E2 in the warp's shared memory, warp-cooperative
