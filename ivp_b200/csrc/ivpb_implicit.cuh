@@ -287,6 +287,17 @@ template <int N> struct MatSel {
   static constexpr int BLK = (N <= 6) ? 128 : 64;       // 4 N^2 doubles per thread must fit 227 KB for RADAU
 };
 constexpr int IMPLICIT_MAX_N = 8;
+// Resident blocks per SM asked of the compiler for implicit_kernel (see ivpb_kernels.cuh for the measurements)
+template <int N, int METHOD>
+constexpr int implicit_min_blocks() {
+#ifdef IVPB_IMPL_MB
+  return MatSel<N>::REG ? IVPB_IMPL_MB : 1;
+#else
+  if (!MatSel<N>::REG) return 1;
+  if (N <= 2) return 5;
+  return METHOD == M_RADAU ? 3 : 4;
+#endif
+}
 
 // =================================================================================================
 // RADAU -- reference src/methods/radau.rs:114-796
@@ -313,6 +324,33 @@ struct RadauTraj {
   static constexpr bool BATCH_HEAVY = false;
   using Out = SolOutDev<Prob, M_RADAU, FEAT>;
   using Mat = typename std_conditional<REG, RegMat<N>, SmemMat<N, BLK>>::type;
+  static constexpr bool USER = (FEAT & K_USER) != 0;
+  double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
+  struct UserInterp {                                  // StepInterpolant of the accepted step (src/dense.rs:32-97)
+    const double (&c)[4][N]; double xold, h; bool ok;
+    __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<M_RADAU, N>(t, yi, c, xold, h); }
+  };
+  struct UserEmit {
+    Out& so; const KArgs& a; i64 idx;
+    __device__ __forceinline__ void operator()(double t, const double* yv) { so.push(a, idx, t, yv); }
+  };
+  // The callback slot of radau.rs:336-356,712-740: DefaultSolOut, or the problem's own SolOut (ModifiedSolution
+  // re-evaluates f0; scal keeps the values of the unmodified state, like the reference).  Returns 1 on Interrupt.
+  __device__ __forceinline__ int callback(const KArgs& a, bool first_call, double xold, double hstep) {
+    if constexpr (USER) {
+      const UserInterp ip{cont, xold, hstep, !first_call};
+      UserEmit em{so, a, idx};
+      const int fl = Prob::solout(xold, x, y, p, ustate, ip, em);
+      if (fl == 1) { status = ST_INTERRUPT; return 1; }
+      if (fl == 2) { Prob::ode(x, y, p, f0); nfev += 1; return 2; }
+      return 0;
+    } else {
+      double tev, yev[N];
+      if (so.solout(a, idx, p, first_call, xold, x, y, cont, hstep, xold, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return 1; }
+      return 0;
+    }
+  }
   struct NoMat {};
   typename std_conditional<MASS, Mat, NoMat>::type massm;      // radau.rs:283: filled once by IVP::mass
   double hhfac;                                                // radau.rs:296 (only read for index-2/3 variables)
@@ -381,8 +419,11 @@ struct RadauTraj {
     Prob::ode(x, y, p, f0);
     nfev = 1;
     if constexpr (FEAT != 0) {
-      double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if constexpr (USER) {
+#pragma unroll
+        for (int q = 0; q < Prob::NSTATE; ++q) ustate[q] = 0.0;
+      }
+      if (callback(a, true, x, 0.0) == 1) return true;
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) scal[i] = a.atol[i] + a.rtol[i] * fabs(y[i]);
@@ -652,10 +693,7 @@ struct RadauTraj {
 #pragma unroll
       for (int i = 0; i < N; ++i) scal[i] = a.atol[i] + a.rtol[i] * fabs(y[i]);
       if constexpr (FEAT != 0) {
-        double tev, yev[N];
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-        }
+        if (callback(a, false, xold, h) == 1) return true;
       }
       if (last) { h = hnew; status = ST_SUCCESS; return true; }
       singular_count = 0;

@@ -72,10 +72,15 @@ __host__ inline const void* erk_lookup(int method, int feat) {
 
 
 #ifdef IVPB_WITH_IMPLICIT
-// Implicit kernels (ivpb_implicit.cuh): one resident block per SM is assumed for the launch bounds; the
-// runtime asks the occupancy API for the real number.
+// Implicit kernels (ivpb_implicit.cuh).  They are latency-bound (ncu, profiles/r1h_*_ncu_full.txt: issue slots 21-26 %
+// busy, top stalls "no instruction" and "wait", 8 resident warps per SM at 178-182 registers), so the register-resident
+// variants (n <= 3) trade registers for resident warps: the launch bound below caps the registers at 168 / 128 / 96 and
+// accepts a few hundred bytes of spills.  Measured per 2^18 trajectories with 1 / 3 / 4 / 5 / 6 blocks per SM:
+//   RADAU  VdP mu=1000 (n=2)   99.8 / 74.1 / 64.8 / 58.9 / 60.8 ms      BDF  VdP mu=1000 (n=2)   92.9 / 92.8 / 80.6 / 78.4 / 84.4 ms
+//   RADAU  Robertson   (n=3)   12.5 / 10.8 / 11.7 / 11.8 / 13.1 ms      BDF  Robertson   (n=3)   62.3 / 46.9 / 46.3 / 57.0 / 60.2 ms
+// The shared-memory variants (4 <= n <= 8) are limited by their matrices, not by registers.
 template <class Prob, int METHOD, int FEAT>
-__global__ void __launch_bounds__(ImplicitSel<Prob, METHOD, FEAT>::BLK, 1) implicit_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(ImplicitSel<Prob, METHOD, FEAT>::BLK, (implicit_min_blocks<Prob::N, METHOD>())) implicit_kernel(const __grid_constant__ KArgs a) {
   implicit_body<Prob, METHOD, FEAT>(a);
 }
 
@@ -112,6 +117,9 @@ __host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem
       case K_OUT: return (const void*)&implicit_kernel<Prob, METHOD, K_OUT>;
       case K_OUT | K_EVENTS:
         if constexpr (Prob::NEV > 0) return (const void*)&implicit_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
+        else return nullptr;
+      case K_USER:                       // Options.user_solout (RADAU; the BDF kernels do not take hooks)
+        if constexpr (Prob::HAS_SOLOUT && METHOD == M_RADAU) return (const void*)&implicit_kernel<Prob, METHOD, K_USER>;
         else return nullptr;
       default: return nullptr;
     }

@@ -125,7 +125,7 @@ std::string program_source(const ivpb_user_problem& up, bool implicit) {
          "ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
     s += "  ivpb::implicit_warp_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
   } else if (implicit) {
-    s += "extern \"C\" __global__ void __launch_bounds__((ivpb::ImplicitSel<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>::BLK), 1) "
+    s += "extern \"C\" __global__ void __launch_bounds__((ivpb::ImplicitSel<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>::BLK), (ivpb::implicit_min_blocks<PUser::N, IVPB_USER_METHOD>())) "
          "ivpb_user_kernel(const __grid_constant__ ivpb::KArgs a) {\n";
     s += "  ivpb::implicit_body<PUser, IVPB_USER_METHOD, IVPB_USER_FEAT>(a);\n}\n";
   } else {

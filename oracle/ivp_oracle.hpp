@@ -940,10 +940,11 @@ Solution solve_ivp(const F& f, double x0, double xend, const std::vector<double>
         case Method::RK23: R = rk23::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
         case Method::DOPRI5: R = dopri5::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
         case Method::DOP853: R = dop853::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
-        default: throw ConfigError("user SolOut hooks are implemented for the explicit methods");
+        case Method::RADAU: R = radau::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
+        default: throw ConfigError("user SolOut hooks are implemented for the explicit methods and RADAU");
       }
       S.t = std::move(us.t); S.y = std::move(us.y);
-      S.nfev = R.nfev; S.nstep = R.nstep; S.naccpt = R.naccpt; S.nrejct = R.nrejct;
+      S.nfev = R.nfev; S.njev = R.njev; S.nlu = R.nlu; S.nstep = R.nstep; S.naccpt = R.naccpt; S.nrejct = R.nrejct;
       S.status = R.status; S.h_next = R.h;
       S.x_last = us.x_last; S.y_last = std::move(us.y_last);
       return S;

@@ -231,7 +231,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   f.ode(x, y.data(), f0.data());
   R.nfev += 1;
   if (so) {
-    if (so->solout(xold, x, y, nullptr) == Flag::Interrupt) { R.h = h; R.status = Status::UserInterrupt; return R; }
+    const Flag fl0 = so->solout(xold, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) { R.h = h; R.status = Status::UserInterrupt; return R; }
+    if (fl0 == Flag::ModifiedSolution) { f.ode(x, y.data(), f0.data()); R.nfev += 1; }      // radau.rs:347-351
   }
   for (size_t i = 0; i < n; ++i) scal[i] = atol[i] + rtol[i] * std::fabs(y[i]);
   theta = thet;
@@ -419,7 +421,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
       for (size_t i = 0; i < n; ++i) scal[i] = atol[i] + rtol[i] * std::fabs(y[i]);
       if (so) {
         StepInterp ip{cont.data(), cont.size(), xold, h, &interpolate};
-        if (so->solout(xold, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        const Flag fl = so->solout(xold, x, y, &ip);
+        if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+        if (fl == Flag::ModifiedSolution) { f.ode(x, y.data(), f0.data()); R.nfev += 1; }     // radau.rs:731-735 (scal is not rebuilt)
       }
       if (last) { h = hnew; R.status = Status::Success; break; }
       singular_count = 0;
