@@ -10,13 +10,21 @@
 
 namespace ivpb {
 
-// Small systems leave registers to spare: asking for 5 resident blocks (96 registers/thread) costs no spills
-// for n <= 2 and measured +4 % on the north-star kernel; larger systems keep the whole register file.
+// Small systems (n <= 2) leave registers to spare: asking for 7 resident blocks per SM caps the registers at 72 (24 bytes
+// of spills in the DOP853 kernel) and keeps 28 warps resident.  North star, ms per 2^20 trajectories with 5 / 6 / 7 / 8 /
+// 10 blocks: (5 measured +4 % over 1 earlier) 15.54 / 15.49 / 15.21 / 17.09 / 20.07; VdP DOPRI5 19.79 (5) / 18.93 (7) / 24.08 (8).  Larger systems keep
+// the whole register file.
+#ifndef IVPB_MB_SMALL
+#define IVPB_MB_SMALL 7
+#endif
+#ifndef IVPB_MB_MID
+#define IVPB_MB_MID 5      // n = 3, 4: Lorenz DOPRI5 8.18 (1) / 7.88 (5) / 9.47 (6) ms per 2^20 trajectories
+#endif
 #ifndef IVPB_MB_BIG
 #define IVPB_MB_BIG 1
 #endif
 template <class Prob, int METHOD, int FEAT>
-__global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? 5 : (Prob::N <= 4 ? 1 : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? IVPB_MB_SMALL : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
   erk_body<Prob, METHOD, FEAT>(a);
 }
 
