@@ -13,7 +13,8 @@ namespace ivpb {
 // Small systems (n <= 2) leave registers to spare: asking for 7 resident blocks per SM caps the registers at 72 (24 bytes
 // of spills in the DOP853 kernel) and keeps 28 warps resident.  North star, ms per 2^20 trajectories with 5 / 6 / 7 / 8 /
 // 10 blocks: (5 measured +4 % over 1 earlier) 15.54 / 15.49 / 15.21 / 17.09 / 20.07; VdP DOPRI5 19.79 (5) / 18.93 (7) / 24.08 (8).  Larger systems keep
-// the whole register file.
+// the whole register file.  Kernels with a user SolOut hook (K_USER) stay at 5: the hook's own code needs the registers
+// (ball_bounce: 6.8 ms at 5 blocks, 7.3 ms at 7).
 #ifndef IVPB_MB_SMALL
 #define IVPB_MB_SMALL 7
 #endif
@@ -24,7 +25,7 @@ namespace ivpb {
 #define IVPB_MB_BIG 1
 #endif
 template <class Prob, int METHOD, int FEAT>
-__global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? IVPB_MB_SMALL : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
   erk_body<Prob, METHOD, FEAT>(a);
 }
 

@@ -64,6 +64,9 @@ def ensemble(name: str, N: int, offset: int = 0):
         y0 = np.stack([1.0 + 19.0 * u[:, 0], -5.0 + 15.0 * u[:, 1]], axis=1)
         par = np.stack([np.full(N, 9.81), 0.05 * u[:, 2], 0.6 + 0.3 * u[:, 3]], axis=1)
         return "ball_bounce", y0, par, 0.0, 15.0
+    if name == "mass_linear3":   # M y' = k A y with a full constant M, y0 ~ U(-2, 2)^3, k ~ U(0.5, 40)
+        u = uniform(N, 4, offset=offset)
+        return "mass_linear3", 4.0 * u[:, :3] - 2.0, 0.5 + 39.5 * u[:, 3:4], 0.0, 2.0
     if name == "robertson_dae":  # Robertson as an index-1 DAE (mass matrix diag(1, 1, 0)), x + y + z = 1
         u = uniform(N, 1, offset=offset)
         y0 = np.zeros((N, 3))

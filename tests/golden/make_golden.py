@@ -34,6 +34,13 @@ CASES = {
     "vdpstiff_radau": ("vdp_stiff", 24, None, dict(method=Method.RADAU, rtol=1e-4, atol=1e-6)),
     "vdpstiff_bdf": ("vdp_stiff", 24, None, dict(method=Method.BDF, rtol=1e-4, atol=1e-6)),
     "medakzo_bdf": ("medakzo", 6, 7.0, dict(method=Method.BDF, rtol=1e-5, atol=1e-7)),
+    # RADAU with a mass matrix (+ index-2 scaling), the SolOut hook with ModifiedSolution
+    "robertson_dae_radau_mass": ("robertson_dae", 24, 1e6, dict(method=Method.RADAU, rtol=1e-6, atol=1e-10, mass_storage="Full",
+                                                               t_eval=np.array([1e-2, 1.0, 1e2, 1e4, 1e6]))),
+    "robertson_dae_radau_nind2": ("robertson_dae", 16, 1e3, dict(method=Method.RADAU, rtol=1e-6, atol=1e-10, mass_storage="Full", nind2=1)),
+    "mass_linear3_radau_jac": ("mass_linear3", 24, None, dict(method=Method.RADAU, rtol=1e-8, atol=1e-11, mass_storage="Full", jac_mode=1)),
+    "ball_bounce_dop853_hook": ("ball_bounce", 32, None, dict(method=Method.DOP853, rtol=1e-8, atol=1e-10, user_solout=True, max_out=48)),
+    "ball_bounce_radau_hook": ("ball_bounce", 16, None, dict(method=Method.RADAU, rtol=1e-8, atol=1e-10, user_solout=True, max_out=48)),
 }
 FIELDS = ("status", "counters", "t_final", "y_final", "h_next", "n_out", "t_out", "y_out", "ev_count", "ev_t", "ev_y")
 
