@@ -790,6 +790,50 @@ struct BdfTraj {
   bool lu_is_current, jac_pending, os_pending;
   Out so;
 
+  static constexpr bool USER = (FEAT & K_USER) != 0;
+  double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
+  struct UserInterp {                                  // StepInterpolant of the accepted step (bdf.rs:516-519)
+    const double (&c)[7][N]; double xold, h; bool ok;
+    __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<M_BDF, N>(t, yi, c, xold, h); }
+  };
+  struct UserEmit {
+    Out& so; const KArgs& a; i64 idx;
+    __device__ __forceinline__ void operator()(double t, const double* yv) { so.push(a, idx, t, yv); }
+  };
+  // The callback slot of bdf.rs:243-274,516-545: DefaultSolOut, or the problem's own SolOut.  ModifiedSolution restarts the
+  // difference table at order 1 from the changed state and asks for a new Jacobian (bdf.rs:255-271,525-541; the single
+  // Jacobian site at the top of the next trip evaluates it at the saved point).  Returns 1 on Interrupt.
+  __device__ __forceinline__ int callback(const KArgs& a, bool first_call, double xold, const double (&cont)[7][N],
+                                          double hstep, double ixold) {
+    if constexpr (USER) {
+      const UserInterp ip{cont, ixold, hstep, !first_call};
+      UserEmit em{so, a, idx};
+      const int fl = Prob::solout(xold, x, y, p, ustate, ip, em);
+      if (fl == 1) { status = ST_INTERRUPT; return 1; }
+      if (fl == 2) {
+        double f0[N];
+        Prob::ode(x, y, p, f0);
+        nfev += 1;
+        const double direction = signum(a.tf - a.t0);
+        for (int k = 2; k < ND; ++k)
+#pragma unroll
+          for (int i = 0; i < N; ++i) D(k, i) = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { D(0, i) = y[i]; D(1, i) = f0[i] * current_h * direction; JY(i) = y[i]; }
+        order = 1; n_equal_steps = 0;
+        jx = x; jac_pending = true; njev += 1;
+        lu_is_current = false;
+        return 2;
+      }
+      return 0;
+    } else {
+      double tev, yev[N];
+      if (so.solout(a, idx, p, first_call, xold, x, y, cont, hstep, ixold, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return 1; }
+      return 0;
+    }
+  }
+
   // true when the next trip starts with the expensive, rarely needed blocks (see run_schedule)
   __device__ __forceinline__ bool heavy() const { return os_pending || jac_pending || pend != 1.0 || !lu_is_current; }
 
@@ -905,8 +949,11 @@ struct BdfTraj {
       for (int c = 0; c < 7; ++c)
 #pragma unroll
         for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
-      double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if constexpr (USER) {
+#pragma unroll
+        for (int q = 0; q < Prob::NSTATE; ++q) ustate[q] = 0.0;
+      }
+      if (callback(a, true, x, cont, 0.0, x) == 1) return true;
     }
     return false;
   }
@@ -1143,10 +1190,7 @@ struct BdfTraj {
         for (int k = 0; k < MAX_ORDER; ++k) cont[1 + k][i] = (k + 1 <= order) ? D(k + 1, i) : 0.0;
         cont[6][i] = (double)order;
       }
-      double tev, yev[N];
-      if (so.solout(a, idx, p, false, x - h_signed, x, y, cont, h_signed, x_start, tev, yev)) {
-        status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-      }
+      if (callback(a, false, x - h_signed, cont, h_signed, x_start) == 1) return true;
     }
     if (direction * (x - xend) >= 0.0) { status = ST_SUCCESS; return true; }
     // order / step-size selection (bdf.rs:552-606) is owed to the next trip: it is the first thing step() does

@@ -127,8 +127,8 @@ __host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem
       case K_OUT | K_EVENTS:
         if constexpr (Prob::NEV > 0) return (const void*)&implicit_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
         else return nullptr;
-      case K_USER:                       // Options.user_solout (RADAU; the BDF kernels do not take hooks)
-        if constexpr (Prob::HAS_SOLOUT && METHOD == M_RADAU) return (const void*)&implicit_kernel<Prob, METHOD, K_USER>;
+      case K_USER:                       // Options.user_solout: the problem's own SolOut
+        if constexpr (Prob::HAS_SOLOUT) return (const void*)&implicit_kernel<Prob, METHOD, K_USER>;
         else return nullptr;
       default: return nullptr;
     }

@@ -941,7 +941,7 @@ Solution solve_ivp(const F& f, double x0, double xend, const std::vector<double>
         case Method::DOPRI5: R = dopri5::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
         case Method::DOP853: R = dop853::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
         case Method::RADAU: R = radau::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
-        default: throw ConfigError("user SolOut hooks are implemented for the explicit methods and RADAU");
+        case Method::BDF: R = bdf::solve(f, x0, y0, xend, o.rtol, o.atol, cfg, &us); break;
       }
       S.t = std::move(us.t); S.y = std::move(us.y);
       S.nfev = R.nfev; S.njev = R.njev; S.nlu = R.nlu; S.nstep = R.nstep; S.naccpt = R.naccpt; S.nrejct = R.nrejct;

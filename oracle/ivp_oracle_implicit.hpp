@@ -588,8 +588,23 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
   std::vector<std::vector<double>> scratch(MAX_ORDER + 1, std::vector<double>(n, 0.0));
   std::vector<size_t> pivot(n);
 
+  // ControlFlag::ModifiedSolution, bdf.rs:255-271 and :525-541: restart the difference table at order 1 from the changed state
+  auto modified = [&]() {
+    f.ode(x, y.data(), f0.data());
+    R.nfev += 1;
+    d[0] = y;
+    for (size_t i = 0; i < n; ++i) d[1][i] = f0[i] * current_h * direction;
+    for (size_t k = 2; k < d.size(); ++k) std::fill(d[k].begin(), d[k].end(), 0.0);
+    order = 1;
+    n_equal_steps = 0;
+    eval_jac(f, x, y, jac);
+    R.njev += 1;
+    lu_is_current = false;
+  };
   if (so) {
-    if (so->solout(x, x, y, nullptr) == Flag::Interrupt) { R.h = direction * current_h; R.status = Status::UserInterrupt; return R; }
+    const Flag fl0 = so->solout(x, x, y, nullptr);
+    if (fl0 == Flag::Interrupt) { R.h = direction * current_h; R.status = Status::UserInterrupt; return R; }
+    if (fl0 == Flag::ModifiedSolution) modified();
   }
 
   for (;;) {
@@ -721,7 +736,9 @@ IntegrationResult solve(const F& f, double x0, const std::vector<double>& y0, do
     }
     if (so) {
       StepInterp ip{cont.data(), cont.size(), x_start, h_signed, &interpolate};
-      if (so->solout(x - h_signed, x, y, &ip) == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+      const Flag fl = so->solout(x - h_signed, x, y, &ip);
+      if (fl == Flag::Interrupt) { R.status = Status::UserInterrupt; break; }
+      if (fl == Flag::ModifiedSolution) modified();
     }
     if (direction * (x - xend) >= 0.0) { R.status = Status::Success; break; }
     if (n_equal_steps >= order + 1) {

@@ -41,6 +41,7 @@ CASES = {
     "mass_linear3_radau_jac": ("mass_linear3", 24, None, dict(method=Method.RADAU, rtol=1e-8, atol=1e-11, mass_storage="Full", jac_mode=1)),
     "ball_bounce_dop853_hook": ("ball_bounce", 32, None, dict(method=Method.DOP853, rtol=1e-8, atol=1e-10, user_solout=True, max_out=48)),
     "ball_bounce_radau_hook": ("ball_bounce", 16, None, dict(method=Method.RADAU, rtol=1e-8, atol=1e-10, user_solout=True, max_out=48)),
+    "ball_bounce_bdf_hook": ("ball_bounce", 16, None, dict(method=Method.BDF, rtol=1e-8, atol=1e-10, user_solout=True, max_out=48)),
 }
 FIELDS = ("status", "counters", "t_final", "y_final", "h_next", "n_out", "t_out", "y_out", "ev_count", "ev_t", "ev_y")
 

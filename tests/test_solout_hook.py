@@ -1,6 +1,7 @@
 """the solvers' SolOut callback slot with a problem-supplied hook (reference src/solout.rs:55-78) --
 ControlFlag::Interrupt / ModifiedSolution as handled by every explicit solver (dop853.rs:246-268,596-624,
-dopri5.rs:250-264,414-434, rk23.rs:172-188,258-285, rk4.rs:124-140,196-216) -- running on the device, so that
+dopri5.rs:250-264,414-434, rk23.rs:172-188,258-285, rk4.rs:124-140,196-216) and by RADAU / BDF (radau.rs:336-356,712-740,
+bdf.rs:243-274,516-545) -- running on the device, so that
 "bounce and continue" (reference examples/bouncing_ball.py:14-36, a host loop of solve_ivp restarts) needs no host
 round trip.  Options.user_solout = 1 is the reference's low-level `Method::solve(.., Some(&mut solout))` call.
 """
@@ -12,7 +13,8 @@ from ivp_b200 import Direction, EventConfig, Method, Options, Status, synth
 from ivp_b200.api import IVPB_FLAG_STRICT_FP, PROBLEMS
 
 EXPLICIT = [Method.RK23, Method.DOPRI5, Method.DOP853, Method.RK4]
-HOOKED = EXPLICIT + [Method.RADAU]          # radau.rs:347-351,731-735 handles the same flags (f0 is re-evaluated)
+# radau.rs:347-351,731-735 (f0 re-evaluated) and bdf.rs:255-271,525-541 (difference table restarted at order 1, new Jacobian)
+HOOKED = EXPLICIT + [Method.RADAU, Method.BDF]
 
 
 def opts_for(method, **kw):
@@ -60,8 +62,6 @@ def test_oracle_bounce_hook_matches_the_host_restart_chain(oracle, method):
 def test_oracle_hook_config_errors(oracle):
     with pytest.raises(RuntimeError, match="no SolOut hook"):
         oracle.solve_batch(PROBLEMS["sho"], 0.0, 1.0, [[1.0, 0.0]], None, Options(user_solout=True))
-    with pytest.raises(RuntimeError, match="explicit methods"):
-        oracle.solve_batch(PROBLEMS["ball_bounce"], 0.0, 1.0, [[1.0, 0.0]], [[9.81, 0.0, 0.5]], Options(method=Method.BDF, user_solout=True))
 
 
 # ---- the CUDA path -----------------------------------------------------------------------------------------------------
@@ -138,8 +138,6 @@ def test_user_solout_config_errors():
     with pytest.raises(ib.ConfigError, match="no SolOut hook"):
         ib.solve_ivp_batch("sho", 0.0, 1.0, y0, None, Options(user_solout=True))
     par = np.array([[9.81, 0.0, 0.5]])
-    with pytest.raises(ib.ConfigError, match="explicit methods"):
-        ib.solve_ivp_batch("ball_bounce", 0.0, 1.0, y0, par, Options(method=Method.BDF, user_solout=True))
     with pytest.raises(ib.ConfigError, match="DefaultSolOut"):
         ib.solve_ivp_batch("ball_bounce", 0.0, 1.0, y0, par, Options(user_solout=True, t_eval=[0.5]))
     # without user_solout the same problem is an ordinary ODE under DefaultSolOut: the ball falls through the floor
