@@ -41,6 +41,12 @@ static void api_surface() {
   bool threw = false;
   try { Problem::builtin("no_such_problem"); } catch (const ConfigError&) { threw = true; }
   CHECK(threw, "unknown built-in problem is a ConfigError");
+  // options.rs:105-122 (mass_storage, nind1..3) and the SolOut slot of Method::solve
+  Options m = Options::builder().method(Method::RADAU).mass_storage(Options::MatrixStorage::Full).nind2(1).user_solout(true).build();
+  CHECK(d.mass_storage == Options::MatrixStorage::Identity && !d.nind1 && !d.nind2 && !d.nind3 && !d.user_solout, "mass / DAE / hook defaults");
+  CHECK(m.mass_storage == Options::MatrixStorage::Full && m.nind2 && *m.nind2 == 1 && !m.nind1 && m.user_solout, "mass / DAE / hook setters");
+  Problem dae = Problem::builtin("robertson_dae"), bounce = Problem::builtin("ball_bounce");
+  CHECK(dae.n() == 3 && dae.n_params() == 3 && bounce.n() == 2 && bounce.n_params() == 3, "built-ins of the widened rows");
 }
 
 static void no_device_fails_loudly() {
@@ -237,6 +243,47 @@ static void example_programs_as_batches() {
   }
 }
 
+// ---- RADAU with a mass matrix, SolOut hooks, extrapolating dense output ---------------------
+static void mass_matrix_hooks_and_extrapolation() {
+  {  // Robertson as an index-1 DAE (M = diag(1, 1, 0)) against its ODE form, radau.rs:375-386,525-539,626-634
+    Problem dae = Problem::builtin("robertson_dae"), ode = Problem::builtin("robertson");
+    const std::vector<double> y0 = {1.0, 0.0, 0.0}, par = {0.04, 1e4, 3e7};
+    Options od = Options::builder().method(Method::RADAU).rtol(1e-8).atol(1e-12).mass_storage(Options::MatrixStorage::Full).build();
+    Options oo = Options::builder().method(Method::RADAU).rtol(1e-8).atol(1e-12).build();
+    Solution a = solve_ivp(dae, 0.0, 1e5, y0, od, par), b = solve_ivp(ode, 0.0, 1e5, y0, oo, par);
+    CHECK(a.status == Status::Success && b.status == Status::Success, "DAE / ODE status");
+    for (int i = 0; i < 3; ++i)
+      CHECK(std::fabs(a.y.back()[i] - b.y.back()[i]) <= 1e-6 * std::fabs(b.y.back()[i]) + 1e-11, "DAE == ODE form, component %d", i);
+    CHECK(std::fabs(a.y.back()[0] + a.y.back()[1] + a.y.back()[2] - 1.0) < 1e-10, "the algebraic row holds");
+    bool threw = false;
+    try { solve_ivp(dae, 0.0, 1.0, y0, oo, par); } catch (const ConfigError&) { threw = true; }
+    CHECK(threw, "a mass-matrix problem without mass_storage = Full is Error::Config");
+    threw = false;
+    try { solve_ivp(dae, 0.0, 1.0, y0, Options::builder().method(Method::RADAU).mass_storage(Options::MatrixStorage::Full).nind1(1).nind2(1).build(), par); }
+    catch (const ConfigError&) { threw = true; }                  // radau.rs:236-245 InvalidDAEPartition
+    CHECK(threw, "nind1 + nind2 + nind3 != n is Error::Config");
+  }
+  {  // the ball that bounces inside one solve: SolOut + ControlFlag::ModifiedSolution (src/solout.rs:18-29)
+    Problem bounce = Problem::builtin("ball_bounce");
+    for (Method m : {Method::DOPRI5, Method::DOP853, Method::RADAU, Method::BDF}) {
+      Solution s = solve_ivp(bounce, 0.0, 15.0, {10.0, 5.0},
+                             Options::builder().method(m).rtol(1e-8).atol(1e-10).user_solout(true).build(), {9.81, 0.02, 0.75});
+      CHECK(s.status == Status::UserInterrupt && s.t.size() == 18, "%s: 17 impacts + the start point, then |v| < 0.1 stops it (%zu)", name(m), s.t.size());
+      CHECK(std::fabs(s.t[1] - 2.0726) < 1e-3 && std::fabs(s.t.back() - 9.1664) < 1e-3, "%s: first / last impact %g %g", name(m), s.t[1], s.t.back());
+    }
+  }
+  {  // ContinuousOutput::evaluate_extrapolate (cont.rs:91-150)
+    Problem sho = Problem::builtin("sho");
+    Solution s = solve_ivp(sho, 0.0, 1.0, {1.0, 0.0}, Options::builder().method(Method::DOP853).rtol(1e-10).atol(1e-12).dense_output(true).build());
+    auto in = s.sol_extrapolate(0.5), out = s.sol_extrapolate(1.05);
+    CHECK(in && std::fabs((*in)[0] - std::cos(0.5)) < 1e-9, "inside the span: interpolation");
+    CHECK(out && std::fabs((*out)[0] - std::cos(1.05)) < 1e-6, "beyond the span: the last segment extrapolates");
+    bool threw = false;
+    try { s.sol(1.05); } catch (const InterpolationError&) { threw = true; }
+    CHECK(threw, "Solution::sol outside the span stays an error (solution.rs:25-44)");
+  }
+}
+
 int main(int argc, char** argv) {
   const bool api_only = argc > 1 && std::strcmp(argv[1], "--api-only") == 0;
   api_surface();
@@ -252,6 +299,7 @@ int main(int argc, char** argv) {
     backward_integration_works();
     dense_output_tests();
     example_programs_as_batches();
+    mass_matrix_hooks_and_extrapolation();
   }
   std::printf("%d checks, %d failed\n", g_checks, g_fail);
   return g_fail ? 1 : 0;
