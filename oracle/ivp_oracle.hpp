@@ -7,7 +7,8 @@
 // PARITY PINNING: the reference cannot be executed here, and its own tests are all
 // tolerance based (no golden step counts / bit patterns).  The oracle is therefore pinned
 // against every known-answer expectation those tests hold for this path (see
-// tests/test_oracle_pins.py, each citing tests/*.rs / tests/test_ivp.py line ranges), but
+// tests/test_oracle_pins.py, each citing tests/*.rs / tests/test_ivp.py line ranges, and
+// tests/test_reference_pytests.py, the reference's Python test files restated one by one), but
 // step-count parity is defined oracle-vs-GPU only: "parity unpinned at the bit level".
 //
 // Every function cites the reference file:line it follows.  Semantics mirrored from Rust:
