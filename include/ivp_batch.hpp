@@ -267,9 +267,10 @@ class Problem {
   // and, if n_events > 0 / has_jac, ivp_events(t, y, p, g) / ivp_jac(t, y, p, J row-major).
   // `has_mass`: the source also defines `ivp_mass(const double* p, double* M)` (IVP::mass, row-major n x n).
   static Problem from_cuda_source(std::string src, int n, int p = 0, int n_events = 0, bool has_jac = false,
-                                  bool has_mass = false) {
+                                  bool has_mass = false, bool has_solout = false) {
     Problem q;
-    q.src_ = std::move(src); q.n_ = n; q.p_ = p; q.n_events_ = n_events; q.has_jac_ = (has_jac ? 1 : 0) | (has_mass ? 2 : 0);
+    q.src_ = std::move(src); q.n_ = n; q.p_ = p; q.n_events_ = n_events;
+    q.has_jac_ = (has_jac ? 1 : 0) | (has_mass ? 2 : 0) | (has_solout ? 4 : 0);     // `ivp_solout`: see include/ivpb.h
     return q;
   }
   int n() const { return n_; }

@@ -96,6 +96,14 @@ impl OptionsBuilder {
     pub fn max_out(mut self, n: usize) -> Self { self.0.max_out = n; self }
     pub fn analytic_jac(mut self, b: bool) -> Self { self.0.analytic_jac = b; self }
     pub fn strict_fp(mut self, b: bool) -> Self { self.0.strict_fp = b; self }
+    pub fn max_segments(mut self, n: usize) -> Self { self.0.max_segments = n; self }
+    /// ivp `Options.mass_storage(MatrixStorage::Full)`: RADAU integrates `M y' = f` with the problem's `ivp_mass`.
+    pub fn mass_full(mut self, b: bool) -> Self { self.0.mass_full = b; self }
+    pub fn nind1(mut self, k: usize) -> Self { self.0.nind1 = Some(k); self }
+    pub fn nind2(mut self, k: usize) -> Self { self.0.nind2 = Some(k); self }
+    pub fn nind3(mut self, k: usize) -> Self { self.0.nind3 = Some(k); self }
+    /// The problem's own `SolOut` (`ivp_solout`) instead of `DefaultSolOut` (ivp: `Method::solve(.., Some(&mut solout))`).
+    pub fn user_solout(mut self, b: bool) -> Self { self.0.user_solout = b; self }
     pub fn build(self) -> Options { self.0 }
 }
 
@@ -129,10 +137,11 @@ impl Problem {
         if unsafe { sys::ivpb_builtin_problem(ctx.raw, id, &mut n, &mut p, &mut ne) } != sys::IVPB_OK { return Err(Error::Config(last_error(ctx.raw))); }
         Ok(Problem { handle: id, n: n as usize, p: p as usize, n_events: ne as usize })
     }
-    pub fn from_cuda_source(ctx: &Context, src: &str, n: usize, p: usize, n_events: usize, has_jac: bool, has_mass: bool) -> Result<Self, Error> {
+    pub fn from_cuda_source(ctx: &Context, src: &str, n: usize, p: usize, n_events: usize, has_jac: bool, has_mass: bool,
+                            has_solout: bool) -> Result<Self, Error> {
         let c = CString::new(src).map_err(|e| Error::Config(e.to_string()))?;
         let mut h = -1;
-        let rc = unsafe { sys::ivpb_nvrtc_problem(ctx.raw, c.as_ptr(), n as i32, p as i32, n_events as i32, (has_jac as i32) | ((has_mass as i32) << 1), &mut h) };
+        let rc = unsafe { sys::ivpb_nvrtc_problem(ctx.raw, c.as_ptr(), n as i32, p as i32, n_events as i32, (has_jac as i32) | ((has_mass as i32) << 1) | ((has_solout as i32) << 2), &mut h) };
         if rc != sys::IVPB_OK { return Err(Error::Config(last_error(ctx.raw))); }
         Ok(Problem { handle: h, n, p, n_events })
     }
