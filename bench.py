@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--strict", action="store_true", help="-fmad=false kernel variant (A/B)")
     ap.add_argument("--fast-implicit", action="store_true", help="RADAU / BDF workloads: FMA-contracted kernels (default: strict)")
     ap.add_argument("--no-zerocopy", action="store_true", help="e2e arm: staged H2D/D2H copies instead of mapped pinned buffers (A/B)")
+    ap.add_argument("--no-sort", action="store_true", help="RADAU / BDF: index order instead of the locality order of the ensemble (A/B)")
+    ap.add_argument("--sort", action="store_true", help="explicit methods: locality order too (A/B)")
     ap.add_argument("--jac-mode", type=int, default=0, help="implicit workloads: 0 finite differences, 1 analytic")
     args = ap.parse_args()
     from ivp_b200.dist import dist_env, reduce_time_and_count, weak_offset
@@ -228,7 +230,7 @@ def main():
     prob_name, y0_h, par_h, t0, tf = synth.ensemble(ens, Nper, offset=offset)
     problem = api.Problem.builtin(prob_name)
     flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0) | \
-        (api.IVPB_FLAG_NO_ZEROCOPY if args.no_zerocopy else 0) | (api.IVPB_FLAG_FAST_FP if args.fast_implicit else 0)
+        (api.IVPB_FLAG_NO_ZEROCOPY if args.no_zerocopy else 0) | (api.IVPB_FLAG_NO_SORT if args.no_sort else 0) | (api.IVPB_FLAG_SORT if args.sort else 0) | (api.IVPB_FLAG_FAST_FP if args.fast_implicit else 0)
     n_te = N_T_EVAL.get(args.workload, 0)
     opts = workload_options(args.workload, t0, tf, flags, args.jac_mode)
     mo = _abi.MarshalledOptions(opts, problem.n, problem.n_events)
@@ -387,7 +389,7 @@ def main():
                        "outputs": "final state + status + counters" + (f" + {n_te} t_eval samples" if n_te else "") +
                                   (" + event times" if ne else ""), "parallelism": f"trajectory-sharded x{world}",
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "schedule": "static" if args.static else "work-queue refill", "fp": "strict" if (args.strict or (method in ("RADAU", "BDF") and not args.fast_implicit)) else "fma"},
+                       "schedule": ("static" if args.static else "work-queue refill") + (", locality order" if (args.sort or (method in ("RADAU", "BDF") and not args.no_sort)) else ""), "fp": "strict" if (args.strict or (method in ("RADAU", "BDF") and not args.fast_implicit)) else "fma"},
             "accepted_steps_per_step": acc_all, "rejected_steps_rank0": int(nrejct.sum()),
             "status_success_frac_rank0": float(np.mean(status == 0)),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

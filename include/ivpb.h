@@ -108,6 +108,11 @@ typedef struct {
                                   ensembles lose step-count parity under any last-bit perturbation (VdP mu=1000: 73 % RADAU,
                                   97 % BDF with FMA) while the FMA build is only 17-29 % faster there.  The explicit methods
                                   default to the FMA build (2x faster; north-star parity 100 %) and take IVPB_FLAG_STRICT_FP. */
+#define IVPB_FLAG_NO_SORT 16u  /* RADAU / BDF: hand the trajectories out in index order instead of the locality order (a Morton
+                                  curve through the varying coordinates of y0 / params, so that the lanes of a warp hold
+                                  neighbouring initial conditions and diverge less; results are identical either way) */
+#define IVPB_FLAG_SORT 32u     /* explicit methods: use the locality order too (off by default there: small gain on the device,
+                                  a loss end to end with mapped host buffers, see ivpb_runtime.cu launch_shard) */
 #define IVPB_FLAG_NO_ZEROCOPY 4u /* ivpb_solve_batch: always stage through device buffers, even when the caller's
                                     buffers are page-locked (default: pinned y0 / params / per-trajectory results are
                                     read and written by the kernel directly over PCIe, overlapping the solve) */

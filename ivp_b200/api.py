@@ -32,6 +32,8 @@ IVPB_FLAG_STRICT_FP = 1
 IVPB_FLAG_NO_REFILL = 2
 IVPB_FLAG_NO_ZEROCOPY = 4
 IVPB_FLAG_FAST_FP = 8
+IVPB_FLAG_NO_SORT = 16
+IVPB_FLAG_SORT = 32
 
 #: Every symbol include/ivpb.h declares (checked by the CPU test-suite against the built library).
 ABI_SYMBOLS = [

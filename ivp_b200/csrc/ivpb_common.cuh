@@ -30,6 +30,8 @@ struct KArgs {
   const double* y0;      // [N][n] row-major
   const double* params;  // [N][p] row-major (may be null when p == 0)
   u64* queue;            // work-queue head (atomicAdd), zeroed before launch
+  const unsigned* perm;  // locality order (null = identity): queue position k integrates trajectory perm[k], so the lanes of a
+                         // warp hold neighbouring initial conditions and take (nearly) the same accept / reject / Newton paths
   double rtol[MAX_N], atol[MAX_N];   // scalar tolerances are broadcast by the host
   const double* rtol_ext;            // n > MAX_N with Tolerance::Vector: device arrays [n] (else null: rtol[0])
   const double* atol_ext;

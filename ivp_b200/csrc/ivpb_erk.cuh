@@ -1163,7 +1163,7 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
       }
       if (!active && idx < a.N) {
         active = true;
-        if (T.init(a, idx)) { T.finish(a); active = false; }
+        if (T.init(a, a.perm ? (i64)a.perm[idx] : idx)) { T.finish(a); active = false; }
       }
     }
     if (__ballot_sync(FULL, active) == 0u) {
@@ -1217,7 +1217,7 @@ __device__ __forceinline__ void run_schedule_warp(const KArgs& a) {
     }
     first = false;
     if (idx >= a.N) break;
-    if (!T.init(a, idx)) {
+    if (!T.init(a, a.perm ? (i64)a.perm[idx] : idx)) {
       while (!T.step(a)) {}
     }
     T.finish(a);

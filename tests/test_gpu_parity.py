@@ -934,3 +934,25 @@ def test_strict_build_reproduces_committed_golden_vectors():
             v = getattr(g, f)
             if v is not None and f"{name}/{f}" in gold:
                 assert np.array_equal(v, gold[f"{name}/{f}"], equal_nan=v.dtype.kind == "f"), (name, f)
+
+
+@pytest.mark.parametrize("wl,method,kw", [
+    ("vdp", Method.DOP853, dict(rtol=1e-8, atol=1e-8, t_eval=np.linspace(0.0, 100.0, 7))),
+    ("ball", Method.DOPRI5, dict(rtol=1e-8, atol=1e-10)),
+    ("cr3bp", Method.DOP853, dict(rtol=1e-10, atol=1e-12)),
+    ("robertson", Method.BDF, dict(rtol=1e-6, atol=1e-6)),
+    ("vdp_stiff", Method.RADAU, dict(rtol=1e-4, atol=1e-6, t_eval=np.linspace(0.0, 3000.0, 5))),
+])
+def test_locality_order_changes_nothing_but_the_schedule(wl, method, kw):
+    """The work queue hands the trajectories out along a Morton curve through the varying coordinates of y0 / params
+    (default for RADAU / BDF, IVPB_FLAG_SORT for the explicit methods).  Every trajectory's arithmetic is independent of
+    its neighbours, so all outputs are bit-identical to the index-order run."""
+    from ivp_b200.api import IVPB_FLAG_NO_SORT, IVPB_FLAG_SORT
+    prob, y0, par, t0, tf = synth.ensemble(wl, 9001)              # >= 4096: below that the order is not built
+    a = ib.solve_ivp_batch(prob, t0, tf, y0, par, Options(method=method, flags=IVPB_FLAG_SORT, **kw))
+    b = ib.solve_ivp_batch(prob, t0, tf, y0, par, Options(method=method, flags=IVPB_FLAG_NO_SORT, **kw))
+    for f in ("status", "counters", "t_final", "y_final", "h_next", "n_out", "t_out", "y_out", "ev_count", "ev_t", "ev_y"):
+        u, v = getattr(a, f), getattr(b, f)
+        assert (u is None) == (v is None)
+        if u is not None:
+            assert np.array_equal(u, v, equal_nan=u.dtype.kind == "f"), f
