@@ -393,7 +393,7 @@ def main():
             "accepted_steps_per_step": acc_all, "rejected_steps_rank0": int(nrejct.sum()),
             "status_success_frac_rank0": float(np.mean(status == 0)),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s_max / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers" + (", staged copies)" if args.no_zerocopy else
+                    "ms_per_step": e2e_s_max / e2e_steps * 1e3, "api": "ivpb_solve_batch (pinned host buffers" + (", staged copies)" if (args.no_zerocopy or args.sort or (method in ("RADAU", "BDF") and not args.no_sort)) else
                                                                   ", kernel reads/writes them over PCIe while integrating, t_eval samples included; event blocks staged)")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))

@@ -751,7 +751,11 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   // overlap the integration instead of bracketing it (north star: ~80 MB per step moved during a ~15 ms kernel
   // instead of ~1.5 ms of serial copies).  Only fields every trajectory writes in full take this route; sample
   // and event blocks (partially written, must read as zero elsewhere) and the dense log are staged as before.
-  const bool allow_zc = !(opt->flags & IVPB_FLAG_NO_ZEROCOPY);
+  // ... unless the shard is integrated in locality order (RADAU / BDF by default, launch_shard): rows would then cross
+  // PCIe out of order, which costs more than the two serial copies it saves (Robertson BDF e2e 27.6 ms mapped).
+  const bool ordered = (opt->flags & IVPB_FLAG_SORT) ||
+                       ((opt->method == IVPB_RADAU || opt->method == IVPB_BDF) && !(opt->flags & IVPB_FLAG_NO_SORT));
+  const bool allow_zc = !(opt->flags & IVPB_FLAG_NO_ZEROCOPY) && !ordered;
   auto mapped = [&](const void* hp) -> char* {
     if (!allow_zc || !hp) return nullptr;
     cudaPointerAttributes at;
