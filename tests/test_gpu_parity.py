@@ -345,6 +345,17 @@ def test_multi_device_context_matches_single_device():
     assert np.array_equal(st.cpu().numpy(), one.status)
     assert np.array_equal(cn.cpu().numpy().view(np.uint32), one.counters)
     assert np.array_equal(yf.cpu().numpy(), one.y_final) and np.array_equal(yo.cpu().numpy(), one.y_out)
+    # an implicit solve (locality order: each shard is sorted on its own device) and an explicit one that opts in
+    from ivp_b200.api import IVPB_FLAG_SORT
+    prob, y0, par, t0, tf = synth.ensemble("robertson", 20011)
+    for o in (Options(method=Method.BDF, rtol=1e-6, atol=1e-6), Options(method=Method.RADAU, rtol=1e-6, atol=1e-6, t_eval=[1.0, 1e4, 1e8])):
+        a, b = ib.solve_ivp_batch(prob, t0, tf, y0, par, o), ib.solve_ivp_batch(prob, t0, tf, y0, par, o, ctx=ctx)
+        for f in ("status", "counters", "t_final", "y_final", "n_out", "t_out", "y_out"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    prob, y0, par, t0, tf = synth.ensemble("vdp", 20011)
+    o = Options(method=Method.DOPRI5, rtol=1e-6, atol=1e-9, flags=IVPB_FLAG_SORT)
+    a, b = ib.solve_ivp_batch(prob, t0, 20.0, y0, par, o), ib.solve_ivp_batch(prob, t0, 20.0, y0, par, o, ctx=ctx)
+    assert np.array_equal(a.counters, b.counters) and np.array_equal(a.y_final, b.y_final)
 
 
 USER_VDP = r"""
