@@ -91,4 +91,29 @@ struct MassLinear4 : ProblemBase<MassLinear4, 4, 1, 0> {
   }
 };
 
+// fun_medazko at the reference's own size (tests/test_helpers.py:54-80 with n = 200 grid points => 400 states), for the golden
+// numbers of tests/test_ivp.py:245-269 and tests/test_stiff.py:147-183.  (The device kernels stop at n = 84 / 118; this pins
+// the ORACLE's RADAU / BDF / LU / finite-difference Jacobian against the reference's published MEDAKZO values.)
+struct Medakzo400 : ProblemBase<Medakzo400, 400, 0, 0> {
+  static constexpr int NG = 200;
+  static double z(double t, const double* y, int m) {
+    if (m == 0) return t <= 5.0 ? 2.0 : 0.0;
+    if (m == 1) return 0.0;
+    if (m == 2 * NG + 2) return y[2 * NG - 2];
+    return y[m - 2];
+  }
+  void ode(double t, const double* y, double* f) const {
+    const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+    for (int i = 0; i < 2 * NG; ++i) {
+      const int j = i / 2 + 1;
+      const double u = z(t, y, 2 * j), v = z(t, y, 2 * j + 1);
+      if (i & 1) { f[i] = -k * v * u; continue; }
+      const double w = (double)j * d - 1.0;
+      const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+      const double zp = z(t, y, 2 * j + 2), zm = z(t, y, 2 * j - 2);
+      f[i] = alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
+    }
+  }
+};
+
 }  // namespace oracle

@@ -315,3 +315,24 @@ def test_oracle_reproduces_committed_golden_vectors(oracle):
             v = getattr(o, f)
             if v is not None:
                 assert np.array_equal(v, gold[f"{name}/{f}"], equal_nan=v.dtype.kind == "f"), (name, f)
+
+
+# reference tests/test_ivp.py:245-269, tests/test_stiff.py:147-183 (test_integration_sparse_difference*): MEDAKZO on 200 grid
+# points (n = 400) with the reference's golden values.  The reference passes jac_sparsity to its Python binding's finite
+# differences; the Jacobian VALUES are the same dense forward differences of src/ivp.rs:67-107 the oracle uses.
+@pytest.mark.parametrize("method", IMPLICIT)
+def test_medakzo_400_golden_values(oracle, method):
+    n = 200
+    y0 = np.zeros(2 * n)
+    y0[1::2] = 1
+    s = oracle.solve_batch(108, 0.0, 20.0, [y0], None, Options(method=method, max_out=4096))      # default rtol 1e-3, atol 1e-6
+    assert s.status[0] == Status.Success and s.t_out[0, 0] == 0.0
+    y = s.y_final[0]
+    np.testing.assert_allclose(y[78], 0.233994e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[79], 0, atol=1e-3)
+    np.testing.assert_allclose(y[148], 0.359561e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[149], 0, atol=1e-3)
+    np.testing.assert_allclose(y[198], 0.117374129e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[199], 0.6190807e-5, atol=1e-3)
+    np.testing.assert_allclose(y[238], 0, atol=1e-3)
+    np.testing.assert_allclose(y[239], 0.9999997, rtol=1e-2)
