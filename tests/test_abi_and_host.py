@@ -236,3 +236,56 @@ def test_scipy_style_front_end_argument_handling():
     assert has and cfgs[0].terminal_count == 1 and int(cfgs[0].direction) < 0
     cfgs, has = scipy_api._event_configs(None, 1)
     assert not has and cfgs[0].terminal_count is None
+
+
+def test_options_struct_layout_matches_header():
+    """Field order of the ctypes `ivpb_options` mirror == include/ivpb.h (fields were appended for mass matrices and hooks)."""
+    src = open(os.path.join(ROOT, "include", "ivpb.h")).read()
+    body = src[src.index("typedef struct {", src.index("Mirrors `Options`")):]
+    body = re.sub(r"/\*.*?\*/", "", body[: body.index("} ivpb_options;")], flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct {", "").strip()
+        if not decl:
+            continue
+        first, *rest = decl.split(",")
+        names.append(re.findall(r"(\w+)\s*$", first.strip())[0])
+        names += [r.strip().lstrip("*") for r in rest]
+    assert names == [f[0] for f in _abi.IvpbOptions._fields_]
+
+
+def test_new_option_fields_are_marshalled():
+    from ivp_b200.api import IVPB_FLAG_NO_SORT, IVPB_FLAG_SORT
+    o = _abi.MarshalledOptions(Options(method=Method.RADAU, mass_storage="Full", nind2=1, user_solout=True,
+                                       flags=IVPB_FLAG_NO_SORT), 3, 0).struct
+    assert (o.mass_storage, o.nind1, o.nind2, o.nind3, o.user_solout, o.flags) == (1, -1, 1, -1, 1, 16)
+    d = _abi.MarshalledOptions(Options(), 3, 0).struct
+    assert (d.mass_storage, d.nind1, d.nind2, d.nind3, d.user_solout) == (0, -1, -1, -1, 0) and IVPB_FLAG_SORT == 32
+    with pytest.raises(ValueError, match="mass_storage"):
+        _abi.MarshalledOptions(Options(mass_storage="Banded"), 3, 0)
+
+
+def test_nvrtc_compiles_mass_matrix_and_solout_hooks_without_gpu():
+    """has_jac bit 1 (`ivp_mass`) and bit 2 (`ivp_solout`): the adaptor and the K_USER / mass kernels compile for sm_100a."""
+    src = USER_VDP + """
+__device__ void ivp_mass(const double* p, double* M) { M[0] = 2.0; M[1] = 0.5; M[2] = 0.0; M[3] = 1.0; }
+template <class Interp, class Emit>
+__device__ int ivp_solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit) {
+  if (!dense.valid()) { emit(x, y); return 0; }
+  double yi[2];
+  dense.eval(0.5 * (xold + x), yi);
+  if (yi[0] < 0.0) { y[0] = -y[0]; state[0] += 1.0; return 2; }
+  return y[0] > 10.0 ? 1 : 0;
+}
+"""
+    for method in (0, 1, 2, 3, 4, 5):                      # feature 4 = K_USER: the hook in every solver
+        size, log = _nvrtc_compile(src, 2, 1, 0, 4, method, 4, 1 if method >= 4 else 0)
+        assert size > 10000, log
+    for feat in (0, 1):                                     # RADAU with the mass matrix (strict and FMA builds)
+        for strict in (0, 1):
+            size, log = _nvrtc_compile(src, 2, 1, 0, 2, 4, feat, strict)
+            assert size > 10000, log
+    five = ("__device__ void ivp_ode(double t, const double* y, const double* p, double* d) { for (int i = 0; i < 5; ++i) d[i] = -y[i]; }\n"
+            "__device__ void ivp_mass(const double* p, double* M) { for (int i = 0; i < 25; ++i) M[i] = (i % 6 == 0) ? 1.0 + i : 0.1; }")
+    size, log = _nvrtc_compile(five, 5, 0, 0, 2, 4, 1, 1)   # n = 5: the mass matrix is the fifth shared-memory matrix
+    assert size > 10000, log
