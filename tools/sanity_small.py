@@ -25,4 +25,11 @@ run("cr3bp", 64, 1.0, method=Method.RADAU, rtol=1e-6, atol=1e-8)
 run("cr3bp", 64, 1.0, method=Method.BDF, rtol=1e-6, atol=1e-8)
 run("medakzo", 5, 0.5, method=Method.RADAU, rtol=1e-5, atol=1e-7)
 run("medakzo", 5, 0.5, method=Method.BDF, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_FAST_FP)
+run("robertson_dae", 64, 1e3, method=Method.RADAU, rtol=1e-6, atol=1e-10, mass_storage="Full")          # mass matrix
+run("mass_linear3", 64, None, method=Method.RADAU, rtol=1e-8, atol=1e-11, mass_storage="Full", jac_mode=1)
+for m in (Method.DOPRI5, Method.RADAU, Method.BDF):                                                       # SolOut hooks
+    kw = dict(first_step=1e-3) if m == Method.RK4 else dict(rtol=1e-8, atol=1e-10)
+    g = run("ball_bounce", 64, None, method=m, user_solout=True, max_out=48, **kw)
+    print("  bounces", int(g.n_out.min()) - 1, "..", int(g.n_out.max()) - 1)
+run("robertson", 5000, 1e3, method=Method.BDF, rtol=1e-6, atol=1e-6)                                      # locality order (N >= 4096)
 print("sanity ok")
