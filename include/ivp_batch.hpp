@@ -165,6 +165,7 @@ struct ContinuousOutput {
   std::shared_ptr<ivpb_ctx> ctx;
   int64_t index = 0;
   int n = 0;
+  uint64_t generation = 0;     // ivpb_dense_generation at solve time: a later dense solve invalidates this handle (IVPB_ERR_CONFIG)
 };
 
 // ---- Solution (reference src/solve/solution.rs:7-97) -------------------------------------------
@@ -180,7 +181,7 @@ struct Solution {
   std::optional<std::pair<Float, Float>> sol_span() const {
     if (!continuous_sol) return std::nullopt;
     double a = 0, b = 0; int32_t m = 0;
-    if (ivpb_dense_span(continuous_sol->ctx.get(), continuous_sol->index, 1, &a, &b, &m) != IVPB_OK || m <= 0) return std::nullopt;
+    if (ivpb_dense_span(continuous_sol->ctx.get(), continuous_sol->generation, continuous_sol->index, 1, &a, &b, &m) != IVPB_OK || m <= 0) return std::nullopt;
     return std::make_pair(a, b);
   }
   std::vector<std::vector<Float>> sol_many(const std::vector<Float>& ts) const {
@@ -193,7 +194,7 @@ struct Solution {
     std::vector<int64_t> tr(ts.size(), continuous_sol->index);
     std::vector<Float> y(ts.size() * (size_t)n);
     std::vector<int32_t> ok(ts.size());
-    if (ivpb_dense_eval(continuous_sol->ctx.get(), (int64_t)ts.size(), tr.data(), ts.data(), y.data(), ok.data()) != IVPB_OK)
+    if (ivpb_dense_eval(continuous_sol->ctx.get(), continuous_sol->generation, n, (int64_t)ts.size(), tr.data(), ts.data(), y.data(), ok.data()) != IVPB_OK)
       throw InterpolationError(ivpb_last_error(continuous_sol->ctx.get()));
     std::vector<std::vector<Float>> out(ts.size());
     for (size_t k = 0; k < ts.size(); ++k) {
@@ -210,7 +211,7 @@ struct Solution {
     std::vector<Float> y((size_t)n);
     int32_t ok = 0;
     const int64_t tr = continuous_sol->index;
-    if (ivpb_dense_eval_extrapolate(continuous_sol->ctx.get(), 1, &tr, &t, y.data(), &ok) != IVPB_OK || !ok) return std::nullopt;
+    if (ivpb_dense_eval_extrapolate(continuous_sol->ctx.get(), continuous_sol->generation, n, 1, &tr, &t, y.data(), &ok) != IVPB_OK || !ok) return std::nullopt;
     return y;
   }
   // batched-solve additions
@@ -364,7 +365,7 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
     const uint32_t* c = &counters[6 * i];
     s.nfev = c[0]; s.njev = c[1]; s.nlu = c[2]; s.nstep = c[3]; s.naccpt = c[4]; s.nrejct = c[5];
     s.h_next = h_next[i];
-    if (options.dense_output) s.continuous_sol = ContinuousOutput{ctx.shared(), (int64_t)i, n};
+    if (options.dense_output) s.continuous_sol = ContinuousOutput{ctx.shared(), (int64_t)i, n, ivpb_dense_generation(ctx.get())};
     const size_t m = std::min<size_t>((size_t)std::max(n_out[i], 0), cap);
     s.truncated = (size_t)std::max(n_out[i], 0) > cap;
     s.t.assign(&t_out[i * cap], &t_out[i * cap] + m);

@@ -180,7 +180,10 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
 
 /* Same solve with DEVICE buffers resident on the context's first device, enqueued on `stream`
  * (a cudaStream_t, may be NULL = default stream); returns after enqueueing. rtol/atol/t_eval/event
- * config in `opt` stay host pointers (small, copied to constant-like device storage). */
+ * config in `opt` stay host pointers (small, copied to constant-like device storage).
+ * One solve is in flight per context: a call enqueued on another stream starts on the device after the previous call of
+ * the same context has finished (the per-device work-queue counter and staging buffers are shared; the runtime orders the
+ * calls with an event).  Use one context per stream for solves that should overlap.  A context is not thread-safe. */
 int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_t N, double t0,
                             double tf, const double* d_y0, const double* d_params,
                             const ivpb_outputs* d_out, void* stream);
@@ -190,17 +193,26 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
  * had dense_output = 1.  Query q: trajectory traj[q] (index into that batch), time ts[q]; y[q][n] receives the
  * interpolated state, ok[q] = 1 if a stored segment covers ts[q] within 1e-12 (first match in step order, like
  * the reference's linear search), else 0 and y[q] is untouched.  All pointers are HOST pointers. */
-int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok);
+int ivpb_dense_eval(ivpb_ctx* ctx, uint64_t generation, int n, int64_t n_query, const int64_t* traj, const double* ts,
+                    double* y, int32_t* ok);
+/* Which dense log the context retains: a counter incremented by every dense_output solve (0 = none yet).  The three
+ * dense calls take the generation the caller's Solution belongs to and its state size n and fail with IVPB_ERR_CONFIG
+ * when the retained log is a different one (a newer dense solve replaced it) or has another state size -- so a stale
+ * Solution can neither read someone else's trajectory nor overrun its y buffer (n doubles per query).  generation = 0
+ * skips the identity check ("whatever is retained"); n is always checked.  The log lives in buffers of its own: solves
+ * without dense_output, on either entry point, leave it intact. */
+uint64_t ivpb_dense_generation(const ivpb_ctx* ctx);
 /* ContinuousOutput::evaluate_extrapolate (src/solve/cont.rs:91-150; what the reference's Python OdeSolution.__call__
  * uses, src/python/solution.rs:41,116): as ivpb_dense_eval, but a time outside every stored step is answered by the
  * FIRST segment when it lies below that segment's lower edge and by the LAST segment when it lies above that one's
  * upper edge (the reference's rule, independent of the direction of integration).  ok[q] = 0 only for a trajectory
  * without segments. */
-int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y,
-                                int32_t* ok);
+int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, uint64_t generation, int n, int64_t n_query, const int64_t* traj,
+                                const double* ts, double* y, int32_t* ok);
 /* Solution::sol_span for trajectories [first, first + count): t_start = first.xold, t_end = last.xold + last.h
  * (src/solve/cont.rs:67-76); n_seg = segments stored (0 => no span). */
-int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg);
+int ivpb_dense_span(ivpb_ctx* ctx, uint64_t generation, int64_t first, int64_t count, double* t_start, double* t_end,
+                    int32_t* n_seg);
 
 /* Pinned host memory for y0 / params / outputs: ivpb_solve_batch maps such buffers into the kernel (zero-copy,
  * see IVPB_FLAG_NO_ZEROCOPY) or, for the staged fields, copies at full PCIe rate.  Pageable buffers work too,

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -40,7 +41,7 @@ ABI_SYMBOLS = [
     "ivpb_create", "ivpb_destroy", "ivpb_last_error", "ivpb_device_count", "ivpb_builtin_problem",
     "ivpb_nvrtc_problem", "ivpb_solve_batch", "ivpb_solve_batch_device", "ivpb_host_alloc", "ivpb_host_free",
     "ivpb_launch_count", "ivpb_measure_fp64_peak", "ivpb_version", "ivpb_dense_eval", "ivpb_dense_span",
-    "ivpb_dense_eval_extrapolate",
+    "ivpb_dense_eval_extrapolate", "ivpb_dense_generation",
 ]
 
 
@@ -82,11 +83,13 @@ def load_library():
     L.ivpb_measure_fp64_peak.argtypes = [vp, _abi.c_double_p]
     L.ivpb_version.restype = C.c_char_p
     L.ivpb_dense_eval.restype = C.c_int
-    L.ivpb_dense_eval.argtypes = [vp, C.c_int64, _abi.c_int64_p, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
+    L.ivpb_dense_eval.argtypes = [vp, C.c_uint64, C.c_int, C.c_int64, _abi.c_int64_p, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
+    L.ivpb_dense_generation.restype = C.c_uint64
+    L.ivpb_dense_generation.argtypes = [vp]
     L.ivpb_dense_eval_extrapolate.restype = C.c_int
     L.ivpb_dense_eval_extrapolate.argtypes = L.ivpb_dense_eval.argtypes
     L.ivpb_dense_span.restype = C.c_int
-    L.ivpb_dense_span.argtypes = [vp, C.c_int64, C.c_int64, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
+    L.ivpb_dense_span.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
     _lib = L
     return L
 
@@ -99,7 +102,9 @@ class Problem:
                  has_jac: bool = False):
         self.handle, self.n, self.p, self.n_events, self.name = handle, n, p, n_events, name
         self.cuda_src, self.has_jac = cuda_src, has_jac
-        self._ctx_handles = {}
+        # NVRTC handle per context, keyed by the Context object itself (weakly): an id() would be reused by CPython once a
+        # context has been collected, handing a new context a stale handle
+        self._ctx_handles = weakref.WeakKeyDictionary()
 
     @staticmethod
     def builtin(name_or_id) -> "Problem":
@@ -119,16 +124,22 @@ class Problem:
         return Problem(-1, n, p, n_events, "user", cuda_src=src, has_jac=int(bool(has_jac)) | (2 if has_mass else 0) | (4 if has_solout else 0))
 
     def resolve(self, ctx: "Context") -> int:
-        if self.cuda_src is None:
+        if self.cuda_src is None and self.n > 0:
             return self.handle
-        key = id(ctx)
+        key = ctx
         if key not in self._ctx_handles:
             h = C.c_int32()
-            rc = ctx.lib.ivpb_nvrtc_problem(ctx.ptr, self.cuda_src.encode(), self.n, self.p, self.n_events,
+            rc = ctx.lib.ivpb_nvrtc_problem(ctx.ptr, self.cuda_src.encode() if self.cuda_src else None, self.n, self.p, self.n_events,
                                             int(self.has_jac), C.byref(h))
             ctx.check(rc)
             self._ctx_handles[key] = h.value
         return self._ctx_handles[key]
+
+
+    @staticmethod
+    def empty(n_events: int = 0) -> "Problem":
+        """The reference's empty state vector (`y0.is_empty()`, src/solve/solve_ivp.rs:148-176): nothing to integrate."""
+        return Problem(-1, 0, 0, n_events, "empty", cuda_src=None)
 
 
 def builtin(name_or_id) -> Problem:
@@ -183,7 +194,11 @@ class Context:
         return v.value
 
     # -- dense output (Solution::sol on the device) ------------------------------------------------
-    def dense_eval(self, traj: np.ndarray, ts: np.ndarray, n: int, extrapolate: bool = False):
+    def dense_generation(self) -> int:
+        """Identity of the retained dense log (0 = none); BatchSolution remembers it and every dense call checks it."""
+        return int(self.lib.ivpb_dense_generation(self.ptr))
+
+    def dense_eval(self, traj: np.ndarray, ts: np.ndarray, n: int, extrapolate: bool = False, generation: int = 0):
         """ivpb_dense_eval (or ivpb_dense_eval_extrapolate: ContinuousOutput::evaluate_extrapolate, cont.rs:91-150) on
         the log retained by the last dense_output solve: (y[Q, n], ok[Q])."""
         traj = np.ascontiguousarray(np.asarray(traj, dtype=np.int64).reshape(-1))
@@ -193,13 +208,13 @@ class Context:
         y = np.zeros((ts.size, n))
         ok = np.zeros(ts.size, dtype=np.int32)
         fn = self.lib.ivpb_dense_eval_extrapolate if extrapolate else self.lib.ivpb_dense_eval
-        self.check(fn(self.ptr, ts.size, _abi.ptr(traj), _abi.ptr(ts), _abi.ptr(y), _abi.ptr(ok)))
+        self.check(fn(self.ptr, int(generation), int(n), ts.size, _abi.ptr(traj), _abi.ptr(ts), _abi.ptr(y), _abi.ptr(ok)))
         return y, ok.astype(bool)
 
-    def dense_span(self, first: int, count: int):
+    def dense_span(self, first: int, count: int, generation: int = 0):
         t0, t1 = np.zeros(count), np.zeros(count)
         m = np.zeros(count, dtype=np.int32)
-        self.check(self.lib.ivpb_dense_span(self.ptr, int(first), int(count), _abi.ptr(t0), _abi.ptr(t1), _abi.ptr(m)))
+        self.check(self.lib.ivpb_dense_span(self.ptr, int(generation), int(first), int(count), _abi.ptr(t0), _abi.ptr(t1), _abi.ptr(m)))
         return t0, t1, m
 
     # -- host buffers ---------------------------------------------------------------------------
@@ -271,7 +286,9 @@ def solve_ivp_batch(problem, t0: float, tf: float, y0, params=None, options: Opt
                                     seg_cap=mo.seg_cap, n_cont=n_cont)
     if N > 0:
         ctx.solve_host(problem, t0, tf, y0, par, mo, st)
-    return BatchSolution(n=problem.n, n_events=problem.n_events, extras={"ctx": ctx, "dense": mo.seg_cap > 0 and N > 0},
+    dense = mo.seg_cap > 0 and N > 0
+    return BatchSolution(n=problem.n, n_events=problem.n_events,
+                         extras={"ctx": ctx, "dense": dense, "dense_generation": ctx.dense_generation() if dense else 0},
                          **{k: arrays.get(k) for k in _abi.OUTPUT_FIELDS})
 
 

@@ -44,6 +44,7 @@ struct KArgs {
   int max_events, jac_mode;
   int zero_tail;         // t_out / y_out are the caller's mapped host buffers: `finish` zero-fills the slots a trajectory
                          // left unwritten (nobody memsets them), so the whole row is defined when the kernel ends
+  int block_sync;        // thread-per-trajectory kernels: the warps of a block start every attempted step together (run_schedule)
   int vec_io;            // y0 / y_final rows are 16-byte aligned: move them as double2 (LDG.128 / STG.128)
   int nind1, nind2, nind3;   // RADAU with a mass matrix: resolved DAE partition (radau.rs:210-245); nind1 + nind2 + nind3 == n
   double newton_tol;     // implicit methods: Newton stopping tolerance (radau.rs:198-205, bdf.rs:174-184), host-computed

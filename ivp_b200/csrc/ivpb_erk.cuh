@@ -19,6 +19,7 @@
 #include "dop853_tableau.cuh"
 #include "ivpb_fastmath.cuh"
 #include "ivpb_libm_pow.cuh"
+#include "ivpb_exact.cuh"
 
 namespace ivpb {
 
@@ -63,24 +64,24 @@ template <int METHOD, int N>
 __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (&c)[MethodTraits<METHOD>::NC][N],
                                            double xold, double h) {
   if constexpr (METHOD == M_DOP853) {          // dop853.rs:659-670
-    const double s = (xi - xold) / h, s1 = 1.0 - s;
+    const double s = ex::div(xi - xold, h), s1 = 1.0 - s;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double conpar = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, c[7][i], c[6][i]), c[5][i]), c[4][i]);
       yi[i] = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, IVPB_MA(s1, conpar, c[3][i]), c[2][i]), c[1][i]), c[0][i]);
     }
   } else if constexpr (METHOD == M_DOPRI5) {   // dopri5.rs:467-478
-    const double th = (xi - xold) / h, th1 = 1.0 - th;
+    const double th = ex::div(xi - xold, h), th1 = 1.0 - th;
 #pragma unroll
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(th, IVPB_MA(th1, IVPB_MA(th, IVPB_MA(th1, c[4][i], c[3][i]), c[2][i]), c[1][i]), c[0][i]);
   } else if constexpr (METHOD == M_RK23) {     // rk23.rs:313-321
-    const double xc = (xi - xold) / h, x2 = xc * xc, x3 = x2 * xc;
+    const double xc = ex::div(xi - xold, h), x2 = xc * xc, x3 = x2 * xc;
 #pragma unroll
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(h, IVPB_MA(c[3][i], x3, IVPB_MA(c[2][i], x2, c[1][i] * xc)), c[0][i]);
   } else if constexpr (METHOD == M_RADAU) {    // radau.rs:798-809
-    const double s = (xi - (xold + h)) / h;
+    const double s = ex::div(xi - (xold + h), h);
     const double C1M1 = -0.8449489742783178, C2M1 = -0.3550510257216822;
 #pragma unroll
     for (int i = 0; i < N; ++i) yi[i] = c[0][i] + s * (c[1][i] + (s - C2M1) * (c[2][i] + (s - C1M1) * c[3][i]));
@@ -106,7 +107,7 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
       yi[i] = sum;
     }
   } else {                                      // rk4.rs:229-244 (cubic Hermite, cont = [y_old, k4 stage, f_new, y_new])
-    const double t = (xi - xold) / h, t2 = t * t, t3 = t2 * t;
+    const double t = ex::div(xi - xold, h), t2 = t * t, t3 = t2 * t;
     const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
     const double h01 = -2.0 * t3 + 3.0 * t2, h11 = t3 - t2;
 #pragma unroll
@@ -249,12 +250,13 @@ __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const doub
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
-    qf[i] = L::valid(i) ? f0[i] / sk : 0.0;
-    qy[i] = L::valid(i) ? y[i] / sk : 0.0;
+    const ex::Recip rsk = ex::recip(sk);       // ex::div == `/` bit for bit (ivpb_exact.cuh), one reciprocal for both
+    qf[i] = L::valid(i) ? ex::div(f0[i], rsk) : 0.0;
+    qy[i] = L::valid(i) ? ex::div(y[i], rsk) : 0.0;
   }
   // interleaved in the reference (dnf, dny in one loop); the two sums are independent
   const double dnf = L::sumsq(qf), dny = L::sumsq(qy);
-  double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
+  double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : ex::sqrt(ex::div(dny, dnf)) * 0.01;
   if (hh > fabs(hmax)) hh = fabs(hmax);
   hh = fabs(hh) * signum(posneg);
   double y1[N], f1[N];
@@ -264,12 +266,12 @@ __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const doub
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
-    qf[i] = L::valid(i) ? (f1[i] - f0[i]) / sk : 0.0;
+    qf[i] = L::valid(i) ? ex::div(f1[i] - f0[i], sk) : 0.0;
   }
   double der2 = L::sumsq(qf);
-  der2 = sqrt(der2) / fabs(hh);
-  const double der12 = fmax(fabs(der2), sqrt(dnf));
-  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(0.01 / der12, 1.0 / (double)IORD);
+  der2 = ex::div(ex::sqrt(der2), fabs(hh));
+  const double der12 = fmax(fabs(der2), ex::sqrt(dnf));
+  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(ex::div(0.01, der12), 1.0 / (double)IORD);
   const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));
   return fabs(hf) * signum(posneg);
 }
@@ -755,7 +757,8 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       const double erri = IVPB_MA(-D853_BHH[2], k[2][i], IVPB_MA(-D853_BHH[1], k[8][i], IVPB_MA(-D853_BHH[0], k[0][i], k[3][i])));
       IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], D853_LIN_COEF[1], k, i)
 #ifdef IVPB_STRICT
-      const double q2 = erri / sk, q1 = e8 / sk;         // dop853.rs:412,423
+      const ex::Recip rsk = ex::recip(sk);               // dop853.rs:412,423: two correctly rounded quotients, one reciprocal
+      const double q2 = ex::div(erri, rsk), q1 = ex::div(e8, rsk);
 #else
       const double rsk = fm::rcp(sk);                      // one reciprocal shared by both norms
       const double q2 = erri * rsk, q1 = e8 * rsk;
@@ -767,12 +770,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     double deno = IVPB_MA(0.01, err2, err);
     if (deno <= 0.0) deno = 1.0;
 #ifdef IVPB_STRICT
-    err = fabs(h) * err * sqrt(1.0 / ((double)NG * deno));
+    err = fabs(h) * err * ex::sqrt(ex::div(1.0, (double)NG * deno));
     const double fac11 = ivpb_libm_pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
     // facold^beta == 1 exactly (beta = 0), so fac = fac11 (dop853.rs:434)
-    const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
-    double hnew = h / fac;
-    const double hrej = h / fmin(facc1, fac11 / safe);       // dop853.rs:645
+    const double fmin1 = fmin(facc1, ex::div(fac11, safe));
+    const double fac = fmax(facc2, fmin1);
+    double hnew = ex::div(h, fac);
+    // dop853.rs:645: the rejected step is h / min(facc1, fac11 / safe).  Same quotient whenever the lower clamp is idle
+    // (always after a rejection: err > 1 => fac11 >= 1 > facc2 * safe), so the second division is almost never executed.
+    const double hrej = (fac == fmin1) ? hnew : ex::div(h, fmin1);
 #else
     // Same controller written with the reciprocal step factor 1/fac = safe * err^(-1/8), which needs
     // multiplications only (see ivpb_fastmath.cuh): hnew = h * clamp(safe/fac11, 1/facc1, 1/facc2).
@@ -793,7 +799,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #pragma unroll
         for (int i = 0; i < N; ++i) { sd1[i] = k[3][i] - k[2][i]; sd2[i] = k[4][i] - y1[i]; }
         const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
-        if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
+        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden));
         if (hlamb > 6.1) {
           nonstiff = 0; iasti += 1;
           if (iasti == 15) { status = ST_STIFF; return true; }
@@ -926,7 +932,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       k[3][i] = acc * h;
 #ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
-      const double q = k[3][i] / sk;
+      const double q = ex::div(k[3][i], sk);
 #else
       const double sk = fma(rt(a, i), fm::maxsel(fabs(y[i]), fabs(y1[i])), at(a, i));
       const double q = k[3][i] * fm::rcp(sk);
@@ -935,11 +941,11 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     }
     double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = sqrt(err / (double)NG);
+    err = ex::sqrt(ex::div(err, (double)NG));
     const double fac11 = ivpb_libm_pow(err, expo1);
-    double fac = fac11 / ivpb_libm_pow(facold, beta);
-    fac = fmax(facc2, fmin(facc1, fac / safe));
-    double hnew = h / fac;
+    double fac = ex::div(fac11, ivpb_libm_pow(facold, beta));
+    fac = fmax(facc2, fmin(facc1, ex::div(fac, safe)));
+    double hnew = ex::div(h, fac);
     const bool accept = err <= 1.0;
 #else
     // Same PI controller in log2 space: err = sqrt(e2), so log2(err) = log2(e2)/2 needs no square root, and
@@ -970,7 +976,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
           sd2[i] = y1[i] - ysti;
         }
         const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
-        if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
+        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden));
         if (hlamb > 3.25) {
           nonstiff = 0; iasti += 1;
           if (iasti == 15) { status = ST_STIFF; return true; }
@@ -1002,7 +1008,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
     } else {
 #ifdef IVPB_STRICT
-      hnew = h / fmin(facc1, fac11 / safe);
+      hnew = ex::div(h, fmin(facc1, ex::div(fac11, safe)));
 #else
       hnew = h * fm::maxsel(safe * fm::exp2_fast(-expo1 * lerr), 0.2);
 #endif
@@ -1040,7 +1046,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       const double ye = h * IVPB_MA(e4, k4[i], IVPB_MA(e3, k3[i], IVPB_MA(e2, k2[i], e1 * k1[i])));
       const double tol = IVPB_MA(rt(a, i), fmax(fabs(yt[i]), fabs(y[i])), at(a, i));
 #ifdef IVPB_STRICT
-      const double q = ye / tol;
+      const double q = ex::div(ye, tol);
 #else
       const double q = ye * fm::rcp(tol);
 #endif
@@ -1048,7 +1054,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     }
     double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = sqrt(err / (double)NG);
+    err = ex::sqrt(ex::div(err, (double)NG));
     const double sfac = safe * ivpb_libm_pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
     const bool accept = err <= 1.0;
 #else
@@ -1137,11 +1143,19 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #define IVPB_BATCH_DEN 1      // ensembles: 1/2 -> 89 ms, 3/4 -> 80 ms, 1/1 -> 62 ms (Robertson, 2^18 trajectories)
 #endif
 // Generic persistent scheduler: Traj provides init(a, idx) -> done, step(a) -> done, finish(a).
+//
+// KArgs::block_sync (block-synchronous trips): the warps of a block start every attempted step together
+// (__syncthreads_or doubles as the loop test).  The step code of the larger systems is far bigger than the
+// instruction caches (CR3BP DOP853 with dense output: 50 KB hot loop in the FMA build, 110 KB in the strict one, against a
+// 32 KB L1.5 I$), so warps that drift apart each stream the whole loop from L2 on their own (ncu: "no instruction"
+// is the top stall, 5.4 per issue in the strict kernel); in lock step one warp's fetch serves all of them.  Results are
+// unaffected: only the interleaving of independent trajectories changes.
 template <class Traj>
 __device__ __forceinline__ void run_schedule(const KArgs& a) {
   Traj T;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const bool bsync = a.block_sync != 0;        // uniform over the grid
   bool active = false, exhausted = false;
   for (;;) {
     // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp).
@@ -1166,13 +1180,20 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         if (T.init(a, a.perm ? (i64)a.perm[idx] : idx)) { T.finish(a); active = false; }
       }
     }
-    if (__ballot_sync(FULL, active) == 0u) {
+    if (bsync) {
+      // block-uniform decisions: leave when no lane of the block has work and every warp has seen the end of the queue
+      if (!__syncthreads_or(active ? 1 : 0)) {
+        if (!__syncthreads_or(exhausted ? 0 : 1)) break;
+        continue;
+      }
+    } else if (__ballot_sync(FULL, active) == 0u) {
       if (exhausted) break;
       continue;
     }
     // ---- hot loop: every lane that owns a trajectory attempts steps until one of them finishes.  Nothing of
     // the refill logic is live in here.
     bool done = false;
+    bool any;
     do {
       bool run = active;
       if constexpr (Traj::BATCH_HEAVY) {
@@ -1185,7 +1206,8 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         run = active && (!hv || nh * IVPB_BATCH_DEN >= na * IVPB_BATCH_NUM);
       }
       if (run) done = T.step(a);
-    } while (!__any_sync(FULL, done));
+      any = bsync ? (__syncthreads_or(done ? 1 : 0) != 0) : __any_sync(FULL, done);
+    } while (!any);
     if (done) { T.finish(a); active = false; }
   }
 }

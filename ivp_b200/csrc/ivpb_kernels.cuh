@@ -25,7 +25,7 @@ namespace ivpb {
 #define IVPB_MB_BIG 1
 #endif
 template <class Prob, int METHOD, int FEAT>
-__global__ void __launch_bounds__(IVPB_BLOCK, (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__((Prob::N > 4 ? 2 * IVPB_BLOCK : IVPB_BLOCK), (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
   erk_body<Prob, METHOD, FEAT>(a);
 }
 

@@ -84,9 +84,13 @@ struct Device {
   cudaStream_t stream = nullptr;
   u64* queue = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
+  cudaEvent_t ev_last = nullptr;    // end of the most recent solve enqueued on this device: the per-device queue counter,
+                                    // t_eval / tolerance staging and sort buffers are shared, so solves on one context are
+                                    // serialised on the device even when the caller hands in different streams
   Buf y0, params, t_eval, tol_ext, scratch, out[OUT_FIELDS];
   Buf sort_keys, sort_vals, sort_tmp, sort_minmax;   // locality order of the shard (locality_order)
   Buf q_traj, q_ts, q_y, q_ok;      // ivpb_dense_eval query staging (grow-only)
+  Buf dense_nseg, dense_segx, dense_segc;   // the retained dense log of this device's shard (never shared with dev.out[])
 };
 
 // bytes per trajectory of every output field (include/ivpb.h `ivpb_outputs`)
@@ -117,6 +121,7 @@ void array_to_out(void* const a[OUT_FIELDS], ivpb_outputs* d) {
 // The dense output retained by the last host-buffer solve with dense_output = 1 (ivpb_dense_eval).
 struct DenseLog {
   bool valid = false;
+  uint64_t generation = 0;            // identity of the retained log (ivpb_dense_generation)
   int method = 0, n = 0, n_cont = 0, cap = 0;
   int64_t N = 0;
   std::vector<int64_t> lo, count;     // shard of every device
@@ -289,6 +294,33 @@ __global__ void zero_interval_kernel(KArgs a, int n, int nev, int method) {
   }
 }
 
+// reference src/solve/solve_ivp.rs:148-176: y0.is_empty() => nothing to integrate; t = t_eval (all of it) or [x0, xend],
+// every y an empty vector, Success, all counters zero.
+__global__ void empty_state_kernel(KArgs a, int nev) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  if (a.status) a.status[i] = ivpb::ST_SUCCESS;
+  if (a.counters) for (int c = 0; c < 6; ++c) a.counters[i * 6 + c] = 0u;
+  if (a.t_final) a.t_final[i] = a.tf;
+  if (a.h_next) a.h_next[i] = 0.0;
+  int m = 0;
+  if (a.n_t_eval >= 0) {
+    for (int j = 0; j < a.n_t_eval; ++j, ++m)
+      if (m < a.out_cap && a.t_out) a.t_out[i * a.out_cap + m] = a.t_eval[j];
+  } else {
+    if (a.out_cap > 0 && a.t_out) a.t_out[i * a.out_cap] = a.t0;
+    if (a.out_cap > 1 && a.t_out) a.t_out[i * a.out_cap + 1] = a.tf;
+    m = 2;
+  }
+  if (a.n_out) a.n_out[i] = m;
+  if (a.ev_count) for (int e = 0; e < nev; ++e) a.ev_count[i * nev + e] = 0;
+  if (a.seg_cap > 0) {   // ContinuousOutput::constant with an empty state: one segment at x0
+    a.seg_n[i] = 1;
+    a.seg_x[2 * i * a.seg_cap] = a.t0;
+    a.seg_x[2 * i * a.seg_cap + 1] = 1e-15;
+  }
+}
+
 // ---- locality order ---------------------------------------------------------------------------------------------
 // Trajectories are independent, so the order in which the work queue hands them out is free.  Neighbouring initial
 // conditions (and parameters) mostly take the same accept / reject / Newton decisions, so a warp whose 32 lanes hold
@@ -398,8 +430,8 @@ void fill_args(KArgs& a, const ProblemInfo& pi, const ivpb_options* o, int64_t N
   } else if (o->method == IVPB_BDF) {
     // bdf.rs:174-184
     const double eps = std::numeric_limits<double>::epsilon();
-    double rtol_min = std::numeric_limits<double>::infinity();
-    for (int i = 0; i < pi.n && i < ivpb::MAX_N; ++i) rtol_min = std::fmin(rtol_min, a.rtol[i]);
+    double rtol_min = std::numeric_limits<double>::infinity();      // over ALL n components (Tolerance::iter(n)), also n > MAX_N
+    for (int i = 0; i < pi.n; ++i) rtol_min = std::fmin(rtol_min, o->rtol[o->n_rtol == 1 ? 0 : i]);
     rtol_min = std::fmax(rtol_min, eps);
     a.newton_tol = std::fmax(10.0 * eps / rtol_min, std::fmin(std::sqrt(rtol_min), 0.03));
     if (a.newton_tol <= 0.0) a.newton_tol = 1e-9;
@@ -464,7 +496,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   a.ev_count = d->ev_count; a.ev_t = d->ev_t; a.ev_y = d->ev_y;
   a.seg_n = d->n_seg; a.seg_x = d->seg_x; a.seg_cont = d->seg_cont;
   a.vec_io = ((reinterpret_cast<uintptr_t>(d_y0) | reinterpret_cast<uintptr_t>(d->y_final)) & 15u) == 0 && (pi.n % 2 == 0);
-  if (!a.seg_n || !a.seg_x || !a.seg_cont) a.seg_cap = 0;      // nowhere to log the segments
+  if (!a.seg_n || !a.seg_x || (!a.seg_cont && pi.n > 0)) a.seg_cap = 0;      // nowhere to log the segments
   if (a.out_cap == 0 || (!a.t_out && !a.y_out && !a.n_out)) {
     if (!o->has_t_eval) a.out_cap = 0;    // nothing to store in step mode
   }
@@ -473,10 +505,21 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     CK(cudaMemcpyAsync(dev.t_eval.p, o->t_eval, sizeof(double) * o->n_t_eval, cudaMemcpyHostToDevice, stream));
     a.t_eval = (const double*)dev.t_eval.p;
   }
-  if (pi.n > ivpb::MAX_N && (o->n_rtol > 1 || o->n_atol > 1)) {
-    // Tolerance::Vector for a warp-per-trajectory problem: per-component arrays in device memory
+  const bool implicit_m2 = o->method == IVPB_RADAU || o->method == IVPB_BDF;
+  if ((pi.n > ivpb::MAX_N || (implicit_m2 && pi.n > 8)) && (o->n_rtol > 1 || o->n_atol > 1)) {
+    // Tolerance::Vector for a warp-per-trajectory launch (explicit n > 32, RADAU / BDF n > 8): WarpLayout reads the
+    // per-component arrays from device memory.  They hold what the step code expects in KArgs::rtol/atol, i.e. for
+    // RADAU the transformed tolerances of radau.rs:188-196 (host libm pow, as in fill_args).
     std::vector<double> tol(2 * (size_t)pi.n);
-    for (int i = 0; i < pi.n; ++i) { tol[i] = o->rtol[o->n_rtol == 1 ? 0 : i]; tol[pi.n + i] = o->atol[o->n_atol == 1 ? 0 : i]; }
+    for (int i = 0; i < pi.n; ++i) {
+      double rt = o->rtol[o->n_rtol == 1 ? 0 : i], at = o->atol[o->n_atol == 1 ? 0 : i];
+      if (o->method == IVPB_RADAU) {
+        const double quot = at / rt;
+        rt = 0.1 * std::pow(rt, 2.0 / 3.0);
+        at = rt * quot;
+      }
+      tol[i] = rt; tol[pi.n + i] = at;
+    }
     CK(dev.tol_ext.ensure(sizeof(double) * tol.size()));
     CK(cudaMemcpyAsync(dev.tol_ext.p, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
@@ -487,6 +530,14 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   const int block = 128;
   const bool warp_mode = pi.n > ivpb::MAX_N;      // one trajectory per warp (WarpLayout, ivpb_erk.cuh)
 
+  if (pi.n == 0 && std::fabs(tf - t0) >= 1e-15) {
+    const int grid = (int)((N + block - 1) / block);
+    if (!a.seg_n || !a.seg_x) a.seg_cap = 0;
+    empty_state_kernel<<<grid, block, 0, stream>>>(a, pi.nev);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+  }
   if (std::fabs(tf - t0) < 1e-15) {
     const int grid = (int)((N + block - 1) / block);
     zero_interval_kernel<<<grid, block, 0, stream>>>(a, pi.n, pi.nev, o->method);
@@ -531,6 +582,12 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
 
   const void* kern = nullptr;
   int kblock = block, ksmem = 0, kunits = 0;
+  {   // EXPERIMENT knobs (to be replaced by defaults once measured)
+    const char* e1 = getenv("IVPB_BLOCK_SYNC");
+    const char* e2 = getenv("IVPB_BLOCK_THREADS");
+    if (e1 && !warp_mode) a.block_sync = atoi(e1);
+    if (e2 && !warp_mode && pi.n > 4 && !implicit_method) kblock = atoi(e2);
+  }
   if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
     kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem, &kunits);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: the per-warp matrices of this state size do not fit shared memory");
@@ -580,7 +637,7 @@ int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
   else { int cur = 0; CK(cudaGetDevice(&cur)); ids.push_back(cur); }
   ivpb_ctx* c = new ivpb_ctx();
   for (int id : ids) {
-    if (id < 0 || id >= count) { delete c; return fail(nullptr, IVPB_ERR_CONFIG, "device id out of range"); }
+    if (id < 0 || id >= count) { ivpb_destroy(c); return fail(nullptr, IVPB_ERR_CONFIG, "device id out of range"); }
     Device d;
     d.id = id;
     cudaError_t err = cudaSetDevice(id);
@@ -589,8 +646,13 @@ int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
     if (err == cudaSuccess) err = cudaMalloc((void**)&d.queue, sizeof(u64));
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
-    if (err != cudaSuccess) { delete c; return fail(nullptr, IVPB_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(err)); }
-    c->devs.push_back(d);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_last, cudaEventDisableTiming);
+    c->devs.push_back(d);       // pushed first so that a failed set-up is torn down by ivpb_destroy like everything else
+    if (err != cudaSuccess) {
+      const std::string msg = std::string("device setup: ") + cudaGetErrorString(err);
+      ivpb_destroy(c);
+      return fail(nullptr, IVPB_ERR_CUDA, msg);
+    }
   }
   // peer access for the multi-device device-resident path (results gathered to device 0 over NVLink)
   for (size_t i = 1; i < c->devs.size(); ++i) {
@@ -611,14 +673,17 @@ void ivpb_destroy(ivpb_ctx* ctx) {
   if (!ctx) return;
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.id);
-    cudaStreamSynchronize(d.stream);
+    if (d.stream) cudaStreamSynchronize(d.stream);
     d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.scratch.release();
     d.q_traj.release(); d.q_ts.release(); d.q_y.release(); d.q_ok.release();
+    d.sort_keys.release(); d.sort_vals.release(); d.sort_tmp.release(); d.sort_minmax.release();
+    d.dense_nseg.release(); d.dense_segx.release(); d.dense_segc.release();
     for (auto& b : d.out) b.release();
-    cudaFree(d.queue);
+    if (d.queue) cudaFree(d.queue);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
     if (d.ev_done) cudaEventDestroy(d.ev_done);
-    cudaStreamDestroy(d.stream);
+    if (d.ev_last) cudaEventDestroy(d.ev_last);
+    if (d.stream) cudaStreamDestroy(d.stream);
   }
   for (auto& u : ctx->user) ivpb_nvrtc_release(u);
   delete ctx;
@@ -640,11 +705,12 @@ int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_e
 }
 
 int ivpb_nvrtc_problem(ivpb_ctx* ctx, const char* cuda_src, int n, int p, int n_events, int has_jac, int* handle) {
-  if (!ctx || !cuda_src || !handle) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
-  if (n < 1 || n > 1024) return fail(ctx, IVPB_ERR_CONFIG, "n must be in 1..1024 (n > 32 runs one trajectory per warp and needs ivp_ode_i)");
+  if (!ctx || (!cuda_src && n != 0) || !handle) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
+  // n == 0 is the reference's empty state vector (solve_ivp.rs:148-176): nothing is compiled or integrated
+  if (n < 0 || n > 1024) return fail(ctx, IVPB_ERR_CONFIG, "n must be in 0..1024 (n > 32 runs one trajectory per warp and needs ivp_ode_i)");
   if (p < 0 || n_events < 0 || n_events > ivpb::MAX_EVENTS_FN) return fail(ctx, IVPB_ERR_CONFIG, "bad p / n_events");
   ivpb_user_problem up;
-  up.n = n; up.p = p; up.n_events = n_events; up.has_jac = has_jac; up.src = cuda_src;
+  up.n = n; up.p = p; up.n_events = n_events; up.has_jac = has_jac; up.src = cuda_src ? cuda_src : "";
   ctx->user.push_back(up);
   *handle = IVPB_USER_HANDLE_BASE + (int)ctx->user.size() - 1;
   return 0;
@@ -663,13 +729,20 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   ProblemInfo pi;
   if (int rc = problem_info(ctx, problem, &pi)) return rc;
   if (int rc = validate(ctx, pi, opt, N, t0, tf)) return rc;
-  if (!d_y0 || !d_out) return fail(ctx, IVPB_ERR_CONFIG, "null device buffer");
+  if ((!d_y0 && pi.n > 0) || !d_out) return fail(ctx, IVPB_ERR_CONFIG, "null device buffer");
   if (pi.p > 0 && !d_params) return fail(ctx, IVPB_ERR_CONFIG, "params is null but the problem has parameters");
   Device& dev0 = ctx->devs[0];
   cudaStream_t s0 = (cudaStream_t)stream;
   const int G = (int)ctx->devs.size();
   CK(cudaSetDevice(dev0.id));
-  if (G == 1) return launch_shard(ctx, dev0, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, s0);
+  // One solve in flight per context: this call's work on device 0 starts after the previous call's (another stream may
+  // have been handed in), because the queue counter and the small staging buffers of the device are shared.
+  CK(cudaStreamWaitEvent(s0, dev0.ev_last, 0));
+  if (G == 1) {
+    const int rc = launch_shard(ctx, dev0, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, s0);
+    if (rc == 0) CK(cudaEventRecord(dev0.ev_last, s0));
+    return rc;
+  }
 
   // Multi-device, device-resident: inputs/outputs live on the first device.  Shard g > 0 receives its
   // slice of y0/params by a peer copy over NVLink, integrates it locally, and returns its results by peer
@@ -688,8 +761,10 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
     if (Ng == 0) continue;
     CK(cudaSetDevice(dev.id));
     CK(cudaStreamWaitEvent(dev.stream, dev0.ev_ready, 0));
-    CK(dev.y0.ensure(sizeof(double) * n * Ng));
-    CK(cudaMemcpyPeerAsync(dev.y0.p, dev.id, d_y0 + lo * n, dev0.id, sizeof(double) * n * Ng, dev.stream));
+    if (n > 0) {
+      CK(dev.y0.ensure(sizeof(double) * n * Ng));
+      CK(cudaMemcpyPeerAsync(dev.y0.p, dev.id, d_y0 + lo * n, dev0.id, sizeof(double) * n * Ng, dev.stream));
+    }
     if (pi.p > 0) {
       CK(dev.params.ensure(sizeof(double) * pi.p * Ng));
       CK(cudaMemcpyPeerAsync(dev.params.p, dev.id, d_params + lo * pi.p, dev0.id, sizeof(double) * pi.p * Ng, dev.stream));
@@ -719,6 +794,7 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   }
   for (int g = 1; g < G; ++g)
     if (N * (g + 1) / G - N * g / G > 0) CK(cudaStreamWaitEvent(s0, ctx->devs[g].ev_done, 0));
+  CK(cudaEventRecord(dev0.ev_last, s0));
   return 0;
 }
 
@@ -728,7 +804,7 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   ProblemInfo pi;
   if (int rc = problem_info(ctx, problem, &pi)) return rc;
   if (int rc = validate(ctx, pi, opt, N, t0, tf)) return rc;
-  if (!y0 || !out) return fail(ctx, IVPB_ERR_CONFIG, "null host buffer");
+  if ((!y0 && pi.n > 0) || !out) return fail(ctx, IVPB_ERR_CONFIG, "null host buffer");
   if (pi.p > 0 && !params) return fail(ctx, IVPB_ERR_CONFIG, "params is null but the problem has parameters");
   const int G = (int)ctx->devs.size();
   const int64_t cap = opt->has_t_eval ? (int64_t)opt->n_t_eval + 1 : (int64_t)opt->max_out;
@@ -742,6 +818,7 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   out_to_array(out, host);
   if (seg_cap > 0) {       // a new dense log replaces the retained one; solves without dense_output leave it alone
     ctx->dense.valid = false;
+    ctx->dense.generation += 1;
     ctx->dense.method = opt->method; ctx->dense.n = n; ctx->dense.n_cont = n_cont; ctx->dense.cap = (int)seg_cap;
     ctx->dense.N = N; ctx->dense.lo.assign(G, 0); ctx->dense.count.assign(G, 0);
   }
@@ -781,8 +858,9 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
     const int64_t lo = N * g / G, hi = N * (g + 1) / G, Ng = hi - lo;
     if (Ng == 0) continue;
     CK(cudaSetDevice(dev.id));
+    if (g == 0) CK(cudaStreamWaitEvent(dev.stream, dev.ev_last, 0));    // after a device-buffer solve still in flight on a caller stream
     const double* d_y0 = zc_y0 ? (const double*)zc_y0 + lo * n : nullptr;
-    if (!d_y0) {
+    if (!d_y0 && n > 0) {
       CK(dev.y0.ensure(sizeof(double) * n * Ng));
       CK(cudaMemcpyAsync(dev.y0.p, y0 + lo * n, sizeof(double) * n * Ng, cudaMemcpyHostToDevice, dev.stream));
       d_y0 = (const double*)dev.y0.p;
@@ -803,8 +881,9 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       const bool seg_field = f >= OUT_NSEG && seg_cap > 0;      // the dense log stays on the device even if
       if ((!host[f] && !seg_field) || per[f] == 0) continue;    // the caller wants no host copy of it
       if (zc_out[f]) { dptr[f] = zc_out[f] + per[f] * lo; direct[f] = true; continue; }
-      CK(dev.out[f].ensure(per[f] * Ng));
-      dptr[f] = dev.out[f].p;
+      Buf& b = seg_field ? (f == OUT_NSEG ? dev.dense_nseg : f == OUT_SEGX ? dev.dense_segx : dev.dense_segc) : dev.out[f];
+      CK(b.ensure(per[f] * Ng));
+      dptr[f] = b.p;
     }
     ivpb_outputs d;
     array_to_out(dptr, &d);
@@ -836,11 +915,20 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   return 0;
 }
 
-static int dense_eval_impl(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok,
-                           int extrapolate) {
-  if (!ctx) return IVPB_ERR_CONFIG;
+static int dense_check(ivpb_ctx* ctx, uint64_t generation, int n, bool check_n) {
   const DenseLog& L = ctx->dense;
   if (!L.valid) return fail(ctx, IVPB_ERR_CONFIG, "no dense output retained: solve with dense_output = 1 first (InterpolationError::NotEnabled)");
+  if (generation != 0 && generation != L.generation)
+    return fail(ctx, IVPB_ERR_CONFIG, "this Solution's dense output is no longer retained: a later dense_output solve on the same context replaced it");
+  if (check_n && n != L.n) return fail(ctx, IVPB_ERR_CONFIG, "state size does not match the retained dense output");
+  return 0;
+}
+
+static int dense_eval_impl(ivpb_ctx* ctx, uint64_t generation, int n, int64_t n_query, const int64_t* traj, const double* ts,
+                           double* y, int32_t* ok, int extrapolate) {
+  if (!ctx) return IVPB_ERR_CONFIG;
+  if (int rc = dense_check(ctx, generation, n, true)) return rc;
+  const DenseLog& L = ctx->dense;
   if (n_query < 0 || (n_query > 0 && (!traj || !ts || !y || !ok))) return fail(ctx, IVPB_ERR_CONFIG, "null argument");
   for (int64_t q = 0; q < n_query; ++q)
     if (traj[q] < 0 || traj[q] >= L.N) return fail(ctx, IVPB_ERR_CONFIG, "trajectory index out of range");
@@ -860,8 +948,8 @@ static int dense_eval_impl(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, 
     if (e == cudaSuccess) e = cudaMemcpyAsync(q_traj.p, traj, 8 * M, cudaMemcpyHostToDevice, dev.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(q_ts.p, ts, 8 * M, cudaMemcpyHostToDevice, dev.stream);
     if (e == cudaSuccess)
-      e = ivpb_launch_dense_eval(L.method, L.n, L.n_cont, L.cap, (const int*)dev.out[OUT_NSEG].p,
-                                 (const double*)dev.out[OUT_SEGX].p, (const double*)dev.out[OUT_SEGC].p, (long long)M,
+      e = ivpb_launch_dense_eval(L.method, L.n, L.n_cont, L.cap, (const int*)dev.dense_nseg.p,
+                                 (const double*)dev.dense_segx.p, (const double*)dev.dense_segc.p, (long long)M,
                                  (const long long*)q_traj.p, L.lo[g], L.count[g], (const double*)q_ts.p, (double*)q_y.p,
                                  (int*)q_ok.p, extrapolate, dev.stream);
     ctx->launches += 1;
@@ -880,18 +968,21 @@ static int dense_eval_impl(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, 
   return 0;
 }
 
-int ivpb_dense_eval(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y, int32_t* ok) {
-  return dense_eval_impl(ctx, n_query, traj, ts, y, ok, 0);
+int ivpb_dense_eval(ivpb_ctx* ctx, uint64_t generation, int n, int64_t n_query, const int64_t* traj, const double* ts,
+                    double* y, int32_t* ok) {
+  return dense_eval_impl(ctx, generation, n, n_query, traj, ts, y, ok, 0);
 }
-int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, int64_t n_query, const int64_t* traj, const double* ts, double* y,
-                                int32_t* ok) {
-  return dense_eval_impl(ctx, n_query, traj, ts, y, ok, 1);
+int ivpb_dense_eval_extrapolate(ivpb_ctx* ctx, uint64_t generation, int n, int64_t n_query, const int64_t* traj,
+                                const double* ts, double* y, int32_t* ok) {
+  return dense_eval_impl(ctx, generation, n, n_query, traj, ts, y, ok, 1);
 }
+uint64_t ivpb_dense_generation(const ivpb_ctx* ctx) { return (ctx && ctx->dense.valid) ? ctx->dense.generation : 0; }
 
-int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start, double* t_end, int32_t* n_seg) {
+int ivpb_dense_span(ivpb_ctx* ctx, uint64_t generation, int64_t first, int64_t count, double* t_start, double* t_end,
+                    int32_t* n_seg) {
   if (!ctx) return IVPB_ERR_CONFIG;
+  if (int rc = dense_check(ctx, generation, 0, false)) return rc;
   const DenseLog& L = ctx->dense;
-  if (!L.valid) return fail(ctx, IVPB_ERR_CONFIG, "no dense output retained: solve with dense_output = 1 first (InterpolationError::NotEnabled)");
   if (first < 0 || count < 0 || first + count > L.N || !t_start || !t_end || !n_seg) return fail(ctx, IVPB_ERR_CONFIG, "bad range / null argument");
   for (size_t g = 0; g < ctx->devs.size(); ++g) {
     const int64_t a = std::max<int64_t>(first, L.lo[g]), b = std::min<int64_t>(first + count, L.lo[g] + L.count[g]);
@@ -904,7 +995,7 @@ int ivpb_dense_span(ivpb_ctx* ctx, int64_t first, int64_t count, double* t_start
     if (e == cudaSuccess) e = t1b.ensure(8 * m);
     if (e == cudaSuccess) e = nb.ensure(4 * m);
     if (e == cudaSuccess)
-      e = ivpb_launch_dense_span(L.cap, (const int*)dev.out[OUT_NSEG].p, (const double*)dev.out[OUT_SEGX].p, a - L.lo[g],
+      e = ivpb_launch_dense_span(L.cap, (const int*)dev.dense_nseg.p, (const double*)dev.dense_segx.p, a - L.lo[g],
                                  (long long)m, (double*)t0b.p, (double*)t1b.p, (int*)nb.p, dev.stream);
     ctx->launches += 1;
     if (e == cudaSuccess) e = cudaMemcpyAsync(t_start + (a - first), t0b.p, 8 * m, cudaMemcpyDeviceToHost, dev.stream);

@@ -198,7 +198,8 @@ class BatchSolution:
     def sol_many(self, traj, ts, extrapolate: bool = False):
         """Dense output of trajectory `traj[q]` at `ts[q]`; returns (y[Q, n], ok[Q]).  `extrapolate`: the rule of
         ContinuousOutput::evaluate_extrapolate (cont.rs:91-150) for times outside the stored steps."""
-        return self.extras["ctx"].dense_eval(np.asarray(traj), np.asarray(ts), self.n, extrapolate)
+        return self.extras["ctx"].dense_eval(np.asarray(traj), np.asarray(ts), self.n, extrapolate,
+                                             generation=self.extras.get("dense_generation", 0))
 
     def sol(self, i: int, t: float):
         """Solution::sol for trajectory i: InterpolationError semantics of solution.rs:25-44."""
@@ -216,7 +217,7 @@ class BatchSolution:
     def sol_span(self, i: int):
         if "ctx" not in self.extras or not self.extras.get("dense"):
             return None
-        t0, t1, m = self.extras["ctx"].dense_span(i, 1)
+        t0, t1, m = self.extras["ctx"].dense_span(i, 1, generation=self.extras.get("dense_generation", 0))
         return (float(t0[0]), float(t1[0])) if m[0] > 0 else None
 
     def __len__(self):

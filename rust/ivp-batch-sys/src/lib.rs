@@ -69,6 +69,8 @@ pub const IVPB_FLAG_STRICT_FP: i32 = 1;
 pub const IVPB_FLAG_NO_REFILL: i32 = 2;
 pub const IVPB_FLAG_NO_ZEROCOPY: i32 = 4;
 pub const IVPB_FLAG_FAST_FP: i32 = 8;
+pub const IVPB_FLAG_NO_SORT: i32 = 16;
+pub const IVPB_FLAG_SORT: i32 = 32;
 
 extern "C" {
     pub fn ivpb_create(out: *mut *mut ivpb_ctx, device_ids: *const c_int, n_devices: c_int) -> c_int;
@@ -81,9 +83,10 @@ extern "C" {
                             y0: *const f64, params: *const f64, out: *const ivpb_outputs) -> c_int;
     pub fn ivpb_solve_batch_device(ctx: *mut ivpb_ctx, problem: c_int, opt: *const ivpb_options, n: i64, t0: f64, tf: f64,
                                    d_y0: *const f64, d_params: *const f64, d_out: *const ivpb_outputs, stream: *mut c_void) -> c_int;
-    pub fn ivpb_dense_eval(ctx: *mut ivpb_ctx, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
-    pub fn ivpb_dense_eval_extrapolate(ctx: *mut ivpb_ctx, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
-    pub fn ivpb_dense_span(ctx: *mut ivpb_ctx, first: i64, count: i64, t_start: *mut f64, t_end: *mut f64, n_seg: *mut i32) -> c_int;
+    pub fn ivpb_dense_eval(ctx: *mut ivpb_ctx, generation: u64, n: c_int, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
+    pub fn ivpb_dense_eval_extrapolate(ctx: *mut ivpb_ctx, generation: u64, n: c_int, n_query: i64, traj: *const i64, ts: *const f64, y: *mut f64, ok: *mut i32) -> c_int;
+    pub fn ivpb_dense_span(ctx: *mut ivpb_ctx, generation: u64, first: i64, count: i64, t_start: *mut f64, t_end: *mut f64, n_seg: *mut i32) -> c_int;
+    pub fn ivpb_dense_generation(ctx: *const ivpb_ctx) -> u64;
     pub fn ivpb_host_alloc(bytes: usize) -> *mut c_void;
     pub fn ivpb_host_free(p: *mut c_void);
     pub fn ivpb_launch_count(ctx: *const ivpb_ctx) -> u64;

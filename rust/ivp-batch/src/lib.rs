@@ -151,7 +151,7 @@ impl Problem {
 pub fn sol_many(ctx: &Context, index: usize, n: usize, ts: &[Float]) -> Result<Vec<Vec<Float>>, Error> {
     let traj = vec![index as i64; ts.len()];
     let mut y = vec![0.0; ts.len() * n]; let mut ok = vec![0i32; ts.len()];
-    let rc = unsafe { sys::ivpb_dense_eval(ctx.raw, ts.len() as i64, traj.as_ptr(), ts.as_ptr(), y.as_mut_ptr(), ok.as_mut_ptr()) };
+    let rc = unsafe { sys::ivpb_dense_eval(ctx.raw, 0, n as i32, ts.len() as i64, traj.as_ptr(), ts.as_ptr(), y.as_mut_ptr(), ok.as_mut_ptr()) };
     if rc != sys::IVPB_OK || ok.iter().any(|&k| k == 0) { return Err(Error::Config("t outside the dense output span (InterpolationError)".into())); }
     Ok(y.chunks(n).map(|c| c.to_vec()).collect())
 }
@@ -159,7 +159,7 @@ pub fn sol_many(ctx: &Context, index: usize, n: usize, ts: &[Float]) -> Result<V
 /// `ContinuousOutput::evaluate_extrapolate` (reference src/solve/cont.rs:91-150) for trajectory `index`.
 pub fn sol_extrapolate(ctx: &Context, index: usize, n: usize, t: Float) -> Option<Vec<Float>> {
     let (traj, mut y, mut ok) = (index as i64, vec![0.0; n], 0i32);
-    let rc = unsafe { sys::ivpb_dense_eval_extrapolate(ctx.raw, 1, &traj, &t, y.as_mut_ptr(), &mut ok) };
+    let rc = unsafe { sys::ivpb_dense_eval_extrapolate(ctx.raw, 0, n as i32, 1, &traj, &t, y.as_mut_ptr(), &mut ok) };
     if rc != sys::IVPB_OK || ok == 0 { None } else { Some(y) }
 }
 

@@ -103,7 +103,7 @@ class _OracleDense:
         oracle, pid, t0, tf, Y0, params, opts = self.a
         return oracle.dense_eval(pid, t0, tf, Y0[i], None if params is None else params[i], opts, ts, extrapolate)
 
-    def dense_eval(self, traj, ts, n, extrapolate=False):
+    def dense_eval(self, traj, ts, n, extrapolate=False, generation=0):
         traj, ts = np.atleast_1d(traj), np.atleast_1d(np.asarray(ts, dtype=float))
         y, ok = np.zeros((ts.size, n)), np.zeros(ts.size, dtype=bool)
         for i in np.unique(traj):
@@ -111,7 +111,7 @@ class _OracleDense:
             y[m], ok[m], _ = self._one(int(i), ts[m], extrapolate)
         return y, ok
 
-    def dense_span(self, first, count):
+    def dense_span(self, first, count, generation=0):
         t0, t1, m = np.zeros(count), np.zeros(count), np.zeros(count, dtype=np.int32)
         for k in range(count):
             _, _, span = self._one(first + k, [])
