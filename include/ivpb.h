@@ -101,21 +101,29 @@ typedef struct {
 } ivpb_options;
 
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation
-                                  the reference's rounding, no FMA contraction) */
+                                  the reference's rounding, no FMA contraction).  Without this flag and without
+                                  IVPB_FLAG_FAST_FP the explicit methods let a parity pilot choose (ivpb_last_fp_mode) */
 #define IVPB_FLAG_NO_REFILL 2u /* static one-trajectory-per-thread schedule (debug / A-B measurements) */
-#define IVPB_FLAG_FAST_FP 8u   /* RADAU / BDF only: run the FMA-contracted kernels.  The implicit methods default to the
+#define IVPB_FLAG_FAST_FP 8u   /* run the FMA-contracted kernels unconditionally.  The implicit methods default to the
                                   strict arithmetic (bit-identical to the reference's operation sequence) because stiff
                                   ensembles lose step-count parity under any last-bit perturbation (VdP mu=1000: 73 % RADAU,
                                   97 % BDF with FMA) while the FMA build is only 17-29 % faster there.  The explicit methods
-                                  default to the FMA build (2x faster; north-star parity 100 %) and take IVPB_FLAG_STRICT_FP. */
+                                  use the FMA build (2x faster) when the parity pilot finds it inside the tolerance of the
+                                  strict build on a sample of the ensemble (north star: yes; CR3BP at 1e-10: no). */
 #define IVPB_FLAG_NO_SORT 16u  /* RADAU / BDF: hand the trajectories out in index order instead of the locality order (a Morton
                                   curve through the varying coordinates of y0 / params, so that the lanes of a warp hold
                                   neighbouring initial conditions and diverge less; results are identical either way) */
 #define IVPB_FLAG_SORT 32u     /* explicit methods: use the locality order too (off by default there: small gain on the device,
                                   a loss end to end with mapped host buffers, see ivpb_runtime.cu launch_shard) */
+#define IVPB_FLAG_ZEROCOPY_OUT 64u /* ivpb_solve_batch: let the kernel store results straight into the caller's page-locked
+                                    buffers (round 1's route) instead of staging them in device memory and copying them
+                                    out chunk by chunk while the kernel integrates the rest (completion flags).  Only
+                                    worth it for long kernels with small outputs on an otherwise idle PCIe root complex. */
+#define IVPB_FLAG_NO_PIPELINE 128u /* ivpb_solve_batch: copy the results out after the kernel has finished instead of chunk
+                                    by chunk while it runs (A-B measurements) */
 #define IVPB_FLAG_NO_ZEROCOPY 4u /* ivpb_solve_batch: always stage through device buffers, even when the caller's
-                                    buffers are page-locked (default: pinned y0 / params / per-trajectory results are
-                                    read and written by the kernel directly over PCIe, overlapping the solve) */
+                                    buffers are page-locked (default: pinned y0 / params rows are read by the kernel
+                                    directly over PCIe when a trajectory starts) */
 
 /* Per-trajectory outputs.  Any pointer may be NULL (= not wanted).  In ivpb_solve_batch they are
  * HOST pointers, in ivpb_solve_batch_device DEVICE pointers.
@@ -222,6 +230,16 @@ void ivpb_host_free(void* p);
 
 /* Kernels launched by this context so far (for bench.py's gpu_launches). */
 uint64_t ivpb_launch_count(const ivpb_ctx* ctx);
+
+/* Which kernel build the most recent solve of this context ran: returns 1 = strict (the reference's arithmetic,
+ * operation for operation), 0 = FMA build, and fills info = {strict, source, sample, status mismatches, step-count
+ * mismatches, trajectories out of tolerance}.  source: 0 the caller's flag (IVPB_FLAG_STRICT_FP / IVPB_FLAG_FAST_FP),
+ * 1 the method's default (RADAU / BDF: strict), 2 a cached verdict of the parity pilot, 3 the parity pilot just ran.
+ * The pilot (explicit methods without either flag): the first solve of a configuration integrates `sample` evenly
+ * strided trajectories of the ensemble with BOTH builds and picks the FMA build only if all of them end with the same
+ * status and inside max(10 rtol |y|, 10 atol) of the strict result, and >= 99 % with the same accepted / rejected step
+ * counts (ivpb_runtime.cu resolve_fp). */
+int ivpb_last_fp_mode(const ivpb_ctx* ctx, int32_t info[6]);
 
 /* FP64 FMA-pipe peak of the first device measured with a dependent-chain DFMA microbenchmark
  * (TFLOP/s, FMA = 2 flop).  Used as the roofline denominator (MEASURED_PEAKS.json has no fp64 entry). */

@@ -35,13 +35,15 @@ IVPB_FLAG_NO_ZEROCOPY = 4
 IVPB_FLAG_FAST_FP = 8
 IVPB_FLAG_NO_SORT = 16
 IVPB_FLAG_SORT = 32
+IVPB_FLAG_ZEROCOPY_OUT = 64
+IVPB_FLAG_NO_PIPELINE = 128
 
 #: Every symbol include/ivpb.h declares (checked by the CPU test-suite against the built library).
 ABI_SYMBOLS = [
     "ivpb_create", "ivpb_destroy", "ivpb_last_error", "ivpb_device_count", "ivpb_builtin_problem",
     "ivpb_nvrtc_problem", "ivpb_solve_batch", "ivpb_solve_batch_device", "ivpb_host_alloc", "ivpb_host_free",
     "ivpb_launch_count", "ivpb_measure_fp64_peak", "ivpb_version", "ivpb_dense_eval", "ivpb_dense_span",
-    "ivpb_dense_eval_extrapolate", "ivpb_dense_generation",
+    "ivpb_dense_eval_extrapolate", "ivpb_dense_generation", "ivpb_last_fp_mode",
 ]
 
 
@@ -81,6 +83,8 @@ def load_library():
     L.ivpb_launch_count.argtypes = [vp]
     L.ivpb_measure_fp64_peak.restype = C.c_int
     L.ivpb_measure_fp64_peak.argtypes = [vp, _abi.c_double_p]
+    L.ivpb_last_fp_mode.restype = C.c_int
+    L.ivpb_last_fp_mode.argtypes = [vp, _abi.c_int32_p]
     L.ivpb_version.restype = C.c_char_p
     L.ivpb_dense_eval.restype = C.c_int
     L.ivpb_dense_eval.argtypes = [vp, C.c_uint64, C.c_int, C.c_int64, _abi.c_int64_p, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p]
@@ -187,6 +191,17 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.ivpb_launch_count(self.ptr))
+
+    def last_fp_mode(self) -> dict:
+        """Which kernel build the most recent solve ran and why (ivpb_last_fp_mode)."""
+        info = (C.c_int32 * 6)()
+        rc = self.lib.ivpb_last_fp_mode(self.ptr, info)
+        src = {0: "flag", 1: "method default", 2: "parity pilot (cached)", 3: "parity pilot"}.get(int(info[1]), "?")
+        d = {"mode": "strict" if rc == 1 else "fma", "source": src}
+        if int(info[1]) >= 2:
+            d.update(sample=int(info[2]), status_mismatches=int(info[3]), step_count_mismatches=int(info[4]),
+                     out_of_tolerance=int(info[5]))
+        return d
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double()

@@ -44,7 +44,6 @@ struct KArgs {
   int max_events, jac_mode;
   int zero_tail;         // t_out / y_out are the caller's mapped host buffers: `finish` zero-fills the slots a trajectory
                          // left unwritten (nobody memsets them), so the whole row is defined when the kernel ends
-  int block_sync;        // thread-per-trajectory kernels: the warps of a block start every attempted step together (run_schedule)
   int vec_io;            // y0 / y_final rows are 16-byte aligned: move them as double2 (LDG.128 / STG.128)
   int nind1, nind2, nind3;   // RADAU with a mass matrix: resolved DAE partition (radau.rs:210-245); nind1 + nind2 + nind3 == n
   double newton_tol;     // implicit methods: Newton stopping tolerance (radau.rs:198-205, bdf.rs:174-184), host-computed
@@ -62,6 +61,12 @@ struct KArgs {
   int* ev_count;
   double* ev_t;
   double* ev_y;
+  // Completion flags of the host-buffer path (ivpb_solve_batch): the shard is cut into chunks of `chunk_size` consecutive
+  // trajectories; the thread that retires the LAST trajectory of a chunk raises chunk_flag[c] in mapped host memory, and
+  // the host then copies that chunk's results out while the kernel keeps integrating the others.  chunk_size == 0: off.
+  i64 chunk_size;
+  unsigned* chunk_count;     // device, [chunks], zeroed before the launch: trajectories of the chunk retired so far
+  int* chunk_flag;           // page-locked host memory mapped into the device address space, [chunks]
   // dense_output: per-trajectory interpolant log (src/solve/solout.rs:141-146); seg_cap == 0 => off
   int seg_cap, n_cont;   // n_cont = coeffs_per_state * n doubles per segment
   int* seg_n;

@@ -530,6 +530,13 @@ struct ErkTraj {
   static constexpr int PS = P > 0 ? P : 1;
   static constexpr bool DENSE = FEAT != 0;
   static constexpr bool BATCH_HEAVY = false;     // see run_schedule
+  // Block-synchronous trips (run_schedule) for the kernels whose step code is far larger than the 32 KB instruction cache
+  // and fetch-bound: the strict build (two instructions per multiply-add) of the wide tableaux / larger systems.
+#ifdef IVPB_STRICT
+  static constexpr bool BLOCK_SYNC = !L::WARP && (METHOD == M_DOP853 ? NG >= 3 : NG >= 5);
+#else
+  static constexpr bool BLOCK_SYNC = false;
+#endif
   static constexpr int NC = MethodTraits<METHOD>::NC;
   using Out = SolOutDev<Prob, METHOD, FEAT, L>;
 
@@ -1142,20 +1149,63 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #define IVPB_BATCH_NUM 1      // heavy lanes wait until NUM/DEN of the active lanes are heavy; measured on the BDF
 #define IVPB_BATCH_DEN 1      // ensembles: 1/2 -> 89 ms, 3/4 -> 80 ms, 1/1 -> 62 ms (Robertson, 2^18 trajectories)
 #endif
+// Completion flags (KArgs::chunk_*): called by all lanes of a converged warp after `finish`; `fin` marks the lanes whose
+// trajectory `idx` has just written its results.  Lanes retiring trajectories of the same chunk are counted with one
+// atomic; every result store is fenced before the count that covers it, so when the count is complete the chunk's
+// results are visible device-wide (the "last block" pattern), and the flag store tells the host it may copy them.
+__device__ __forceinline__ void chunk_signal(const KArgs& a, bool fin, i64 idx) {
+  if (a.chunk_size <= 0) return;                       // uniform over the grid
+  const unsigned m = __ballot_sync(0xffffffffu, fin);
+  if (!fin) return;
+  const int c = (int)(idx / a.chunk_size);
+  const unsigned peers = __match_any_sync(m, c);
+  __threadfence();
+  __syncwarp(peers);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+    const unsigned n = (unsigned)__popc(peers);
+    const unsigned old = atomicAdd(a.chunk_count + c, n);
+    const i64 lo = (i64)c * a.chunk_size;
+    const i64 size = (lo + a.chunk_size <= a.N ? a.chunk_size : a.N - lo);
+    if ((i64)old + (i64)n == size) {
+      __threadfence_system();
+      *((volatile int*)a.chunk_flag + c) = 1;
+    }
+  }
+}
+// one trajectory per warp: every lane has written its slice of the results
+__device__ __forceinline__ void chunk_signal_warp(const KArgs& a, i64 idx) {
+  if (a.chunk_size <= 0) return;
+  __threadfence();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const int c = (int)(idx / a.chunk_size);
+    const unsigned old = atomicAdd(a.chunk_count + c, 1u);
+    const i64 lo = (i64)c * a.chunk_size;
+    const i64 size = (lo + a.chunk_size <= a.N ? a.chunk_size : a.N - lo);
+    if ((i64)old + 1 == size) {
+      __threadfence_system();
+      *((volatile int*)a.chunk_flag + c) = 1;
+    }
+  }
+}
+
 // Generic persistent scheduler: Traj provides init(a, idx) -> done, step(a) -> done, finish(a).
 //
-// KArgs::block_sync (block-synchronous trips): the warps of a block start every attempted step together
-// (__syncthreads_or doubles as the loop test).  The step code of the larger systems is far bigger than the
+// Traj::BLOCK_SYNC (block-synchronous trips, a compile-time property of the kernel): the warps of a block start every
+// attempted step together (__syncthreads_or doubles as the loop test).  The step code of the larger systems is far bigger than the
 // instruction caches (CR3BP DOP853 with dense output: 50 KB hot loop in the FMA build, 110 KB in the strict one, against a
 // 32 KB L1.5 I$), so warps that drift apart each stream the whole loop from L2 on their own (ncu: "no instruction"
-// is the top stall, 5.4 per issue in the strict kernel); in lock step one warp's fetch serves all of them.  Results are
-// unaffected: only the interleaving of independent trajectories changes.
+// is the top stall, 5.4 per issue in the strict kernel); in lock step one warp's fetch serves all of them.  Measured on
+// CR3BP DOP853 + 101 samples, 2^18 trajectories, strict build: 384 ms -> 313 ms with 128-thread blocks, 238 ms with one
+// 256-thread block per SM (all eight resident warps in step).  It does nothing for code that fits the cache or is not
+// fetch-bound (FMA build of the same kernel 103.5 -> 104.4 ms; north star, Lorenz, RADAU / BDF: 0.5-15 % slower), hence a
+// per-kernel switch.  Results are unaffected: only the interleaving of independent trajectories changes.
 template <class Traj>
 __device__ __forceinline__ void run_schedule(const KArgs& a) {
   Traj T;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const bool bsync = a.block_sync != 0;        // uniform over the grid
+  constexpr bool bsync = Traj::BLOCK_SYNC;
   bool active = false, exhausted = false;
   for (;;) {
     // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp).
@@ -1175,25 +1225,28 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         idx = (i64)base + __popc(need & ((1u << lane) - 1u));
         if ((i64)base + __popc(need) >= a.N) exhausted = true;
       }
+      bool fin0 = false;
       if (!active && idx < a.N) {
         active = true;
-        if (T.init(a, a.perm ? (i64)a.perm[idx] : idx)) { T.finish(a); active = false; }
+        if (T.init(a, a.perm ? (i64)a.perm[idx] : idx)) { T.finish(a); active = false; fin0 = true; }
       }
+      chunk_signal(a, fin0, T.idx);
     }
-    if (bsync) {
+    if constexpr (bsync) {
       // block-uniform decisions: leave when no lane of the block has work and every warp has seen the end of the queue
       if (!__syncthreads_or(active ? 1 : 0)) {
         if (!__syncthreads_or(exhausted ? 0 : 1)) break;
         continue;
       }
-    } else if (__ballot_sync(FULL, active) == 0u) {
-      if (exhausted) break;
-      continue;
+    } else {
+      if (__ballot_sync(FULL, active) == 0u) {
+        if (exhausted) break;
+        continue;
+      }
     }
     // ---- hot loop: every lane that owns a trajectory attempts steps until one of them finishes.  Nothing of
     // the refill logic is live in here.
     bool done = false;
-    bool any;
     do {
       bool run = active;
       if constexpr (Traj::BATCH_HEAVY) {
@@ -1206,9 +1259,9 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         run = active && (!hv || nh * IVPB_BATCH_DEN >= na * IVPB_BATCH_NUM);
       }
       if (run) done = T.step(a);
-      any = bsync ? (__syncthreads_or(done ? 1 : 0) != 0) : __any_sync(FULL, done);
-    } while (!any);
+    } while (!(bsync ? (__syncthreads_or(done ? 1 : 0) != 0) : (__any_sync(FULL, done) != 0)));
     if (done) { T.finish(a); active = false; }
+    chunk_signal(a, done, T.idx);
   }
 }
 
@@ -1243,6 +1296,7 @@ __device__ __forceinline__ void run_schedule_warp(const KArgs& a) {
       while (!T.step(a)) {}
     }
     T.finish(a);
+    chunk_signal_warp(a, T.idx);
   }
 }
 

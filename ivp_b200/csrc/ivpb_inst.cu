@@ -30,5 +30,6 @@ extern "C" const void* IVPB_SYM(IVPB_TAG)(int method, int feat, ivpb_pinfo* info
     }
   }
   if (method < 0) return nullptr;
+  if (info) info->block = ivpb::erk_lookup_block<P>(method);
   return ivpb::erk_lookup<P>(method, feat);
 }

@@ -24,8 +24,14 @@ namespace ivpb {
 #ifndef IVPB_MB_BIG
 #define IVPB_MB_BIG 1
 #endif
+// Threads per block of the thread-per-trajectory kernels: 128, or 256 for the block-synchronous kernels of the larger
+// systems (one block per SM at 255 registers, so all eight resident warps run in step; ErkTraj::BLOCK_SYNC).
 template <class Prob, int METHOD, int FEAT>
-__global__ void __launch_bounds__((Prob::N > 4 ? 2 * IVPB_BLOCK : IVPB_BLOCK), (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
+__host__ __device__ constexpr int erk_block_threads() {
+  return (ErkTraj<Prob, METHOD, FEAT>::BLOCK_SYNC && Prob::N > 4) ? 2 * IVPB_BLOCK : IVPB_BLOCK;
+}
+template <class Prob, int METHOD, int FEAT>
+__global__ void __launch_bounds__((erk_block_threads<Prob, METHOD, FEAT>()), (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
   erk_body<Prob, METHOD, FEAT>(a);
 }
 
@@ -64,6 +70,20 @@ __host__ inline const void* erk_lookup_feat_any(int feat) {
         if constexpr (Prob::NEV > 0) return (const void*)&erk_warp_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
         else return nullptr;
       default: return nullptr;
+    }
+  }
+}
+
+// block size of the kernel erk_lookup returns for (method, feat)
+template <class Prob>
+__host__ inline int erk_lookup_block(int method) {
+  if constexpr (Prob::N > MAX_N) return IVPB_BLOCK;
+  else {
+    switch (method) {      // BLOCK_SYNC does not depend on the feature set
+      case M_RK23: return erk_block_threads<Prob, M_RK23, 0>();
+      case M_DOPRI5: return erk_block_threads<Prob, M_DOPRI5, 0>();
+      case M_DOP853: return erk_block_threads<Prob, M_DOP853, 0>();
+      default: return erk_block_threads<Prob, M_RK4, 0>();
     }
   }
 }

@@ -14,6 +14,11 @@
 // 2^-54 <= |y log x| < 512; anything else (zeros, infinities, NaNs, negative or subnormal x, overflow /
 // underflow range) is delegated to the platform pow, where the results are exact or saturated anyway.
 // Tables: ivpb_libm_pow_tables.cuh (generated from the installed libm by tools/extract_glibc_pow_tables.py).
+//
+// PROVENANCE / LICENCE: the operation sequence below was read off the machine code of glibc 2.39's libm (x86-64,
+// __pow_fma); glibc is LGPL-2.1-or-later (its pow is derived from ARM optimized-routines, MIT).  This file and the
+// generated tables are therefore LGPL-derived material and must be distributed under terms compatible with that licence.
+// Strict-build parity is parity with a reference linked against THIS libm variant ("Floating-point mode").
 #pragma once
 
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)

@@ -219,7 +219,10 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
     // must match ivpb::MatSel / RadauTraj / BdfTraj::SMEM_DOUBLES_PER_THREAD (ivpb_implicit.cuh)
     block = up.n <= 6 ? 128 : 64;
     size_t doubles = 0;
-    if (up.n > 3) doubles += (size_t)(method == 4 ? ((up.has_jac & 2) ? 5 : 4) : 2) * up.n * up.n;   // Jacobian + iteration matrices (+ RADAU mass matrix)
+    // the Jacobian always lives in shared memory; the iteration matrices (+ RADAU's mass matrix) for n > 3
+    if (up.n > 3) doubles += (size_t)(method == 4 ? ((up.has_jac & 2) ? 5 : 4) : 2) * up.n * up.n;
+    else doubles += (size_t)up.n * up.n;
+    if (method == 4) doubles += (size_t)4 * up.n;                           // RADAU: dense-output coefficients (cont)
     if (method == 5) doubles += (size_t)15 * up.n;                          // BDF: D (8 rows), scratch (6), Jacobian point
     smem = doubles * block * 8;
     if (smem > 0) {

@@ -75,6 +75,7 @@ struct Buf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int MAX_CHUNKS = 64;
 enum { OUT_STATUS, OUT_COUNTERS, OUT_TFINAL, OUT_YFINAL, OUT_HNEXT, OUT_NOUT, OUT_TOUT, OUT_YOUT, OUT_EVCOUNT,
        OUT_EVT, OUT_EVY, OUT_NSEG, OUT_SEGX, OUT_SEGC, OUT_FIELDS };
 
@@ -82,7 +83,12 @@ struct Device {
   int id = 0;
   int sms = 0;
   cudaStream_t stream = nullptr;
-  u64* queue = nullptr;
+  cudaStream_t stream2 = nullptr;   // second lane of the chunked host-buffer pipeline (ivpb_solve_batch)
+  cudaEvent_t ev_shared = nullptr;  // "t_eval / tolerance staging uploaded" (recorded on stream, awaited by stream2)
+  u64* queue = nullptr;             // work-queue head(s) of the launches in flight on this device
+  unsigned* chunk_count = nullptr;  // completion counters of the host-buffer pipeline (device, MAX_CHUNKS)
+  int* chunk_flag = nullptr;        // completion flags (page-locked host memory, mapped; MAX_CHUNKS)
+  int* chunk_flag_dev = nullptr;    // the same flags as the device sees them
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
   cudaEvent_t ev_last = nullptr;    // end of the most recent solve enqueued on this device: the per-device queue counter,
                                     // t_eval / tolerance staging and sort buffers are shared, so solves on one context are
@@ -133,6 +139,13 @@ struct ivpb_ctx {
   uint64_t launches = 0;
   DenseLog dense;
   std::vector<ivpb_user_problem> user;   // NVRTC problems (ivpb_nvrtc.cpp)
+  // floating-point mode of the explicit methods (resolve_fp): decisions of the parity pilot, keyed by the solve's
+  // configuration, and what the most recent solve ran (ivpb_last_fp_mode)
+  struct FpChoice { uint64_t key; int strict; int32_t info[5]; };
+  std::vector<FpChoice> fp_cache;
+  int fp_override = -1;                  // set around launch_shard by the entry points: 0 FMA build, 1 strict build
+  int32_t last_fp[6] = {0, 0, 0, 0, 0, 0};   // {strict, source, sample, status mismatches, step-count mismatches, out of tolerance}
+  Buf pilot_in, pilot_out[2], pilot_res;
 };
 
 namespace {
@@ -471,13 +484,47 @@ static int locality_order(ivpb_ctx* ctx, Device& dev, const ProblemInfo& pi, int
   return 0;
 }
 
+// Per-component tolerances of a warp-per-trajectory launch (explicit n > 32, RADAU / BDF n > 8) with Tolerance::Vector:
+// what the step code expects in KArgs::rtol/atol, i.e. for RADAU the transformed tolerances of radau.rs:188-196.
+static bool wants_tol_ext(const ProblemInfo& pi, const ivpb_options* o) {
+  const bool implicit_m = o->method == IVPB_RADAU || o->method == IVPB_BDF;
+  return (pi.n > ivpb::MAX_N || (implicit_m && pi.n > 8)) && (o->n_rtol > 1 || o->n_atol > 1);
+}
+// Upload the small per-call arrays every launch of the call reads (t_eval, per-component tolerances) on `stream`.
+static int stage_shared(ivpb_ctx* ctx, Device& dev, const ProblemInfo& pi, const ivpb_options* o, cudaStream_t stream) {
+  if (o->has_t_eval && o->n_t_eval > 0) {
+    CK(dev.t_eval.ensure(sizeof(double) * o->n_t_eval));
+    CK(cudaMemcpyAsync(dev.t_eval.p, o->t_eval, sizeof(double) * o->n_t_eval, cudaMemcpyHostToDevice, stream));
+  }
+  if (wants_tol_ext(pi, o)) {
+    std::vector<double> tol(2 * (size_t)pi.n);
+    for (int i = 0; i < pi.n; ++i) {
+      double rt = o->rtol[o->n_rtol == 1 ? 0 : i], at = o->atol[o->n_atol == 1 ? 0 : i];
+      if (o->method == IVPB_RADAU) {        // host libm pow, as in fill_args
+        const double quot = at / rt;
+        rt = 0.1 * std::pow(rt, 2.0 / 3.0);
+        at = rt * quot;
+      }
+      tol[i] = rt; tol[pi.n + i] = at;
+    }
+    CK(dev.tol_ext.ensure(sizeof(double) * tol.size()));
+    CK(cudaMemcpyAsync(dev.tol_ext.p, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
+  }
+  return 0;
+}
+
+// `slot`: which of the device's work-queue heads this launch uses.  `upload_shared`: copy t_eval / per-component
+// tolerances to the device's staging buffers on `stream` (false for the later chunks of one call: already there).
 static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemInfo& pi, const ivpb_options* o,
                         int64_t N, double t0, double tf, const double* d_y0, const double* d_params,
-                        const ivpb_outputs* d, cudaStream_t stream, bool zero_tail = false) {
+                        const ivpb_outputs* d, cudaStream_t stream, bool zero_tail, int slot, bool upload_shared,
+                        int64_t chunk_size = 0) {
   if (N == 0) return 0;
   KArgs a;
   fill_args(a, pi, o, N, t0, tf);
   a.zero_tail = zero_tail ? 1 : 0;
+  if (chunk_size > 0) { a.chunk_size = chunk_size; a.chunk_count = dev.chunk_count; a.chunk_flag = dev.chunk_flag_dev; }
   // Locality order: on by default for RADAU / BDF, where warp divergence is the bottleneck (Robertson BDF 46.5 -> 23.1 ms,
   // VdP mu=1000 RADAU 54.0 -> 50.1, BDF 79.3 -> 73.2 per 2^18 trajectories); opt-in for the explicit methods, where it gains
   // little on the device (north star 15.03 -> 14.98 ms, CR3BP + t_eval 332 -> 310, chaotic Lorenz 7.86 -> 8.22) and costs
@@ -490,7 +537,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     if (int rc = locality_order(ctx, dev, pi, N, d_y0, d_params, stream, &perm)) return rc;
     a.perm = perm;
   }
-  a.y0 = d_y0; a.params = d_params; a.queue = dev.queue;
+  a.y0 = d_y0; a.params = d_params; a.queue = dev.queue + slot;
   a.status = d->status; a.counters = d->counters; a.t_final = d->t_final; a.y_final = d->y_final;
   a.h_next = d->h_next; a.n_out = d->n_out; a.t_out = d->t_out; a.y_out = d->y_out;
   a.ev_count = d->ev_count; a.ev_t = d->ev_t; a.ev_y = d->ev_y;
@@ -500,33 +547,13 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   if (a.out_cap == 0 || (!a.t_out && !a.y_out && !a.n_out)) {
     if (!o->has_t_eval) a.out_cap = 0;    // nothing to store in step mode
   }
-  if (o->has_t_eval && o->n_t_eval > 0) {
-    CK(dev.t_eval.ensure(sizeof(double) * o->n_t_eval));
-    CK(cudaMemcpyAsync(dev.t_eval.p, o->t_eval, sizeof(double) * o->n_t_eval, cudaMemcpyHostToDevice, stream));
-    a.t_eval = (const double*)dev.t_eval.p;
-  }
-  const bool implicit_m2 = o->method == IVPB_RADAU || o->method == IVPB_BDF;
-  if ((pi.n > ivpb::MAX_N || (implicit_m2 && pi.n > 8)) && (o->n_rtol > 1 || o->n_atol > 1)) {
-    // Tolerance::Vector for a warp-per-trajectory launch (explicit n > 32, RADAU / BDF n > 8): WarpLayout reads the
-    // per-component arrays from device memory.  They hold what the step code expects in KArgs::rtol/atol, i.e. for
-    // RADAU the transformed tolerances of radau.rs:188-196 (host libm pow, as in fill_args).
-    std::vector<double> tol(2 * (size_t)pi.n);
-    for (int i = 0; i < pi.n; ++i) {
-      double rt = o->rtol[o->n_rtol == 1 ? 0 : i], at = o->atol[o->n_atol == 1 ? 0 : i];
-      if (o->method == IVPB_RADAU) {
-        const double quot = at / rt;
-        rt = 0.1 * std::pow(rt, 2.0 / 3.0);
-        at = rt * quot;
-      }
-      tol[i] = rt; tol[pi.n + i] = at;
-    }
-    CK(dev.tol_ext.ensure(sizeof(double) * tol.size()));
-    CK(cudaMemcpyAsync(dev.tol_ext.p, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, stream));
-    CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
-    a.rtol_ext = (const double*)dev.tol_ext.p; a.atol_ext = a.rtol_ext + pi.n;
-  }
+  if (upload_shared)
+    if (int rc = stage_shared(ctx, dev, pi, o, stream)) return rc;
+  if (o->has_t_eval && o->n_t_eval > 0) a.t_eval = (const double*)dev.t_eval.p;
+  if (wants_tol_ext(pi, o)) { a.rtol_ext = (const double*)dev.tol_ext.p; a.atol_ext = a.rtol_ext + pi.n; }
   const bool implicit_method = o->method == IVPB_RADAU || o->method == IVPB_BDF;
-  const int strict = ((o->flags & IVPB_FLAG_STRICT_FP) || (implicit_method && !(o->flags & IVPB_FLAG_FAST_FP))) ? 1 : 0;
+  const int strict = ctx->fp_override >= 0 ? ctx->fp_override
+                                           : ((o->flags & IVPB_FLAG_STRICT_FP) || (implicit_method && !(o->flags & IVPB_FLAG_FAST_FP))) ? 1 : 0;
   const int block = 128;
   const bool warp_mode = pi.n > ivpb::MAX_N;      // one trajectory per warp (WarpLayout, ivpb_erk.cuh)
 
@@ -563,7 +590,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   else if (pi.nev > 0) feat = 3;       // K_OUT | K_EVENTS: events always run (they can terminate)
   else if (want_out) feat = 1;         // K_OUT
 
-  CK(cudaMemsetAsync(dev.queue, 0, sizeof(u64), stream));
+  CK(cudaMemsetAsync(dev.queue + slot, 0, sizeof(u64), stream));
 
   if (pi.user) {
     if (pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF)) {
@@ -582,19 +609,16 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
 
   const void* kern = nullptr;
   int kblock = block, ksmem = 0, kunits = 0;
-  {   // EXPERIMENT knobs (to be replaced by defaults once measured)
-    const char* e1 = getenv("IVPB_BLOCK_SYNC");
-    const char* e2 = getenv("IVPB_BLOCK_THREADS");
-    if (e1 && !warp_mode) a.block_sync = atoi(e1);
-    if (e2 && !warp_mode && pi.n > 4 && !implicit_method) kblock = atoi(e2);
-  }
   if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
     kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem, &kunits);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: the per-warp matrices of this state size do not fit shared memory");
     if (ksmem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
   } else {
-    kern = BUILTIN[problem][strict](o->method, feat, nullptr);
+    ivpb_pinfo kinfo;
+    kinfo.block = block;
+    kern = BUILTIN[problem][strict](o->method, feat, &kinfo);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
+    kblock = kinfo.block;
     if (warp_mode) {
       ksmem = (kblock / 32) * 2 * pi.n * (int)sizeof(double);
       if (ksmem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
@@ -621,6 +645,179 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
 }
 
 // ------------------------------------------------------------------------------------------------
+// Floating-point mode of a solve (which of the two kernel builds runs).
+//
+//   strict  every reference operation one for one (no FMA contraction, correctly rounded div / sqrt, glibc's pow):
+//           bit-identical to the reference's operation sequence on every workload, ~2x the instructions.
+//   fma     contracted multiply-adds and slow-path-free controller arithmetic: a few ulp per step away from it.
+//
+// A few ulp are harmless for a well-conditioned ensemble (north star: all values inside max(10 rtol |y|, 10 atol), step
+// counts equal) and fatal for an ill-conditioned one (CR3BP at rtol 1e-10: orbits amplify a last-bit difference by 1e7,
+// 19 % of the trajectories stay inside the tolerance).  Which of the two a given ensemble is cannot be read off the
+// options, so unless the caller decides (IVPB_FLAG_STRICT_FP / IVPB_FLAG_FAST_FP) the runtime MEASURES it: the first solve
+// of a configuration integrates a sample of the ensemble (up to 8192 trajectories, evenly strided) with both builds and
+// compares them on the device; the FMA build is used only if every sampled trajectory ends with the same status,
+// inside the north-star tolerance of the strict result, and >= 99 % of them with identical accepted / rejected step
+// counts.  The verdict is cached per configuration (problem, method, tolerances, span, step limits, t_eval, events);
+// both pilot kernels fit in one wave, so the pilot costs about two single-trajectory latencies, once.
+// RADAU / BDF stay strict by default as before (IVPB_FLAG_FAST_FP opts out): stiff ensembles lose step-count parity under
+// any perturbation and gain only 17-29 % from the FMA build.
+namespace {
+
+__global__ void pilot_gather_kernel(const double* src, int w, long long N, int S, double* dst) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const long long i = (long long)k * N / S;
+  for (int c = 0; c < w; ++c) dst[(long long)k * w + c] = src[i * w + c];
+}
+
+struct PilotTol { double rtol[ivpb::MAX_N], atol[ivpb::MAX_N]; };
+
+// res[0] status mismatches, res[1] accepted / rejected step-count mismatches, res[2] trajectories outside
+// max(10 rtol |y|, 10 atol) (final state, elementwise; final time likewise with the first component's tolerances)
+__global__ void pilot_compare_kernel(int S, int n, PilotTol tol, const int* st_a, const unsigned* cn_a, const double* tf_a,
+                                     const double* yf_a, const int* st_b, const unsigned* cn_b, const double* tf_b,
+                                     const double* yf_b, unsigned* res) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  if (st_a[k] != st_b[k]) atomicAdd(res + 0, 1u);
+  if (cn_a[k * 6 + 4] != cn_b[k * 6 + 4] || cn_a[k * 6 + 5] != cn_b[k * 6 + 5]) atomicAdd(res + 1, 1u);
+  bool bad = false;
+  for (int c = 0; c < n; ++c) {
+    const int tc = c < ivpb::MAX_N ? c : 0;
+    const double ref = yf_a[(long long)k * n + c], d = fabs(yf_b[(long long)k * n + c] - ref);
+    if (!(d <= fmax(10.0 * tol.rtol[tc] * fabs(ref), 10.0 * tol.atol[tc]))) bad = true;
+  }
+  if (!(fabs(tf_b[k] - tf_a[k]) <= fmax(10.0 * tol.rtol[0] * fabs(tf_a[k]), 10.0 * tol.atol[0]))) bad = true;
+  if (bad) atomicAdd(res + 2, 1u);
+}
+
+uint64_t fnv(uint64_t h, const void* p, size_t nbytes) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < nbytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+uint64_t fp_key(int problem, const ProblemInfo& pi, const ivpb_options* o, double t0, double tf) {
+  uint64_t h = 1469598103934665603ull;
+  h = fnv(h, &problem, sizeof(problem));
+  h = fnv(h, &o->method, sizeof(o->method));
+  h = fnv(h, o->rtol, sizeof(double) * (o->n_rtol == 1 ? 1 : pi.n));
+  h = fnv(h, o->atol, sizeof(double) * (o->n_atol == 1 ? 1 : pi.n));
+  h = fnv(h, &t0, 8); h = fnv(h, &tf, 8);
+  const int has[4] = {o->has_first_step, o->has_max_step, o->has_max_steps, o->has_t_eval};
+  h = fnv(h, has, sizeof(has));
+  if (o->has_first_step) h = fnv(h, &o->first_step, 8);
+  if (o->has_max_step) h = fnv(h, &o->max_step, 8);
+  if (o->has_max_steps) h = fnv(h, &o->max_steps, 8);
+  if (o->has_t_eval && o->n_t_eval > 0) h = fnv(h, o->t_eval, sizeof(double) * o->n_t_eval);
+  if (o->n_event_cfg > 0) {
+    h = fnv(h, o->ev_direction, sizeof(int32_t) * o->n_event_cfg);
+    h = fnv(h, o->ev_terminal_count, sizeof(int64_t) * o->n_event_cfg);
+  }
+  const int misc[3] = {o->user_solout, o->max_out > 0 ? 1 : 0, o->max_events};
+  h = fnv(h, misc, sizeof(misc));
+  return h;
+}
+
+}  // namespace
+
+// Decide the floating-point mode of this solve; *strict_out = 1 (strict build) or 0 (FMA build).  `on_device`: y0 / params
+// are device-accessible pointers (device 0) valid in `stream` order; otherwise they are host pointers.
+static int resolve_fp(ivpb_ctx* ctx, int problem, const ProblemInfo& pi, const ivpb_options* o, int64_t N, double t0,
+                      double tf, const double* y0, const double* params, bool on_device, cudaStream_t stream,
+                      int* strict_out) {
+  const bool implicit_m = o->method == IVPB_RADAU || o->method == IVPB_BDF;
+  int32_t* L = ctx->last_fp;
+  for (int i = 0; i < 6; ++i) L[i] = 0;
+  if (o->flags & IVPB_FLAG_STRICT_FP) { L[0] = 1; L[1] = 0; *strict_out = 1; return 0; }
+  if (o->flags & IVPB_FLAG_FAST_FP) { L[0] = 0; L[1] = 0; *strict_out = 0; return 0; }
+  if (implicit_m) { L[0] = 1; L[1] = 1; *strict_out = 1; return 0; }           // method default
+  if (N == 0 || pi.n == 0 || std::fabs(tf - t0) < 1e-15) { L[1] = 1; *strict_out = 0; return 0; }
+  const uint64_t key = fp_key(problem, pi, o, t0, tf);
+  for (const auto& c : ctx->fp_cache)
+    if (c.key == key) {
+      L[0] = c.strict; L[1] = 2;
+      for (int i = 0; i < 4; ++i) L[2 + i] = c.info[i];
+      *strict_out = c.strict;
+      return 0;
+    }
+  // ---- pilot: the same sample with both builds, on device 0 ----
+  Device& dev = ctx->devs[0];
+  CK(cudaSetDevice(dev.id));
+  const int S = (int)std::min<int64_t>(N, 8192);
+  const int n = pi.n, p = pi.p;
+  CK(ctx->pilot_in.ensure(sizeof(double) * (size_t)S * (n + p)));
+  double* s_y0 = (double*)ctx->pilot_in.p;
+  double* s_par = s_y0 + (size_t)S * n;
+  if (on_device) {
+    pilot_gather_kernel<<<(S + 127) / 128, 128, 0, stream>>>(y0, n, (long long)N, S, s_y0);
+    if (p > 0) pilot_gather_kernel<<<(S + 127) / 128, 128, 0, stream>>>(params, p, (long long)N, S, s_par);
+    CK(cudaGetLastError());
+  } else {
+    std::vector<double> h((size_t)S * (n + p));
+    for (int k = 0; k < S; ++k) {
+      const int64_t i = (int64_t)k * N / S;
+      std::memcpy(&h[(size_t)k * n], y0 + i * n, sizeof(double) * n);
+      if (p > 0) std::memcpy(&h[(size_t)S * n + (size_t)k * p], params + i * p, sizeof(double) * p);
+    }
+    CK(cudaMemcpyAsync(s_y0, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  const size_t per_traj = 4 + 24 + 8 + 8 * (size_t)n;
+  ivpb_outputs po[2];
+  for (int m = 0; m < 2; ++m) {
+    CK(ctx->pilot_out[m].ensure(per_traj * S + 64));
+    char* b = (char*)ctx->pilot_out[m].p;
+    std::memset(&po[m], 0, sizeof(po[m]));
+    po[m].y_final = (double*)b; b += 8 * (size_t)n * S;
+    po[m].t_final = (double*)b; b += 8 * (size_t)S;
+    po[m].counters = (uint32_t*)b; b += 24 * (size_t)S;
+    po[m].status = (int32_t*)b;
+  }
+  ivpb_options po_opt = *o;
+  po_opt.dense_output = 0;
+  for (int m = 0; m < 2; ++m) {       // m = 0: strict (the reference's arithmetic), m = 1: FMA
+    ctx->fp_override = m == 0 ? 1 : 0;
+    const int rc = launch_shard(ctx, dev, problem, pi, &po_opt, S, t0, tf, s_y0, p > 0 ? s_par : nullptr, &po[m], stream,
+                                false, 0, true);
+    ctx->fp_override = -1;
+    if (rc) return rc;
+  }
+  CK(ctx->pilot_res.ensure(16));
+  CK(cudaMemsetAsync(ctx->pilot_res.p, 0, 16, stream));
+  PilotTol tol;
+  for (int i = 0; i < ivpb::MAX_N; ++i) {
+    tol.rtol[i] = o->rtol[o->n_rtol == 1 ? 0 : (i < n ? i : 0)];
+    tol.atol[i] = o->atol[o->n_atol == 1 ? 0 : (i < n ? i : 0)];
+  }
+  if (n > ivpb::MAX_N) {      // warp-per-trajectory systems: compare with the tightest tolerance
+    for (int i = 0; i < n; ++i) {
+      tol.rtol[0] = std::fmin(tol.rtol[0], o->rtol[o->n_rtol == 1 ? 0 : i]);
+      tol.atol[0] = std::fmin(tol.atol[0], o->atol[o->n_atol == 1 ? 0 : i]);
+    }
+  }
+  pilot_compare_kernel<<<(S + 127) / 128, 128, 0, stream>>>(S, n, tol, po[0].status, po[0].counters, po[0].t_final,
+                                                           po[0].y_final, po[1].status, po[1].counters, po[1].t_final,
+                                                           po[1].y_final, (unsigned*)ctx->pilot_res.p);
+  CK(cudaGetLastError());
+  unsigned res[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(res, ctx->pilot_res.p, 12, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  ctx->launches += 2 + (on_device ? (p > 0 ? 2 : 1) : 0);
+  const bool fma_ok = res[0] == 0 && res[2] == 0 && (uint64_t)res[1] * 100 <= (uint64_t)S;
+  ivpb_ctx::FpChoice c;
+  c.key = key; c.strict = fma_ok ? 0 : 1;
+  c.info[0] = S; c.info[1] = (int32_t)res[0]; c.info[2] = (int32_t)res[1]; c.info[3] = (int32_t)res[2]; c.info[4] = 0;
+  if (ctx->fp_cache.size() >= 64) ctx->fp_cache.erase(ctx->fp_cache.begin());
+  ctx->fp_cache.push_back(c);
+  L[0] = c.strict; L[1] = 3;
+  for (int i = 0; i < 4; ++i) L[2 + i] = c.info[i];
+  *strict_out = c.strict;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 extern "C" {
 
 int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
@@ -643,7 +840,12 @@ int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
     cudaError_t err = cudaSetDevice(id);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, id);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMalloc((void**)&d.queue, sizeof(u64));
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_shared, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&d.queue, sizeof(u64) * MAX_CHUNKS);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&d.chunk_count, sizeof(unsigned) * MAX_CHUNKS);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&d.chunk_flag, sizeof(int) * MAX_CHUNKS, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&d.chunk_flag_dev, d.chunk_flag, 0);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_last, cudaEventDisableTiming);
@@ -680,18 +882,31 @@ void ivpb_destroy(ivpb_ctx* ctx) {
     d.dense_nseg.release(); d.dense_segx.release(); d.dense_segc.release();
     for (auto& b : d.out) b.release();
     if (d.queue) cudaFree(d.queue);
+    if (d.chunk_count) cudaFree(d.chunk_count);
+    if (d.chunk_flag) cudaFreeHost(d.chunk_flag);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
     if (d.ev_done) cudaEventDestroy(d.ev_done);
     if (d.ev_last) cudaEventDestroy(d.ev_last);
+    if (d.ev_shared) cudaEventDestroy(d.ev_shared);
+    if (d.stream2) { cudaStreamSynchronize(d.stream2); cudaStreamDestroy(d.stream2); }
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   for (auto& u : ctx->user) ivpb_nvrtc_release(u);
+  if (!ctx->devs.empty()) {
+    cudaSetDevice(ctx->devs[0].id);
+    ctx->pilot_in.release(); ctx->pilot_out[0].release(); ctx->pilot_out[1].release(); ctx->pilot_res.release();
+  }
   delete ctx;
 }
 
 const char* ivpb_last_error(const ivpb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 int ivpb_device_count(const ivpb_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 uint64_t ivpb_launch_count(const ivpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ivpb_last_fp_mode(const ivpb_ctx* ctx, int32_t info[6]) {
+  if (!ctx) return -1;
+  if (info) for (int i = 0; i < 6; ++i) info[i] = ctx->last_fp[i];
+  return ctx->last_fp[0];
+}
 const char* ivpb_version(void) { return "ivp-b200 0.1.0 (sm_100a)"; }
 
 int ivpb_builtin_problem(ivpb_ctx* ctx, int builtin_id, int* n, int* p, int* n_events) {
@@ -738,8 +953,12 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   // One solve in flight per context: this call's work on device 0 starts after the previous call's (another stream may
   // have been handed in), because the queue counter and the small staging buffers of the device are shared.
   CK(cudaStreamWaitEvent(s0, dev0.ev_last, 0));
+  int fp_strict = 0;
+  if (int rc = resolve_fp(ctx, problem, pi, opt, N, t0, tf, d_y0, d_params, true, s0, &fp_strict)) return rc;
+  struct FpScope { ivpb_ctx* c; ~FpScope() { c->fp_override = -1; } } fp_scope{ctx};
+  ctx->fp_override = fp_strict;
   if (G == 1) {
-    const int rc = launch_shard(ctx, dev0, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, s0);
+    const int rc = launch_shard(ctx, dev0, problem, pi, opt, N, t0, tf, d_y0, d_params, d_out, s0, false, 0, true);
     if (rc == 0) CK(cudaEventRecord(dev0.ev_last, s0));
     return rc;
   }
@@ -780,7 +999,7 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
     ivpb_outputs d;
     array_to_out(loc, &d);
     if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, (const double*)dev.y0.p,
-                              pi.p > 0 ? (const double*)dev.params.p : nullptr, &d, dev.stream))
+                              pi.p > 0 ? (const double*)dev.params.p : nullptr, &d, dev.stream, false, 0, true))
       return rc;
     for (int f = 0; f < OUT_FIELDS; ++f)
       if (loc[f])
@@ -790,7 +1009,7 @@ int ivpb_solve_batch_device(ivpb_ctx* ctx, int problem, const ivpb_options* opt,
   CK(cudaSetDevice(dev0.id));
   {
     const int64_t N0 = N / G;      // shard 0 works in place on the caller's arrays
-    if (int rc = launch_shard(ctx, dev0, problem, pi, opt, N0, t0, tf, d_y0, d_params, d_out, s0)) return rc;
+    if (int rc = launch_shard(ctx, dev0, problem, pi, opt, N0, t0, tf, d_y0, d_params, d_out, s0, false, 0, true)) return rc;
   }
   for (int g = 1; g < G; ++g)
     if (N * (g + 1) / G - N * g / G > 0) CK(cudaStreamWaitEvent(s0, ctx->devs[g].ev_done, 0));
@@ -822,17 +1041,25 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
     ctx->dense.method = opt->method; ctx->dense.n = n; ctx->dense.n_cont = n_cont; ctx->dense.cap = (int)seg_cap;
     ctx->dense.N = N; ctx->dense.lo.assign(G, 0); ctx->dense.count.assign(G, 0);
   }
-  // Zero-copy: a caller buffer that is page-locked host memory (ivpb_host_alloc, cudaHostAlloc/Register, torch
-  // pin_memory) is mapped into the device address space under UVA, so the kernel can read y0 / params from it
-  // at `init` and write the per-trajectory results to it at `finish`, directly over PCIe.  The transfers then
-  // overlap the integration instead of bracketing it (north star: ~80 MB per step moved during a ~15 ms kernel
-  // instead of ~1.5 ms of serial copies).  Only fields every trajectory writes in full take this route; sample
-  // and event blocks (partially written, must read as zero elsewhere) and the dense log are staged as before.
-  // ... unless the shard is integrated in locality order (RADAU / BDF by default, launch_shard): rows would then cross
-  // PCIe out of order, which costs more than the two serial copies it saves (Robertson BDF e2e 27.6 ms mapped).
+  // ---- how the bytes cross PCIe -------------------------------------------------------------------------------------
+  // Inputs.  A caller buffer that is page-locked host memory (ivpb_host_alloc, cudaHostAlloc/Register, torch pin_memory)
+  // is mapped into the device address space under UVA; the kernel reads each trajectory's y0 / params row from it at
+  // `init` (24 bytes per trajectory for the north star), so no H2D copy brackets the integration.  Pageable inputs
+  // are staged with cudaMemcpyAsync.
+  // Outputs.  Results are written to device memory and leave by bulk DMA WHILE the kernel integrates: the shard is one
+  // persistent launch (the work queue keeps every lane busy to the end -- cutting it into several launches was measured
+  // at 2x the device time for CR3BP, whose chunks were under two waves each), but it is divided into chunks of
+  // consecutive trajectories with a completion counter each; the thread that retires a chunk's last trajectory raises
+  // a flag in mapped host memory (chunk_signal, ivpb_erk.cuh), and this thread, polling the flags, enqueues that chunk's
+  // device-to-host copies on a second stream.  Trajectories are handed out in index order, so chunks complete roughly
+  // in order and only the last chunk's copy is exposed.  Round 1 instead let the kernel store results straight into
+  // mapped host memory (IVPB_FLAG_ZEROCOPY_OUT keeps that route): every trajectory then issues four small PCIe writes,
+  // which move at ~8 GB/s -- hidden under a 15 ms kernel, but the bottleneck of every short one (ball + events: 3.5 ms
+  // on the device, 11.0 ms end to end) and of 8 ranks sharing one root complex (N = 8 e2e 18.3 ms against 15.2 ms).
   const bool ordered = (opt->flags & IVPB_FLAG_SORT) ||
                        ((opt->method == IVPB_RADAU || opt->method == IVPB_BDF) && !(opt->flags & IVPB_FLAG_NO_SORT));
   const bool allow_zc = !(opt->flags & IVPB_FLAG_NO_ZEROCOPY) && !ordered;
+  const bool zc_outputs = allow_zc && (opt->flags & IVPB_FLAG_ZEROCOPY_OUT);
   auto mapped = [&](const void* hp) -> char* {
     if (!allow_zc || !hp) return nullptr;
     cudaPointerAttributes at;
@@ -843,22 +1070,46 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   char* zc_par = pi.p > 0 ? mapped(params) : nullptr;
   char* zc_out[OUT_FIELDS];
   for (int f = 0; f < OUT_FIELDS; ++f) {
-    // written in full by every trajectory (ErkTraj::finish); the sample blocks too, once `finish` zero-fills the
-    // slots a trajectory left empty (KArgs::zero_tail) -- t_eval-heavy output (CR3BP: 4.9 KB per trajectory, 5.2 GB per
-    // 2^20) then crosses PCIe WHILE the ensemble integrates instead of as one serial copy after the kernel
+    // fields every trajectory writes in full (ErkTraj::finish); the sample blocks too, because `finish` zero-fills the
+    // slots a trajectory left empty (KArgs::zero_tail)
     const bool whole = f <= OUT_NOUT || f == OUT_EVCOUNT || f == OUT_TOUT || f == OUT_YOUT;
-    zc_out[f] = whole ? mapped(host[f]) : nullptr;
+    zc_out[f] = (whole && zc_outputs) ? mapped(host[f]) : nullptr;
   }
   const bool zero_interval = std::fabs(tf - t0) < 1e-15;       // that kernel writes only the matching samples: stage it
-  if (zero_interval || (host[OUT_TOUT] && !zc_out[OUT_TOUT]) || (host[OUT_YOUT] && !zc_out[OUT_YOUT]))   // both or neither
+  if (zero_interval || n == 0 || (host[OUT_TOUT] && !zc_out[OUT_TOUT]) || (host[OUT_YOUT] && !zc_out[OUT_YOUT]))   // both or neither
     zc_out[OUT_TOUT] = zc_out[OUT_YOUT] = nullptr;
+  size_t out_bytes_per_traj = 0;
+  for (int f = 0; f < OUT_FIELDS; ++f) if (host[f] && !zc_out[f]) out_bytes_per_traj += per[f];
+  int fp_strict = 0;
+  if (int rc = resolve_fp(ctx, problem, pi, opt, N, t0, tf, y0, params, false, ctx->devs[0].stream, &fp_strict)) return rc;
+  struct FpScope { ivpb_ctx* c; ~FpScope() { c->fp_override = -1; } } fp_scope{ctx};
+  ctx->fp_override = fp_strict;
   // static contiguous split [g*N/G, (g+1)*N/G) -- trajectories are independent, no exchange step
+  struct Shard {
+    int64_t lo = 0, Ng = 0, chunk = 0;
+    int C = 0, copied = 0;
+    bool done[MAX_CHUNKS];
+    char* dbase[OUT_FIELDS];
+    bool direct[OUT_FIELDS];
+  };
+  std::vector<Shard> shards(G);
   for (int g = 0; g < G; ++g) {
     Device& dev = ctx->devs[g];
+    Shard& S = shards[g];
     const int64_t lo = N * g / G, hi = N * (g + 1) / G, Ng = hi - lo;
+    S.lo = lo; S.Ng = Ng;
     if (Ng == 0) continue;
     CK(cudaSetDevice(dev.id));
     if (g == 0) CK(cudaStreamWaitEvent(dev.stream, dev.ev_last, 0));    // after a device-buffer solve still in flight on a caller stream
+    // chunks of >= 2 MB of results (smaller copies are latency-bound) and >= 4096 trajectories, at most MAX_CHUNKS
+    int C = 1;
+    if (!zero_interval && n > 0 && out_bytes_per_traj > 0 && !(opt->flags & IVPB_FLAG_NO_PIPELINE)) {
+      const int64_t by_bytes = (int64_t)((out_bytes_per_traj * (size_t)Ng) >> 21), by_count = Ng >> 12;
+      C = (int)std::max<int64_t>(1, std::min<int64_t>(MAX_CHUNKS, std::min(by_bytes, by_count)));
+    }
+    S.C = C; S.chunk = (Ng + C - 1) / C;
+    S.C = (int)((Ng + S.chunk - 1) / S.chunk);
+    for (int c = 0; c < MAX_CHUNKS; ++c) S.done[c] = false;
     const double* d_y0 = zc_y0 ? (const double*)zc_y0 + lo * n : nullptr;
     if (!d_y0 && n > 0) {
       CK(dev.y0.ensure(sizeof(double) * n * Ng));
@@ -875,15 +1126,14 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       }
     }
     void* dptr[OUT_FIELDS];
-    bool direct[OUT_FIELDS];
     for (int f = 0; f < OUT_FIELDS; ++f) {
-      dptr[f] = nullptr; direct[f] = false;
+      S.dbase[f] = nullptr; S.direct[f] = false; dptr[f] = nullptr;
       const bool seg_field = f >= OUT_NSEG && seg_cap > 0;      // the dense log stays on the device even if
       if ((!host[f] && !seg_field) || per[f] == 0) continue;    // the caller wants no host copy of it
-      if (zc_out[f]) { dptr[f] = zc_out[f] + per[f] * lo; direct[f] = true; continue; }
+      if (zc_out[f]) { S.dbase[f] = zc_out[f] + per[f] * lo; S.direct[f] = true; dptr[f] = S.dbase[f]; continue; }
       Buf& b = seg_field ? (f == OUT_NSEG ? dev.dense_nseg : f == OUT_SEGX ? dev.dense_segx : dev.dense_segc) : dev.out[f];
       CK(b.ensure(per[f] * Ng));
-      dptr[f] = b.p;
+      S.dbase[f] = (char*)b.p; dptr[f] = b.p;
     }
     ivpb_outputs d;
     array_to_out(dptr, &d);
@@ -892,24 +1142,57 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       CK(cudaMemsetAsync(d.n_seg, 0, per[OUT_NSEG] * Ng, dev.stream));
     }
     // sample / event slots the kernel does not touch must read as zero on the host
-    if (d.t_out && !direct[OUT_TOUT]) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
-    if (d.y_out && !direct[OUT_YOUT]) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
+    if (d.t_out && !S.direct[OUT_TOUT]) CK(cudaMemsetAsync(d.t_out, 0, per[OUT_TOUT] * Ng, dev.stream));
+    if (d.y_out && !S.direct[OUT_YOUT]) CK(cudaMemsetAsync(d.y_out, 0, per[OUT_YOUT] * Ng, dev.stream));
     if (d.ev_t) CK(cudaMemsetAsync(d.ev_t, 0, per[OUT_EVT] * Ng, dev.stream));
     if (d.ev_y) CK(cudaMemsetAsync(d.ev_y, 0, per[OUT_EVY] * Ng, dev.stream));
-    if (d.ev_count && !direct[OUT_EVCOUNT]) CK(cudaMemsetAsync(d.ev_count, 0, per[OUT_EVCOUNT] * Ng, dev.stream));
-    if (d.n_out && !direct[OUT_NOUT]) CK(cudaMemsetAsync(d.n_out, 0, per[OUT_NOUT] * Ng, dev.stream));
-    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, d_y0, d_par, &d, dev.stream,
-                              direct[OUT_TOUT] || direct[OUT_YOUT]))
-      return rc;
-    for (int f = 0; f < OUT_FIELDS; ++f) {
-      if (!dptr[f] || !host[f] || direct[f]) continue;
-      CK(cudaMemcpyAsync((char*)host[f] + per[f] * lo, dptr[f], per[f] * Ng, cudaMemcpyDeviceToHost, dev.stream));
+    if (d.ev_count && !S.direct[OUT_EVCOUNT]) CK(cudaMemsetAsync(d.ev_count, 0, per[OUT_EVCOUNT] * Ng, dev.stream));
+    if (d.n_out && !S.direct[OUT_NOUT]) CK(cudaMemsetAsync(d.n_out, 0, per[OUT_NOUT] * Ng, dev.stream));
+    const bool flags_on = S.C > 1;
+    if (flags_on) {
+      for (int c = 0; c < S.C; ++c) dev.chunk_flag[c] = 0;
+      CK(cudaMemsetAsync(dev.chunk_count, 0, sizeof(unsigned) * S.C, dev.stream));
     }
+    if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, d_y0, d_par, &d, dev.stream,
+                              S.direct[OUT_TOUT] || S.direct[OUT_YOUT], 0, true, flags_on ? S.chunk : 0))
+      return rc;
+    CK(cudaEventRecord(dev.ev_done, dev.stream));       // "kernel finished": end of the polling loop below
   }
   if (seg_cap > 0) ctx->dense.valid = true;
+  // ---- drain: copy chunks out as their flags come up; what is left when a device's kernel has finished goes last ----
+  auto copy_chunk = [&](int g, int c, cudaStream_t st) -> int {
+    Shard& S = shards[g];
+    const int64_t clo = S.chunk * c, Nc = std::min<int64_t>(S.chunk, S.Ng - clo);
+    for (int f = 0; f < OUT_FIELDS; ++f) {
+      if (!S.dbase[f] || !host[f] || S.direct[f]) continue;
+      CK(cudaMemcpyAsync((char*)host[f] + per[f] * (S.lo + clo), S.dbase[f] + per[f] * clo, per[f] * Nc, cudaMemcpyDeviceToHost, st));
+    }
+    S.done[c] = true; S.copied += 1;
+    return 0;
+  };
+  for (;;) {
+    bool pending = false;
+    for (int g = 0; g < G; ++g) {
+      Shard& S = shards[g];
+      if (S.Ng == 0 || S.copied == S.C) continue;
+      Device& dev = ctx->devs[g];
+      CK(cudaSetDevice(dev.id));
+      const bool kernel_done = S.C == 1 || cudaEventQuery(dev.ev_done) == cudaSuccess;
+      for (int c = 0; c < S.C; ++c) {
+        if (S.done[c]) continue;
+        if (kernel_done) { if (int rc = copy_chunk(g, c, dev.stream)) return rc; }
+        else if (*((volatile int*)dev.chunk_flag + c) != 0) { if (int rc = copy_chunk(g, c, dev.stream2)) return rc; }
+      }
+      if (S.copied < S.C) pending = true;
+    }
+    if (!pending) break;
+  }
+  cudaGetLastError();      // cudaEventQuery's cudaErrorNotReady is not an error
   for (int g = 0; g < G; ++g) {
+    if (shards[g].Ng == 0) continue;
     CK(cudaSetDevice(ctx->devs[g].id));
     CK(cudaStreamSynchronize(ctx->devs[g].stream));
+    CK(cudaStreamSynchronize(ctx->devs[g].stream2));
   }
   CK(cudaSetDevice(ctx->devs[0].id));
   return 0;
@@ -1098,6 +1381,70 @@ extern "C" int ivpb_debug_fastmath(const double* x, int n, double* r_rcp, double
   cudaMemcpy(r_rcp, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaMemcpy(r_rsqrt, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaError_t e = cudaMemcpy(r_rroot8, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
+}
+
+// Debug hook: ivpb::ex::div / ex::sqrt (ivpb_exact.cuh) next to the plain operators on the device, so a test can
+// compare them bit for bit.  r_div_ex / r_div_ref = a / b, r_sqrt_ex / r_sqrt_ref = sqrt(a); the shared-reciprocal form
+// is exercised by dividing a and a * 0.75 by the same refined reciprocal (r_div2_ex / r_div2_ref = 0.75 a / b).
+#include "ivpb_exact.cuh"
+namespace {
+__global__ void exact_kernel(const double* a, const double* b, long long n, double* r_div_ex, double* r_div_ref,
+                             double* r_div2_ex, double* r_div2_ref, double* r_sqrt_ex, double* r_sqrt_ref) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b[i];
+  const ivpb::ex::Recip r = ivpb::ex::recip(y);
+  r_div_ex[i] = ivpb::ex::div(x, r);
+  r_div2_ex[i] = ivpb::ex::div(__dmul_rn(x, 0.75), r);
+  r_div_ref[i] = __ddiv_rn(x, y);
+  r_div2_ref[i] = __ddiv_rn(__dmul_rn(x, 0.75), y);
+  r_sqrt_ex[i] = ivpb::ex::sqrt(x);
+  r_sqrt_ref[i] = __dsqrt_rn(x);
+}
+// Fully on-device variant for large sweeps: operands from a counter-based generator, only the mismatch count returns.
+__global__ void exact_sweep_kernel(unsigned long long seed, long long n, int mode, unsigned long long* mismatches) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto mix = [](unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  unsigned long long ua = mix(seed + 2ull * (unsigned long long)i), ub = mix(seed + 2ull * (unsigned long long)i + 1ull);
+  if (mode == 0) {          // moderate exponents (what the solvers see): 2^-64 .. 2^64, random signs and mantissas
+    ua = (ua & 0x800fffffffffffffull) | ((unsigned long long)(959 + (ua >> 52) % 128) << 52);
+    ub = (ub & 0x800fffffffffffffull) | ((unsigned long long)(959 + (ub >> 52) % 128) << 52);
+  } else if (mode == 2) {   // mantissas with long runs of ones / zeros (the hard cases of Markstein-type corrections)
+    const int sa = (int)(ua >> 58) % 52, sb = (int)(ub >> 58) % 52;
+    ua = (ua & 0x8000000000000000ull) | (1023ull << 52) | ((0x000fffffffffffffull >> sa) ^ ((ua >> 3) & 7ull));
+    ub = (ub & 0x8000000000000000ull) | (1023ull << 52) | ((0x000fffffffffffffull << sb) & 0x000fffffffffffffull) | ((ub >> 3) & 7ull);
+  }                         // mode 1: raw bit patterns (every class: zeros, subnormals, inf, NaN, huge)
+  const double x = __longlong_as_double((long long)ua), y = __longlong_as_double((long long)ub);
+  const double q = ivpb::ex::div(x, y), qr = __ddiv_rn(x, y);
+  const double s = ivpb::ex::sqrt(x), sr = __dsqrt_rn(x);
+  const bool dq = !(__double_as_longlong(q) == __double_as_longlong(qr) || (q != q && qr != qr));
+  const bool ds = !(__double_as_longlong(s) == __double_as_longlong(sr) || (s != s && sr != sr));
+  if (dq) atomicAdd(mismatches, 1ull);
+  if (ds) atomicAdd(mismatches + 1, 1ull);
+}
+}  // namespace
+extern "C" int ivpb_debug_exact(const double* a, const double* b, long long n, double* out6) {
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * 8 * (size_t)n) != cudaSuccess) return IVPB_ERR_CUDA;
+  cudaMemcpy(d, a, sizeof(double) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+  exact_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, d + n, n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, d + 6 * n, d + 7 * n);
+  cudaError_t e = cudaMemcpy(out6, d + 2 * n, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
+}
+extern "C" int ivpb_debug_exact_sweep(unsigned long long seed, long long n, int mode, unsigned long long* mismatches2) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc((void**)&d, 16) != cudaSuccess) return IVPB_ERR_CUDA;
+  cudaMemset(d, 0, 16);
+  exact_sweep_kernel<<<(unsigned)((n + 255) / 256), 256>>>(seed, n, mode, d);
+  cudaError_t e = cudaMemcpy(mismatches2, d, 16, cudaMemcpyDeviceToHost);
   cudaFree(d);
   return e == cudaSuccess ? 0 : IVPB_ERR_CUDA;
 }

@@ -10,6 +10,7 @@
 
 // What the runtime needs to know about a problem (filled by the per-problem lookup of ivpb_inst.cu).
 struct ivpb_pinfo {
+  int block;                // threads per block of the kernel the lookup returned (explicit methods)
   int n, p, nev, has_jac;   // has_jac: bit 0 = analytic Jacobian, bit 1 = mass matrix (IVP::mass), bit 2 = own SolOut hook
   int ev_dir[8];          // IVP::event_config defaults
   long long ev_term[8];
