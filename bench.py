@@ -358,6 +358,8 @@ def main():
     ap.add_argument("--fast", action="store_true", help="force the FMA-contracted kernel variant (A/B)")
     ap.add_argument("--fast-implicit", action="store_true", help="alias of --fast (RADAU / BDF workloads)")
     ap.add_argument("--no-zerocopy", action="store_true", help="e2e arm: staged H2D/D2H copies instead of mapped pinned buffers (A/B)")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e arm: copy the results out after the kernel instead of chunk by chunk while it runs (A/B)")
+    ap.add_argument("--zerocopy-out", action="store_true", help="e2e arm: kernel stores results straight into the mapped pinned buffers (round-1 route, A/B)")
     ap.add_argument("--no-sort", action="store_true", help="RADAU / BDF: index order instead of the locality order of the ensemble (A/B)")
     ap.add_argument("--sort", action="store_true", help="explicit methods: locality order too (A/B)")
     ap.add_argument("--jac-mode", type=int, default=0, help="implicit workloads: 0 finite differences, 1 analytic")
@@ -395,7 +397,8 @@ def main():
     fast = args.fast or args.fast_implicit
     flags = (api.IVPB_FLAG_NO_REFILL if args.static else 0) | (api.IVPB_FLAG_STRICT_FP if args.strict else 0) | \
         (api.IVPB_FLAG_NO_ZEROCOPY if args.no_zerocopy else 0) | (api.IVPB_FLAG_NO_SORT if args.no_sort else 0) | \
-        (api.IVPB_FLAG_SORT if args.sort else 0) | (api.IVPB_FLAG_FAST_FP if fast else 0)
+        (api.IVPB_FLAG_SORT if args.sort else 0) | (api.IVPB_FLAG_FAST_FP if fast else 0) | \
+        (api.IVPB_FLAG_NO_PIPELINE if args.no_pipeline else 0) | (api.IVPB_FLAG_ZEROCOPY_OUT if args.zerocopy_out else 0)
     ctx = api.Context([local_rank])
     arm = Arm(args, ctx, dev, local_rank, Nper, offset, flags)
     problem, ne, n_te = arm.problem, arm.ne, arm.n_te

@@ -67,6 +67,11 @@ struct KArgs {
   i64 chunk_size;
   unsigned* chunk_count;     // device, [chunks], zeroed before the launch: trajectories of the chunk retired so far
   int* chunk_flag;           // page-locked host memory mapped into the device address space, [chunks]
+  // Arrival flags of the host-buffer path: y0 / params reach the device in chunks of `in_chunk` consecutive trajectories
+  // while the kernel is already running; in_flag[c] (device memory, written by the copy engine after chunk c's data)
+  // tells the scheduler that the rows of chunk c may be read.  in_chunk == 0: everything is resident at launch.
+  i64 in_chunk;
+  const int* in_flag;
   // dense_output: per-trajectory interpolant log (src/solve/solout.rs:141-146); seg_cap == 0 => off
   int seg_cap, n_cont;   // n_cont = coeffs_per_state * n doubles per segment
   int* seg_n;

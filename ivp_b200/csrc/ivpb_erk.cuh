@@ -23,7 +23,8 @@
 
 namespace ivpb {
 
-enum { K_OUT = 1, K_EVENTS = 2, K_USER = 4 };   // kernel feature bits (template parameter FEAT); K_USER: the problem's own SolOut
+enum { K_OUT = 1, K_EVENTS = 2, K_USER = 4 };
+enum { K_NOPIPE = 0x100 };   // lookup flag (not a template feature bit): the twin compiled without arrival / completion flags   // kernel feature bits (template parameter FEAT); K_USER: the problem's own SolOut
 
 // Multiply-add of the solver core.  Default build: an explicit fma, so the result does not depend on which
 // products a particular compiler run chooses to contract -- the static, work-queue and NVRTC instances of a
@@ -1149,11 +1150,24 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #define IVPB_BATCH_NUM 1      // heavy lanes wait until NUM/DEN of the active lanes are heavy; measured on the BDF
 #define IVPB_BATCH_DEN 1      // ensembles: 1/2 -> 89 ms, 3/4 -> 80 ms, 1/1 -> 62 ms (Robertson, 2^18 trajectories)
 #endif
+// Arrival flags (KArgs::in_*): block until the copy engine has delivered the input rows of trajectory `idx`.  The flag is
+// written by a DMA that is stream-ordered after the chunk's data, so a set flag means the rows are in device memory; the
+// rows are read for the first time after this point (nothing stale can sit in L1).
+__device__ __forceinline__ void wait_input(const KArgs& a, i64 idx) {
+  if (a.in_chunk <= 0) return;                         // uniform over the grid
+  const volatile int* f = a.in_flag + idx / a.in_chunk;
+  while (*f == 0) __nanosleep(200);
+  __threadfence();
+}
+
 // Completion flags (KArgs::chunk_*): called by all lanes of a converged warp after `finish`; `fin` marks the lanes whose
 // trajectory `idx` has just written its results.  Lanes retiring trajectories of the same chunk are counted with one
 // atomic; every result store is fenced before the count that covers it, so when the count is complete the chunk's
 // results are visible device-wide (the "last block" pattern), and the flag store tells the host it may copy them.
-__device__ __forceinline__ void chunk_signal(const KArgs& a, bool fin, i64 idx) {
+static __device__ __noinline__ void chunk_signal(const KArgs& a, bool fin, i64 idx) {
+#ifdef IVPB_NO_CHUNK_SIGNAL
+  return;
+#endif
   if (a.chunk_size <= 0) return;                       // uniform over the grid
   const unsigned m = __ballot_sync(0xffffffffu, fin);
   if (!fin) return;
@@ -1200,7 +1214,11 @@ __device__ __forceinline__ void chunk_signal_warp(const KArgs& a, i64 idx) {
 // 256-thread block per SM (all eight resident warps in step).  It does nothing for code that fits the cache or is not
 // fetch-bound (FMA build of the same kernel 103.5 -> 104.4 ms; north star, Lorenz, RADAU / BDF: 0.5-15 % slower), hence a
 // per-kernel switch.  Results are unaffected: only the interleaving of independent trajectories changes.
-template <class Traj>
+//
+// PIPE = false compiles the arrival / completion flags out altogether: the device-resident entry point
+// (ivpb_solve_batch_device) never uses them, and even the uniform early-outs cost the north-star kernel 3 % (15.0 -> 15.46 ms
+// per 2^20 trajectories, measured A/B on one box).
+template <class Traj, bool PIPE = true>
 __device__ __forceinline__ void run_schedule(const KArgs& a) {
   Traj T;
   const unsigned FULL = 0xffffffffu;
@@ -1228,9 +1246,11 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
       bool fin0 = false;
       if (!active && idx < a.N) {
         active = true;
-        if (T.init(a, a.perm ? (i64)a.perm[idx] : idx)) { T.finish(a); active = false; fin0 = true; }
+        const i64 tidx = a.perm ? (i64)a.perm[idx] : idx;
+        if constexpr (PIPE) wait_input(a, tidx);
+        if (T.init(a, tidx)) { T.finish(a); active = false; fin0 = true; }
       }
-      chunk_signal(a, fin0, T.idx);
+      if constexpr (PIPE) chunk_signal(a, fin0, T.idx);
     }
     if constexpr (bsync) {
       // block-uniform decisions: leave when no lane of the block has work and every warp has seen the end of the queue
@@ -1261,13 +1281,13 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
       if (run) done = T.step(a);
     } while (!(bsync ? (__syncthreads_or(done ? 1 : 0) != 0) : (__any_sync(FULL, done) != 0)));
     if (done) { T.finish(a); active = false; }
-    chunk_signal(a, done, T.idx);
+    if constexpr (PIPE) chunk_signal(a, done, T.idx);
   }
 }
 
-template <class Prob, int METHOD, int FEAT>
+template <class Prob, int METHOD, int FEAT, bool PIPE = true>
 __device__ __forceinline__ void erk_body(const KArgs& a) {
-  run_schedule<ErkTraj<Prob, METHOD, FEAT>>(a);
+  run_schedule<ErkTraj<Prob, METHOD, FEAT>, PIPE>(a);
 }
 
 // Warp-per-trajectory scheduler: every warp owns one trajectory at a time and pulls the next index from the
@@ -1292,7 +1312,9 @@ __device__ __forceinline__ void run_schedule_warp(const KArgs& a) {
     }
     first = false;
     if (idx >= a.N) break;
-    if (!T.init(a, a.perm ? (i64)a.perm[idx] : idx)) {
+    const i64 tidx = a.perm ? (i64)a.perm[idx] : idx;
+    wait_input(a, tidx);
+    if (!T.init(a, tidx)) {
       while (!T.step(a)) {}
     }
     T.finish(a);

@@ -32,12 +32,23 @@ namespace ivpb {
 // the error scale of a step (reused by every Newton iteration's norm) and the step size h (U1/h, ALPH/h, BETA/h).  A
 // division by a cached divisor then costs DMUL + 2 DFMA + the guard.  The default build keeps its a * rcp(b) and caches
 // the same reciprocals, which does not change its results.
+// A/B switches (measured per workload, see implicit_min_blocks): keep the pivot reciprocals / the per-trip scale and
+// step-size reciprocals in registers (1) or recompute them at every division (0).
+#ifndef IVPB_CACHE_PIV
+#define IVPB_CACHE_PIV 1
+#endif
+#ifndef IVPB_CACHE_SCALE
+#define IVPB_CACHE_SCALE 1
+#endif
 #ifdef IVPB_STRICT
 #define IVPB_DIV(a, b) (ex::div((a), (b)))
 #define IVPB_XDIV(a, b) (ex::div((a), (b)))      // divisions the default build performs with the plain operator
 #define IVPB_SQRT(a) (ex::sqrt(a))
-__device__ __forceinline__ double recip_of(double b) { return ex::recip(b).y; }
-__device__ __forceinline__ double div_by(double a, double b, double y) { ex::Recip r; r.b = b; r.y = y; return ex::div(a, r); }
+template <int KEEP> __device__ __forceinline__ double recip_t(double b) { if constexpr (KEEP) return ex::recip(b).y; else return 0.0; }
+template <int KEEP> __device__ __forceinline__ double div_t(double a, double b, double y) {
+  if constexpr (KEEP) { ex::Recip r; r.b = b; r.y = y; return ex::div(a, r); }
+  else return ex::div(a, b);
+}
 // division by a compile-time constant: y = RN(1 / b), Markstein's correction step (checked on the device against the
 // operator for every constant used, tests/test_gpu_parity.py::test_exact_div_sqrt_bitwise)
 #define IVPB_DIVC(a, c) (div_by((a), (c), 1.0 / (c)))
@@ -45,10 +56,17 @@ __device__ __forceinline__ double div_by(double a, double b, double y) { ex::Rec
 #define IVPB_DIV(a, b) ((a) * fm::rcp(b))
 #define IVPB_XDIV(a, b) ((a) / (b))
 #define IVPB_SQRT(a) (sqrt(a))
-__device__ __forceinline__ double recip_of(double b) { return fm::rcp(b); }
-__device__ __forceinline__ double div_by(double a, double, double y) { return a * y; }
+template <int KEEP> __device__ __forceinline__ double recip_t(double b) { if constexpr (KEEP) return fm::rcp(b); else return 0.0; }
+template <int KEEP> __device__ __forceinline__ double div_t(double a, double b, double y) {
+  if constexpr (KEEP) return a * y; else return a * fm::rcp(b);
+}
 #define IVPB_DIVC(a, c) ((a) / (c))
 #endif
+// pivots of the LU factors / scales and step sizes of one trip
+__device__ __forceinline__ double piv_recip(double b) { return recip_t<IVPB_CACHE_PIV>(b); }
+__device__ __forceinline__ double piv_div(double a, double b, double y) { return div_t<IVPB_CACHE_PIV>(a, b, y); }
+__device__ __forceinline__ double recip_of(double b) { return recip_t<IVPB_CACHE_SCALE>(b); }
+__device__ __forceinline__ double div_by(double a, double b, double y) { return div_t<IVPB_CACHE_SCALE>(a, b, y); }
 
 #ifndef IVPB_REGMAT_MAX
 #define IVPB_REGMAT_MAX 3
@@ -76,7 +94,7 @@ template <int N, class Mat>
 __device__ __forceinline__ bool lu_decomp(Mat& A, int (&ip)[N], double (&dy)[N]) {
   if constexpr (N == 1) {
     ip[0] = 0;
-    dy[0] = recip_of(A(0, 0));
+    dy[0] = piv_recip(A(0, 0));
     return A(0, 0) != 0.0;
   } else {
     bool ok = true;
@@ -96,9 +114,9 @@ __device__ __forceinline__ bool lu_decomp(Mat& A, int (&ip)[N], double (&dy)[N])
         if (m == i) { pivot = A(i, k); A(i, k) = A(k, k); }
       A(k, k) = pivot;
       if (pivot == 0.0) { ok = false; break; }
-      dy[k] = recip_of(pivot);
+      dy[k] = piv_recip(pivot);
 #ifdef IVPB_STRICT
-      const double t = div_by(1.0, pivot, dy[k]);
+      const double t = piv_div(1.0, pivot, dy[k]);
 #else
       const double t = 1.0 / pivot;
 #endif
@@ -117,7 +135,7 @@ __device__ __forceinline__ bool lu_decomp(Mat& A, int (&ip)[N], double (&dy)[N])
         }
       }
     }
-    dy[N - 1] = recip_of(A(N - 1, N - 1));
+    dy[N - 1] = piv_recip(A(N - 1, N - 1));
     return ok && A(N - 1, N - 1) != 0.0;
   }
 }
@@ -128,7 +146,7 @@ template <int N, class Mat>
 __device__ __forceinline__ bool lu_decomp_complex(Mat& R, Mat& I, int (&ip)[N], double (&dy)[N]) {
   if constexpr (N == 1) {
     ip[0] = 0;
-    dy[0] = recip_of(R(0, 0) * R(0, 0) + I(0, 0) * I(0, 0));
+    dy[0] = piv_recip(R(0, 0) * R(0, 0) + I(0, 0) * I(0, 0));
     return fabs(R(0, 0)) + fabs(I(0, 0)) != 0.0;
   } else {
     bool ok = true;
@@ -149,10 +167,10 @@ __device__ __forceinline__ bool lu_decomp_complex(Mat& R, Mat& I, int (&ip)[N], 
       R(k, k) = tr; I(k, k) = ti;
       if (fabs(tr) + fabs(ti) == 0.0) { ok = false; break; }
       const double den = tr * tr + ti * ti;
-      dy[k] = recip_of(den);
+      dy[k] = piv_recip(den);
 #ifdef IVPB_STRICT
-      tr = div_by(tr, den, dy[k]);
-      ti = div_by(-ti, den, dy[k]);
+      tr = piv_div(tr, den, dy[k]);
+      ti = piv_div(-ti, den, dy[k]);
 #else
       tr = tr / den;
       ti = -ti / den;
@@ -192,7 +210,7 @@ __device__ __forceinline__ bool lu_decomp_complex(Mat& R, Mat& I, int (&ip)[N], 
         }
       }
     }
-    dy[N - 1] = recip_of(R(N - 1, N - 1) * R(N - 1, N - 1) + I(N - 1, N - 1) * I(N - 1, N - 1));
+    dy[N - 1] = piv_recip(R(N - 1, N - 1) * R(N - 1, N - 1) + I(N - 1, N - 1) * I(N - 1, N - 1));
     return ok && (fabs(R(N - 1, N - 1)) + fabs(I(N - 1, N - 1)) != 0.0);
   }
 }
@@ -209,7 +227,7 @@ __device__ __forceinline__ void swap_rt(double (&b)[N], int k, int m) {
 template <int N, class Mat>
 __device__ __forceinline__ void lin_solve(const Mat& A, double (&b)[N], const int (&ip)[N], const double (&dy)[N]) {
   if constexpr (N == 1) {
-    b[0] = div_by(b[0], A(0, 0), dy[0]);
+    b[0] = piv_div(b[0], A(0, 0), dy[0]);
   } else {
 #pragma unroll
     for (int k = 0; k < N - 1; ++k) {
@@ -220,13 +238,13 @@ __device__ __forceinline__ void lin_solve(const Mat& A, double (&b)[N], const in
 #pragma unroll
     for (int kb = 1; kb < N; ++kb) {
       const int k = N - kb;
-      b[k] = div_by(b[k], A(k, k), dy[k]);
+      b[k] = piv_div(b[k], A(k, k), dy[k]);
       const double t = -b[k];
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < k) b[i] = IVPB_MA(A(i, k), t, b[i]);
     }
-    b[0] = div_by(b[0], A(0, 0), dy[0]);
+    b[0] = piv_div(b[0], A(0, 0), dy[0]);
   }
 }
 
@@ -236,11 +254,12 @@ __device__ __forceinline__ void cdiv_diag(const Mat& R, const Mat& I, double& br
   const double rr = R(k, k), ii = I(k, k);
 #ifdef IVPB_STRICT
   const double den = rr * rr + ii * ii;         // the divisor whose refined reciprocal dyk is
-  const double tr = div_by(br * rr + bi * ii, den, dyk);
-  const double ti = div_by(bi * rr - br * ii, den, dyk);
+  const double tr = piv_div(br * rr + bi * ii, den, dyk);
+  const double ti = piv_div(bi * rr - br * ii, den, dyk);
 #else
-  const double tr = (br * rr + bi * ii) * dyk;
-  const double ti = (bi * rr - br * ii) * dyk;
+  const double den = rr * rr + ii * ii;
+  const double tr = piv_div(br * rr + bi * ii, den, dyk);
+  const double ti = piv_div(bi * rr - br * ii, den, dyk);
 #endif
   br = tr; bi = ti;
 }
@@ -304,8 +323,8 @@ __device__ __forceinline__ void eval_jac(const KArgs& a, double x, const double*
     yp[col] = yo + pert;
     Prob::ode(x, yp, p, fp);
     yp[col] = yo;
-#pragma unroll
     const double perty = recip_of(pert);
+#pragma unroll
     for (int row = 0; row < N; ++row) {
 #ifdef IVPB_STRICT
       J(row, col) = div_by(fp[row] - fo[row], pert, perty);

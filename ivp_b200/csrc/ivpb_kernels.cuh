@@ -30,9 +30,10 @@ template <class Prob, int METHOD, int FEAT>
 __host__ __device__ constexpr int erk_block_threads() {
   return (ErkTraj<Prob, METHOD, FEAT>::BLOCK_SYNC && Prob::N > 4) ? 2 * IVPB_BLOCK : IVPB_BLOCK;
 }
-template <class Prob, int METHOD, int FEAT>
+// PIPE: with (host-buffer path) or without (device-resident path) the arrival / completion flags of run_schedule.
+template <class Prob, int METHOD, int FEAT, bool PIPE = true>
 __global__ void __launch_bounds__((erk_block_threads<Prob, METHOD, FEAT>()), (Prob::N <= 2 ? ((FEAT & K_USER) ? 5 : IVPB_MB_SMALL) : (Prob::N <= 4 ? IVPB_MB_MID : IVPB_MB_BIG))) erk_kernel(const __grid_constant__ KArgs a) {
-  erk_body<Prob, METHOD, FEAT>(a);
+  erk_body<Prob, METHOD, FEAT, PIPE>(a);
 }
 
 // Kernel variants per (problem, method): feature 0 (final state only), K_OUT (sampled output),
@@ -40,6 +41,11 @@ __global__ void __launch_bounds__((erk_block_threads<Prob, METHOD, FEAT>()), (Pr
 template <class Prob, int METHOD>
 __host__ inline const void* erk_lookup_feat(int feat) {
   switch (feat) {
+    case K_NOPIPE: return (const void*)&erk_kernel<Prob, METHOD, 0, false>;
+    case K_NOPIPE | K_OUT: return (const void*)&erk_kernel<Prob, METHOD, K_OUT, false>;
+    case K_NOPIPE | K_OUT | K_EVENTS:
+      if constexpr (Prob::NEV > 0) return (const void*)&erk_kernel<Prob, METHOD, K_OUT | K_EVENTS, false>;
+      else return nullptr;
     case 0: return (const void*)&erk_kernel<Prob, METHOD, 0>;
     case K_OUT: return (const void*)&erk_kernel<Prob, METHOD, K_OUT>;
     case K_OUT | K_EVENTS:
@@ -63,7 +69,7 @@ template <class Prob, int METHOD>
 __host__ inline const void* erk_lookup_feat_any(int feat) {
   if constexpr (Prob::N <= MAX_N) return erk_lookup_feat<Prob, METHOD>(feat);
   else {
-    switch (feat) {
+    switch (feat & ~K_NOPIPE) {      // the warp kernels have no twin: one flag test per trajectory is nothing there
       case 0: return (const void*)&erk_warp_kernel<Prob, METHOD, 0>;
       case K_OUT: return (const void*)&erk_warp_kernel<Prob, METHOD, K_OUT>;
       case K_OUT | K_EVENTS:

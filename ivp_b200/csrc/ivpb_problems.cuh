@@ -245,6 +245,28 @@ struct PMedakzo64 : ProblemDefaults<64, 0, 0> {
     const double zp = z(t, y, 2 * j + 2), zm = z(t, y, 2 * j - 2);
     return alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
   }
+  // analytic Jacobian for jac_mode = 1 (row-major 64 x 64); oracle/problems.hpp Medakzo64::jac holds the same expressions
+  static constexpr bool HAS_JAC = true;
+  IVPB_DEV void jac(double, const double* y, const double*, double* J) {
+    const int NG = 32;
+    const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+    for (int q = 0; q < 64 * 64; ++q) J[q] = 0.0;
+    for (int j = 1; j <= NG; ++j) {
+      const int iu = 2 * (j - 1), iv = iu + 1;
+      const double u = y[iu], v = y[iv];
+      const double w = (double)j * d - 1.0;
+      const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+      const double a1 = alpha / (2.0 * d), b1 = beta / (d * d);
+      double duu = -2.0 * b1 - k * v;                  // d f_u_j / d u_j
+      if (j < NG) J[iu * 64 + iu + 2] = a1 + b1;       // d f_u_j / d u_{j+1}
+      else duu = duu + (a1 + b1);                      // boundary: u_{N+1} = u_N
+      if (j > 1) J[iu * 64 + iu - 2] = b1 - a1;        // d f_u_j / d u_{j-1} (j = 1: z(0) = phi(t), not a state)
+      J[iu * 64 + iu] = duu;
+      J[iu * 64 + iv] = -k * u;                        // d f_u_j / d v_j
+      J[iv * 64 + iu] = -k * v;                        // d f_v_j / d u_j
+      J[iv * 64 + iv] = -k * u;                        // d f_v_j / d v_j
+    }
+  }
 };
 
 }  // namespace ivpb

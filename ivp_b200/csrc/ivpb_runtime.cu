@@ -89,6 +89,8 @@ struct Device {
   unsigned* chunk_count = nullptr;  // completion counters of the host-buffer pipeline (device, MAX_CHUNKS)
   int* chunk_flag = nullptr;        // completion flags (page-locked host memory, mapped; MAX_CHUNKS)
   int* chunk_flag_dev = nullptr;    // the same flags as the device sees them
+  int* in_flag = nullptr;           // arrival flags of the input chunks (device, MAX_CHUNKS; set by H2D copies of `ones`)
+  int* ones = nullptr;              // page-locked host array of MAX_CHUNKS ones, the source of those copies
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // cross-device ordering for the peer-copy path
   cudaEvent_t ev_last = nullptr;    // end of the most recent solve enqueued on this device: the per-device queue counter,
                                     // t_eval / tolerance staging and sort buffers are shared, so solves on one context are
@@ -237,8 +239,6 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
       if (o->atol[i] < 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: negative absolute tolerance");
     if (o->has_first_step && o->first_step == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: first_step is zero");
   }
-  if (o->jac_mode == 1 && pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
-    return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1: the warp-cooperative implicit kernels (n > 8) use the finite-difference Jacobian only");
   if (o->jac_mode == 1 && !(pi.has_jac & 1) && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
   if (o->user_solout) {
@@ -256,8 +256,6 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
       return fail(ctx, IVPB_ERR_CONFIG, "mass_storage = Full, but the problem defines no mass matrix (IVP::mass / ivp_mass)");
     if (o->mass_storage == 0 && has_mass)
       return fail(ctx, IVPB_ERR_CONFIG, "the problem defines a mass matrix: RADAU needs mass_storage = Full (Identity storage cannot hold it)");
-    if (has_mass && pi.n > 8)
-      return fail(ctx, IVPB_ERR_CONFIG, "mass matrices are implemented for the thread-per-trajectory RADAU kernels (n <= 8)");
     const int64_t k1 = o->nind1, k2 = o->nind2 < 0 ? 0 : o->nind2, k3 = o->nind3 < 0 ? 0 : o->nind3;
     if (o->nind1 >= 0 || o->nind2 >= 0 || o->nind3 >= 0) {
       if (o->nind1 < 0 ? (k2 + k3 > pi.n) : (k1 + k2 + k3 != pi.n))
@@ -519,11 +517,12 @@ static int stage_shared(ivpb_ctx* ctx, Device& dev, const ProblemInfo& pi, const
 static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemInfo& pi, const ivpb_options* o,
                         int64_t N, double t0, double tf, const double* d_y0, const double* d_params,
                         const ivpb_outputs* d, cudaStream_t stream, bool zero_tail, int slot, bool upload_shared,
-                        int64_t chunk_size = 0) {
+                        int64_t chunk_size = 0, int64_t in_chunk = 0) {
   if (N == 0) return 0;
   KArgs a;
   fill_args(a, pi, o, N, t0, tf);
   a.zero_tail = zero_tail ? 1 : 0;
+  if (in_chunk > 0) { a.in_chunk = in_chunk; a.in_flag = dev.in_flag; }
   if (chunk_size > 0) { a.chunk_size = chunk_size; a.chunk_count = dev.chunk_count; a.chunk_flag = dev.chunk_flag_dev; }
   // Locality order: on by default for RADAU / BDF, where warp divergence is the bottleneck (Robertson BDF 46.5 -> 23.1 ms,
   // VdP mu=1000 RADAU 54.0 -> 50.1, BDF 79.3 -> 73.2 per 2^18 trajectories); opt-in for the explicit methods, where it gains
@@ -596,7 +595,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     if (pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF)) {
       // warp-cooperative implicit kernels keep one Jacobian per resident warp in global memory; the launch shape is
       // chosen inside ivpb_nvrtc_launch, so size the pool for the most warps an SM can hold (64 warps x SMs)
-      const size_t matd = (size_t)(pi.n | 1) * pi.n;
+      // (+ the mass matrix next to it for RADAU problems that have one)
+      const size_t matd = (size_t)(pi.n | 1) * pi.n * ((o->method == IVPB_RADAU && (pi.has_jac & 2)) ? 2 : 1);
       CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)dev.sms * 64));
       a.scratch = (double*)dev.scratch.p;
     }
@@ -616,7 +616,10 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   } else {
     ivpb_pinfo kinfo;
     kinfo.block = block;
-    kern = BUILTIN[problem][strict](o->method, feat, &kinfo);
+    // no arrival / completion flags in this launch (device-resident entry point, or a host-buffer solve too small to
+    // pipeline): take the twin compiled without them (K_NOPIPE, ivpb_kernels.cuh)
+    const int nopipe = (a.chunk_size <= 0 && a.in_chunk <= 0 && !(feat & 4)) ? 0x100 : 0;
+    kern = BUILTIN[problem][strict](o->method, feat | nopipe, &kinfo);
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
     kblock = kinfo.block;
     if (warp_mode) {
@@ -634,7 +637,7 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   const int64_t need = (N + units_per_block - 1) / units_per_block;
   if (a.static_sched || need < grid) grid = need;
   if (impl_warp) {       // per-warp Jacobian slots in global memory (L2-resident: grid x warps x n (n|1) doubles)
-    const size_t matd = (size_t)(pi.n | 1) * pi.n;
+    const size_t matd = (size_t)(pi.n | 1) * pi.n * ((o->method == IVPB_RADAU && (pi.has_jac & 2)) ? 2 : 1);
     CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)grid * (size_t)(kblock / 32)));
     a.scratch = (double*)dev.scratch.p;
   }
@@ -846,6 +849,9 @@ int ivpb_create(ivpb_ctx** out, const int* device_ids, int n_devices) {
     if (err == cudaSuccess) err = cudaMalloc((void**)&d.chunk_count, sizeof(unsigned) * MAX_CHUNKS);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&d.chunk_flag, sizeof(int) * MAX_CHUNKS, cudaHostAllocMapped | cudaHostAllocPortable);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&d.chunk_flag_dev, d.chunk_flag, 0);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&d.in_flag, sizeof(int) * MAX_CHUNKS);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&d.ones, sizeof(int) * MAX_CHUNKS, cudaHostAllocPortable);
+    if (err == cudaSuccess) for (int k = 0; k < MAX_CHUNKS; ++k) d.ones[k] = 1;
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_last, cudaEventDisableTiming);
@@ -884,6 +890,8 @@ void ivpb_destroy(ivpb_ctx* ctx) {
     if (d.queue) cudaFree(d.queue);
     if (d.chunk_count) cudaFree(d.chunk_count);
     if (d.chunk_flag) cudaFreeHost(d.chunk_flag);
+    if (d.in_flag) cudaFree(d.in_flag);
+    if (d.ones) cudaFreeHost(d.ones);
     if (d.ev_ready) cudaEventDestroy(d.ev_ready);
     if (d.ev_done) cudaEventDestroy(d.ev_done);
     if (d.ev_last) cudaEventDestroy(d.ev_last);
@@ -1058,8 +1066,9 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
   // on the device, 11.0 ms end to end) and of 8 ranks sharing one root complex (N = 8 e2e 18.3 ms against 15.2 ms).
   const bool ordered = (opt->flags & IVPB_FLAG_SORT) ||
                        ((opt->method == IVPB_RADAU || opt->method == IVPB_BDF) && !(opt->flags & IVPB_FLAG_NO_SORT));
-  const bool allow_zc = !(opt->flags & IVPB_FLAG_NO_ZEROCOPY) && !ordered;
-  const bool zc_outputs = allow_zc && (opt->flags & IVPB_FLAG_ZEROCOPY_OUT);
+  // the mapped (zero-copy) routes of round 1, inputs and outputs alike, are opt-in now
+  const bool allow_zc = !(opt->flags & IVPB_FLAG_NO_ZEROCOPY) && !ordered && (opt->flags & IVPB_FLAG_ZEROCOPY_OUT);
+  const bool zc_outputs = allow_zc;
   auto mapped = [&](const void* hp) -> char* {
     if (!allow_zc || !hp) return nullptr;
     cudaPointerAttributes at;
@@ -1110,20 +1119,30 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
     S.C = C; S.chunk = (Ng + C - 1) / C;
     S.C = (int)((Ng + S.chunk - 1) / S.chunk);
     for (int c = 0; c < MAX_CHUNKS; ++c) S.done[c] = false;
+    // Inputs: staged in device memory.  Unless the shard is sorted first (locality order needs every row before the
+    // launch), they arrive in chunks on the copy stream WHILE the kernel runs: the kernel starts after the first chunk
+    // (1 MB) instead of after the whole shard, and the scheduler waits on a chunk's arrival flag before it reads a row.
     const double* d_y0 = zc_y0 ? (const double*)zc_y0 + lo * n : nullptr;
-    if (!d_y0 && n > 0) {
-      CK(dev.y0.ensure(sizeof(double) * n * Ng));
-      CK(cudaMemcpyAsync(dev.y0.p, y0 + lo * n, sizeof(double) * n * Ng, cudaMemcpyHostToDevice, dev.stream));
-      d_y0 = (const double*)dev.y0.p;
-    }
-    const double* d_par = nullptr;
-    if (pi.p > 0) {
-      d_par = zc_par ? (const double*)zc_par + lo * pi.p : nullptr;
-      if (!d_par) {
-        CK(dev.params.ensure(sizeof(double) * pi.p * Ng));
-        CK(cudaMemcpyAsync(dev.params.p, params + lo * pi.p, sizeof(double) * pi.p * Ng, cudaMemcpyHostToDevice, dev.stream));
-        d_par = (const double*)dev.params.p;
-      }
+    const double* d_par = (pi.p > 0 && zc_par) ? (const double*)zc_par + lo * pi.p : nullptr;
+    const bool stage_y0 = !d_y0 && n > 0, stage_par = pi.p > 0 && !d_par;
+    const size_t in_bytes = (stage_y0 ? sizeof(double) * n : 0) + (stage_par ? sizeof(double) * pi.p : 0);
+    int Cin = 0;
+    if (in_bytes > 0 && !ordered && !zero_interval && !(opt->flags & IVPB_FLAG_NO_PIPELINE))
+      Cin = (int)std::max<int64_t>(1, std::min<int64_t>(MAX_CHUNKS, std::min<int64_t>((int64_t)((in_bytes * (size_t)Ng) >> 20), Ng >> 12)));
+    if (Cin < 2) Cin = 0;
+    // chunk boundaries on multiples of 16 rows = whole 128-byte lines of every input array: a line fetched into L1 for the
+    // last rows of one chunk must not contain rows of the next chunk that are still in flight
+    const int64_t in_chunk = Cin ? (((Ng + Cin - 1) / Cin + 15) / 16) * 16 : 0;
+    if (Cin) Cin = (int)((Ng + in_chunk - 1) / in_chunk);
+    if (stage_y0) { CK(dev.y0.ensure(sizeof(double) * n * Ng)); d_y0 = (const double*)dev.y0.p; }
+    if (stage_par) { CK(dev.params.ensure(sizeof(double) * pi.p * Ng)); d_par = (const double*)dev.params.p; }
+    if (Cin) {
+      CK(cudaMemsetAsync(dev.in_flag, 0, sizeof(int) * MAX_CHUNKS, dev.stream2));
+      CK(cudaEventRecord(dev.ev_shared, dev.stream2));
+      CK(cudaStreamWaitEvent(dev.stream, dev.ev_shared, 0));        // the kernel must not see flags of the previous call
+    } else {
+      if (stage_y0) CK(cudaMemcpyAsync(dev.y0.p, y0 + lo * n, sizeof(double) * n * Ng, cudaMemcpyHostToDevice, dev.stream));
+      if (stage_par) CK(cudaMemcpyAsync(dev.params.p, params + lo * pi.p, sizeof(double) * pi.p * Ng, cudaMemcpyHostToDevice, dev.stream));
     }
     void* dptr[OUT_FIELDS];
     for (int f = 0; f < OUT_FIELDS; ++f) {
@@ -1154,9 +1173,16 @@ int ivpb_solve_batch(ivpb_ctx* ctx, int problem, const ivpb_options* opt, int64_
       CK(cudaMemsetAsync(dev.chunk_count, 0, sizeof(unsigned) * S.C, dev.stream));
     }
     if (int rc = launch_shard(ctx, dev, problem, pi, opt, Ng, t0, tf, d_y0, d_par, &d, dev.stream,
-                              S.direct[OUT_TOUT] || S.direct[OUT_YOUT], 0, true, flags_on ? S.chunk : 0))
+                              S.direct[OUT_TOUT] || S.direct[OUT_YOUT], 0, true, flags_on ? S.chunk : 0, in_chunk))
       return rc;
     CK(cudaEventRecord(dev.ev_done, dev.stream));       // "kernel finished": end of the polling loop below
+    for (int c = 0; c < Cin; ++c) {                      // input chunks + their arrival flags, in index order, on the copy stream
+      const int64_t clo = in_chunk * c, Nc = std::min<int64_t>(in_chunk, Ng - clo);
+      if (Nc <= 0) break;
+      if (stage_y0) CK(cudaMemcpyAsync((char*)dev.y0.p + sizeof(double) * n * clo, y0 + (lo + clo) * n, sizeof(double) * n * Nc, cudaMemcpyHostToDevice, dev.stream2));
+      if (stage_par) CK(cudaMemcpyAsync((char*)dev.params.p + sizeof(double) * pi.p * clo, params + (lo + clo) * pi.p, sizeof(double) * pi.p * Nc, cudaMemcpyHostToDevice, dev.stream2));
+      CK(cudaMemcpyAsync(dev.in_flag + c, dev.ones + c, sizeof(int), cudaMemcpyHostToDevice, dev.stream2));
+    }
   }
   if (seg_cap > 0) ctx->dense.valid = true;
   // ---- drain: copy chunks out as their flags come up; what is left when a device's kernel has finished goes last ----

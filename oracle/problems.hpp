@@ -222,6 +222,29 @@ struct Medakzo64 : ProblemBase<Medakzo64, 64, 0, 0> {   // tests/test_ivp.py:77-
       f[i] = alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
     }
   }
+  // analytic Jacobian (row-major 64 x 64; the reference's own MEDAKZO test differentiates numerically, tests/test_ivp.py:244-269):
+  // test infrastructure for jac_mode = 1 on the warp-cooperative kernels -- the device problem uses the same expressions
+  static constexpr bool HAS_JAC = true;
+  void jac(double, const double* y, double* J) const {
+    const int NG = 32;
+    const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+    for (int q = 0; q < 64 * 64; ++q) J[q] = 0.0;
+    for (int j = 1; j <= NG; ++j) {
+      const int iu = 2 * (j - 1), iv = iu + 1;
+      const double u = y[iu], v = y[iv];
+      const double w = (double)j * d - 1.0;
+      const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+      const double a1 = alpha / (2.0 * d), b1 = beta / (d * d);
+      double duu = -2.0 * b1 - k * v;                  // d f_u_j / d u_j
+      if (j < NG) J[iu * 64 + iu + 2] = a1 + b1;       // d f_u_j / d u_{j+1}
+      else duu = duu + (a1 + b1);                      // boundary: u_{N+1} = u_N
+      if (j > 1) J[iu * 64 + iu - 2] = b1 - a1;        // d f_u_j / d u_{j-1} (j = 1: z(0) = phi(t), not a state)
+      J[iu * 64 + iu] = duu;
+      J[iu * 64 + iv] = -k * u;                        // d f_u_j / d v_j
+      J[iv * 64 + iu] = -k * v;                        // d f_v_j / d u_j
+      J[iv * 64 + iv] = -k * u;                        // d f_v_j / d v_j
+    }
+  }
 };
 
 }  // namespace oracle

@@ -91,6 +91,21 @@ struct MassLinear4 : ProblemBase<MassLinear4, 4, 1, 0> {
   }
 };
 
+// M y' = p0 A y, n = 12 (the warp-cooperative device kernels, n > 8): tridiagonal A, full constant M
+struct MassLinear12 : ProblemBase<MassLinear12, 12, 1, 0> {
+  void ode(double, const double* y, double* d) const {
+    for (int i = 0; i < 12; ++i) {
+      const double lo = i > 0 ? y[i - 1] : 0.0, hi = i < 11 ? y[i + 1] : 0.0;
+      d[i] = p[0] * (lo - 2.0 * y[i] + hi);
+    }
+  }
+  static constexpr bool HAS_MASS = true;
+  void mass(double* M) const {
+    for (int i = 0; i < 12; ++i)
+      for (int j = 0; j < 12; ++j) M[i * 12 + j] = (i == j) ? 2.0 + 0.25 * (double)i : 0.25 / (1.0 + (double)(i > j ? i - j : j - i)) * ((i + j) % 2 ? -1.0 : 1.0);
+  }
+};
+
 // fun_medazko at the reference's own size (tests/test_helpers.py:54-80 with n = 200 grid points => 400 states), for the golden
 // numbers of tests/test_ivp.py:245-269 and tests/test_stiff.py:147-183.  (The device kernels stop at n = 84 / 118; this pins
 // the ORACLE's RADAU / BDF / LU / finite-difference Jacobian against the reference's published MEDAKZO values.)

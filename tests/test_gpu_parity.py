@@ -908,8 +908,8 @@ def test_warp_cooperative_implicit_medakzo(oracle, method):
     f = ib.solve_ivp_batch("medakzo64", 0.0, 7.0, ym, None, Options(method=method, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_FAST_FP))
     assert np.array_equal(f.status, o.status)
     assert close(f.y_final, o.y_final, 1e-4, 1e-6).all()
-    with pytest.raises(ib.ConfigError):
-        ib.solve_ivp_batch("medakzo64", 0.0, 1.0, ym, None, Options(method=method, jac_mode=1))
+    with pytest.raises(ib.ConfigError, match="no analytic Jacobian"):          # jac_mode = 1 needs IVP::jac (linear100 has none)
+        ib.solve_ivp_batch("linear100", 0.0, 1.0, np.ones((4, 100)), None, Options(method=method, jac_mode=1))
 
 
 USER_DIFFUSION12 = r"""
@@ -1107,3 +1107,38 @@ def test_vector_tolerances_warp_cooperative_implicit(oracle, method):
     assert np.array_equal(g.y_final, o.y_final)
     scalar = ib.solve_ivp_batch(prob, t0, 2.0, y0, par, Options(method=method, rtol=rtol[0], atol=atol[0], flags=IVPB_FLAG_STRICT_FP))
     assert not np.array_equal(scalar.counters, g.counters)
+
+
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_analytic_jacobian_warp_cooperative_implicit(oracle, method):
+    """jac_mode = 1 (IVP::jac supplied by the problem, reference src/ivp.rs:67) on the warp-per-trajectory implicit
+    kernels (n > 8): MEDAKZO n = 64 with its analytic Jacobian, strict build bit-exact with the oracle using the same
+    Jacobian, njev counted the same, and the trajectory agrees with the finite-difference run; then a user problem
+    (NVRTC, n = 10, 8 < n <= 32: every lane sees the whole state) against the matrix exponential."""
+    from ivp_b200 import api
+    N = 40
+    prob, y0, par, t0, tf = synth.ensemble("medakzo", N)
+    opts = Options(method=method, rtol=1e-5, atol=1e-7, jac_mode=1, flags=IVPB_FLAG_STRICT_FP)
+    g = ib.solve_ivp_batch(prob, t0, 3.0, y0, par, opts)
+    o = oracle.solve_batch(PROBLEMS[prob], t0, 3.0, y0, par, opts)
+    assert np.array_equal(g.status, o.status) and np.all(g.status == 0)
+    assert np.array_equal(g.counters, o.counters) and np.array_equal(g.y_final, o.y_final)
+    fd = ib.solve_ivp_batch(prob, t0, 3.0, y0, par, Options(method=method, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_STRICT_FP))
+    np.testing.assert_allclose(g.y_final, fd.y_final, rtol=2e-3, atol=2e-5)
+    assert not np.array_equal(g.y_final, fd.y_final)            # the two Jacobians differ in the last digits
+
+    n = 10
+    rng = np.random.default_rng(11)
+    A = -np.diag(rng.uniform(0.5, 50.0, n)) + 0.3 * rng.standard_normal((n, n))
+    rows = "\n".join(f"  d[{i}] = " + " + ".join(f"({A[i, j]!r}) * y[{j}]" for j in range(n)) + ";" for i in range(n))
+    jac = "\n".join(f"  J[{i * n + j}] = {A[i, j]!r};" for i in range(n) for j in range(n))
+    src = ("__device__ void ivp_ode(double t, const double* y, const double* p, double* d) {\n" + rows + "\n}\n"
+           "__device__ void ivp_jac(double t, const double* y, const double* p, double* J) {\n" + jac + "\n}\n")
+    user = api.Problem.from_cuda_source(src, n=n, has_jac=True)
+    Y0 = rng.uniform(-1.0, 1.0, (25, n))
+    import scipy.linalg
+    exact = Y0 @ scipy.linalg.expm(A * 1.5).T
+    for jm in (1, 0):
+        r = ib.solve_ivp_batch(user, 0.0, 1.5, Y0, None, Options(method=method, rtol=1e-8, atol=1e-10, jac_mode=jm))
+        assert np.all(r.status == 0) and np.all(r.njev > 0)
+        np.testing.assert_allclose(r.y_final, exact, rtol=2e-5, atol=2e-7)

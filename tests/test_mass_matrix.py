@@ -176,3 +176,54 @@ def test_radau_mass_matrix_user_problem_shared_memory_matrices(oracle):
     r = scipy_api.solve_ivp(SRC_MASS4, (0.0, 1.0), y0[0], method="Radau", args=(par[0, 0],), rtol=1e-8, atol=1e-11,
                             mass_storage="Full")
     np.testing.assert_allclose(r.y[:, -1], expm_sol(M4, A4, par[0, 0], 1.0, y0[0]), rtol=1e-6, atol=1e-9)
+
+
+# ---- n > 8: the warp-per-trajectory RADAU kernel (mass matrix next to the Jacobian in the warp's global slot) ----------
+M12 = np.array([[(2.0 + 0.25 * i) if i == j else 0.25 / (1.0 + abs(i - j)) * (-1.0 if (i + j) % 2 else 1.0)
+                 for j in range(12)] for i in range(12)])
+A12 = -2.0 * np.eye(12) + np.eye(12, k=1) + np.eye(12, k=-1)
+
+SRC_MASS12 = """
+__device__ void ivp_ode(double t, const double* y, const double* p, double* d) {
+  for (int i = 0; i < 12; ++i) {
+    const double lo = i > 0 ? y[i - 1] : 0.0, hi = i < 11 ? y[i + 1] : 0.0;
+    d[i] = p[0] * (lo - 2.0 * y[i] + hi);
+  }
+}
+__device__ void ivp_mass(const double* p, double* M) {
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 12; ++j)
+      M[i * 12 + j] = (i == j) ? 2.0 + 0.25 * (double)i : 0.25 / (1.0 + (double)(i > j ? i - j : j - i)) * ((i + j) % 2 ? -1.0 : 1.0);
+}
+"""
+
+
+def test_oracle_mass_linear12_matches_matrix_exponential(oracle):
+    y0, par = mass_ensemble(4, 12)
+    o = oracle.solve_batch(109, 0.0, 1.0, y0, par, Options(method=Method.RADAU, rtol=1e-9, atol=1e-12, mass_storage="Full"))
+    assert np.all(o.status == Status.Success)
+    for i in range(4):
+        np.testing.assert_allclose(o.y_final[i], expm_sol(M12, A12, par[i, 0], 1.0, y0[i]), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_radau_mass_matrix_warp_cooperative_kernel(oracle):
+    """n = 12 > 8: RADAU runs one trajectory per warp; M y' = f with a full constant mass matrix and the index-2 / index-3
+    error scaling (radau.rs:283,358-386,433-445,525-539,626-634) against the oracle's restatement (problem 109)."""
+    from ivp_b200 import api
+    from ivp_b200.api import IVPB_FLAG_STRICT_FP
+    y0, par = mass_ensemble(300, 12)
+    user = api.Problem.from_cuda_source(SRC_MASS12, n=12, p=1, has_mass=True)
+    te = np.linspace(0.0, 1.0, 5)
+    for extra in ({}, dict(nind2=2), dict(nind1=8, nind2=2, nind3=2)):
+        opts = Options(method=Method.RADAU, rtol=1e-8, atol=1e-11, mass_storage="Full", t_eval=te, flags=IVPB_FLAG_STRICT_FP, **extra)
+        g = ib.solve_ivp_batch(user, 0.0, 1.0, y0, par, opts)
+        o = oracle.solve_batch(109, 0.0, 1.0, y0, par, opts, nthreads=8)
+        assert np.all(g.status == Status.Success) and np.array_equal(g.status, o.status)
+        assert (g.counters == o.counters).all(axis=1).mean() >= 0.99          # separate compilations of the RHS
+        np.testing.assert_allclose(g.y_out, o.y_out, rtol=1e-6, atol=1e-9)
+        if not extra:
+            for i in (0, 299):
+                np.testing.assert_allclose(g.y_final[i], expm_sol(M12, A12, par[i, 0], 1.0, y0[i]), rtol=1e-6, atol=1e-9)
+    with pytest.raises(ib.ConfigError, match="mass_storage = Full"):
+        ib.solve_ivp_batch(user, 0.0, 1.0, y0, par, Options(method=Method.RADAU))
