@@ -1130,8 +1130,8 @@ def test_analytic_jacobian_warp_cooperative_implicit(oracle, method):
     n = 10
     rng = np.random.default_rng(11)
     A = -np.diag(rng.uniform(0.5, 50.0, n)) + 0.3 * rng.standard_normal((n, n))
-    rows = "\n".join(f"  d[{i}] = " + " + ".join(f"({A[i, j]!r}) * y[{j}]" for j in range(n)) + ";" for i in range(n))
-    jac = "\n".join(f"  J[{i * n + j}] = {A[i, j]!r};" for i in range(n) for j in range(n))
+    rows = "\n".join(f"  d[{i}] = " + " + ".join(f"({float(A[i, j])!r}) * y[{j}]" for j in range(n)) + ";" for i in range(n))
+    jac = "\n".join(f"  J[{i * n + j}] = {float(A[i, j])!r};" for i in range(n) for j in range(n))
     src = ("__device__ void ivp_ode(double t, const double* y, const double* p, double* d) {\n" + rows + "\n}\n"
            "__device__ void ivp_jac(double t, const double* y, const double* p, double* J) {\n" + jac + "\n}\n")
     user = api.Problem.from_cuda_source(src, n=n, has_jac=True)
