@@ -123,6 +123,9 @@ struct Options {
   int max_events = 8;        // event hits stored per event function and trajectory
   int max_out = 4096;        // step-mode samples stored per trajectory when t_eval is None (0: endpoints only)
   bool analytic_jac = false; // use the problem's ivp_jac instead of the default finite differences
+  // `jac_sparsity` of the reference's Python front end (src/python/sparsity.rs): structural non-zeros as (row, col) pairs;
+  // RADAU / BDF then take one RHS evaluation per group of structurally orthogonal columns instead of one per column.
+  std::optional<std::vector<std::pair<int, int>>> jac_sparsity;
   bool strict_fp = false;    // IVPB_FLAG_STRICT_FP: the reference's rounding, operation for operation (explicit methods;
                              // RADAU / BDF use it by default)
   bool fast_fp = false;      // IVPB_FLAG_FAST_FP: FMA-contracted RADAU / BDF kernels
@@ -150,6 +153,7 @@ class OptionsBuilder {
   OptionsBuilder& max_events(int n) { o_.max_events = n; return *this; }
   OptionsBuilder& max_out(int n) { o_.max_out = n; return *this; }
   OptionsBuilder& analytic_jac(bool b) { o_.analytic_jac = b; return *this; }
+  OptionsBuilder& jac_sparsity(std::vector<std::pair<int, int>> nz) { o_.jac_sparsity = std::move(nz); return *this; }
   OptionsBuilder& strict_fp(bool b) { o_.strict_fp = b; return *this; }
   OptionsBuilder& fast_fp(bool b) { o_.fast_fp = b; return *this; }
   Options build() { return std::move(o_); }
@@ -342,6 +346,23 @@ inline std::vector<Solution> solve_ivp_batch(const Problem& f, Float t0, Float t
   o.max_events = ne > 0 ? options.max_events : 0;
   o.max_out = options.max_out;
   o.jac_mode = options.analytic_jac ? 1 : 0;
+  std::vector<int32_t> sp_colptr, sp_rows;
+  if (options.jac_sparsity) {        // (row, col) pairs -> compressed columns, rows ascending, duplicates dropped
+    std::vector<std::vector<int32_t>> cols((size_t)n);
+    for (auto& rc : *options.jac_sparsity) {
+      if (rc.first < 0 || rc.first >= n || rc.second < 0 || rc.second >= n) throw ConfigError("jac_sparsity entry out of range");
+      cols[(size_t)rc.second].push_back(rc.first);
+    }
+    sp_colptr.push_back(0);
+    for (auto& c : cols) {
+      std::sort(c.begin(), c.end());
+      c.erase(std::unique(c.begin(), c.end()), c.end());
+      sp_rows.insert(sp_rows.end(), c.begin(), c.end());
+      sp_colptr.push_back((int32_t)sp_rows.size());
+    }
+    if (sp_rows.empty()) sp_rows.push_back(0);
+    o.has_jac_sparsity = 1; o.jac_sparsity_colptr = sp_colptr.data(); o.jac_sparsity_rows = sp_rows.data();
+  }
   o.flags = (options.strict_fp ? IVPB_FLAG_STRICT_FP : 0u) | (options.fast_fp ? IVPB_FLAG_FAST_FP : 0u);
 
   const size_t cap = o.has_t_eval ? (size_t)o.n_t_eval + 1 : (size_t)o.max_out;

@@ -98,6 +98,14 @@ typedef struct {
                                   go to t_out / y_out (capacity max_out).  All six methods; n <= 32 (RADAU / BDF: n <= 8). */
   int32_t nind1, nind2, nind3; /* Options.nind1..3: index-1/2/3 variable counts of a DAE, < 0 => None
                                   (partition rules and Error::Config of src/methods/radau.rs:210-245) */
+  /* RADAU / BDF with jac_mode = 0: `jac_sparsity` of the reference's Python front end (src/python/solve.rs, SparsityStructure
+   * src/python/sparsity.rs:13-102).  The structural non-zeros of the Jacobian in compressed-column form; the runtime groups
+   * structurally orthogonal columns with the reference's greedy first-fit rule (sparsity.rs:109-154) and the kernels take one
+   * RHS evaluation per GROUP instead of one per column (sparse_jacobian_fd, sparsity.rs:160-202); entries outside the
+   * pattern stay 0.  has_jac_sparsity = 0 => dense forward differences. */
+  int32_t has_jac_sparsity;
+  const int32_t* jac_sparsity_colptr;   /* [n + 1]  column starts (colptr[n] = number of structural non-zeros) */
+  const int32_t* jac_sparsity_rows;     /* [colptr[n]]  row indices, ascending within a column */
 } ivpb_options;
 
 #define IVPB_FLAG_STRICT_FP 1u /* run the kernel variant compiled with -fmad=false (operation-for-operation

@@ -48,6 +48,9 @@ class IvpbOptions(C.Structure):
         ("nind1", C.c_int32),
         ("nind2", C.c_int32),
         ("nind3", C.c_int32),
+        ("has_jac_sparsity", C.c_int32),
+        ("jac_sparsity_colptr", c_int32_p),
+        ("jac_sparsity_rows", c_int32_p),
     ]
 
 
@@ -125,6 +128,23 @@ def alloc_outputs(N, n, n_events, cap, max_events, want=None, seg_cap=0, n_cont=
     return arrays, st
 
 
+def sparsity_to_csc(sp, n: int):
+    """`jac_sparsity` as the reference's Python front end accepts it (a dense array-like of shape (n, n) whose non-zeros
+    mark the structure, or a scipy sparse matrix; src/python/sparsity.rs:29-84) -> (colptr[n + 1], rows[nnz]) int32."""
+    if hasattr(sp, "toarray"):
+        sp = sp.toarray()
+    a = np.asarray(sp)
+    if a.ndim != 2 or a.shape != (n, n):
+        raise ValueError(f"jac_sparsity must have shape ({n}, {n}), got {a.shape}")
+    nz = a != 0
+    colptr = np.zeros(n + 1, dtype=np.int32)
+    colptr[1:] = np.cumsum(nz.sum(axis=0))
+    rows = np.ascontiguousarray(np.nonzero(nz.T)[1].astype(np.int32))      # column by column, rows ascending
+    if rows.size == 0:
+        rows = np.zeros(1, dtype=np.int32)
+    return colptr, rows
+
+
 class MarshalledOptions:
     """Owns the numpy buffers an IvpbOptions struct points into."""
 
@@ -176,6 +196,13 @@ class MarshalledOptions:
         for fld in ("nind1", "nind2", "nind3"):
             v = getattr(opts, fld, None)
             setattr(o, fld, -1 if v is None else int(v))
+        # jac_sparsity (src/python/sparsity.rs:13-102): dense 0/1 array or anything with .toarray() -> compressed columns
+        self.sp_colptr = self.sp_rows = None
+        sp = getattr(opts, "jac_sparsity", None)
+        if sp is not None:
+            self.sp_colptr, self.sp_rows = sparsity_to_csc(sp, n)
+            o.has_jac_sparsity = 1
+            o.jac_sparsity_colptr, o.jac_sparsity_rows = ptr(self.sp_colptr), ptr(self.sp_rows)
 
     @property
     def seg_cap(self) -> int:

@@ -35,7 +35,14 @@ struct KArgs {
   double rtol[MAX_N], atol[MAX_N];   // scalar tolerances are broadcast by the host
   const double* rtol_ext;            // n > MAX_N with Tolerance::Vector: device arrays [n] (else null: rtol[0])
   const double* atol_ext;
-  double* scratch;       // implicit warp kernels: one Jacobian slot (n x (n|1) doubles) per warp of the grid
+  double* scratch;       // implicit warp kernels: one slot per warp of the grid -- the Jacobian (n x (n|1) doubles), RADAU's
+                         // mass matrix, and for large n the iteration matrices as well (warp_impl_shape below)
+  // jac_sparsity (src/python/sparsity.rs): compressed columns of the Jacobian's structure and the column groups the
+  // runtime built from them; sp_colptr == null => dense forward differences
+  const int* sp_colptr;  // [n + 1]
+  const int* sp_rows;    // [sp_colptr[n]]
+  const int* sp_group;   // [n] group of each column
+  int sp_ngroups;
   double first_step, max_step, min_step;
   int has_first_step, has_max_step, has_min_step, static_sched;
   u64 max_steps;         // usize::MAX when Options.max_steps is None
@@ -78,6 +85,29 @@ struct KArgs {
   double* seg_x;
   double* seg_cont;
 };
+
+// Shape of the warp-cooperative RADAU / BDF kernels (ivpb_implicit_warp.cuh), shared by the device templates and the two
+// launchers (ivpb_runtime.cu, ivpb_nvrtc.cpp).  Per warp, shared memory holds the layout's 2n doubles, the staged vectors
+// (RADAU: b1..b3 + pivots = 4n; BDF: b1, D (8 rows), scratch (6 rows), pivots = 16n) and -- when they fit 227 KB -- the
+// iteration matrices (RADAU: E1, E2re, E2im; BDF: the LU of I - cJ).  The Jacobian (and RADAU's mass matrix) always sit in
+// the warp's slot of KArgs::scratch.  When the matrices do not fit (RADAU n > 84, BDF n > 118: the reference's own
+// MEDAKZO test has n = 400) they move to the same slot in global memory (`gmats`), where they are L2-resident.
+struct WarpImplShape {
+  long long smem_doubles;      // per warp
+  int warps;                   // per block
+  long long scratch_doubles;   // per warp, in KArgs::scratch
+  bool gmats;
+};
+__host__ __device__ constexpr WarpImplShape warp_impl_shape(int n, int method, bool mass) {
+  const long long matd = (long long)(n | 1) * n;
+  const long long vecs = (method == M_RADAU ? 6LL : 18LL) * n;
+  const long long mats = method == M_RADAU ? 3 : 1;
+  const bool g = (vecs + mats * matd) * 8 > 227 * 1024;
+  const long long smem = vecs + (g ? 0 : mats * matd);
+  const int warps = g ? 1 : (smem * 8 * 4 <= 200 * 1024 ? 4 : (smem * 8 * 2 <= 200 * 1024 ? 2 : 1));
+  const long long scratch = (1 + ((method == M_RADAU && mass) ? 1 : 0) + (g ? mats : 0)) * matd;
+  return WarpImplShape{smem, warps, scratch, g};
+}
 
 // std::conditional without <type_traits> (NVRTC has no standard headers)
 template <bool B, class T, class F> struct std_conditional { typedef T type; };

@@ -233,7 +233,46 @@ struct WarpImplBase {
     if constexpr (Prob::HAS_JAC) {
       if (a.jac_mode == 1) { eval_jac_user(x, y, p, J); return; }
     }
+    if (a.sp_colptr) { eval_jac_fd_sparse(a, x, y, p, J); return; }
     eval_jac_fd(x, y, p, J);
+  }
+  // jac_sparsity: forward differences with one RHS evaluation per GROUP of structurally orthogonal columns
+  // (sparse_jacobian_fd, src/python/sparsity.rs:160-202).  Every column of the group is perturbed at once; a column then
+  // reads its own rows of f(y + sum of perturbations) - f(y).  Only the structural non-zeros are written: the rest of the
+  // slot was zeroed when the trajectory started (zero_jac), like the reference's zero-initialised `dfdy`.
+  static __device__ void eval_jac_fd_sparse(const KArgs& a, double x, const double (&y)[NL], const double* p, const WMat<N>& J) {
+    double* row = L::row();
+    double* diff = row + N;                 // the layout's reduction scratch: f(perturbed) - f(y), by row
+    double fo[NL], fp[NL];
+    L::ode(x, y, p, fo);                    // publishes y in `row` as a side effect
+    const double eps = 1.4901161193847656e-08;
+    for (int g = 0; g < a.sp_ngroups; ++g) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i)
+        if (L::valid(i) && a.sp_group[L::gi(i)] == g) row[L::gi(i)] = y[i] + eps * fmax(fabs(y[i]), 1.0);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NL; ++i) fp[i] = L::valid(i) ? L::ode_comp(x, row, p, L::gi(i)) : 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NL; ++i) if (L::valid(i)) diff[L::gi(i)] = fp[i] - fo[i];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        if (L::valid(i) && a.sp_group[L::gi(i)] == g) {
+          const int col = L::gi(i);
+          const double pert = eps * fmax(fabs(y[i]), 1.0);
+          for (int k = a.sp_colptr[col]; k < a.sp_colptr[col + 1]; ++k) { const int r = a.sp_rows[k]; J(r, col) = diff[r] / pert; }
+          row[col] = y[i];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  static __device__ void zero_jac(const KArgs& a, const WMat<N>& J) {
+    if (!a.sp_colptr) return;
+    for (int k = L::lane(); k < WMat<N>::DOUBLES; k += 32) J.b[k] = 0.0;
+    __syncwarp();
   }
   // The problem's `jac` fills a dense row-major n x n matrix, as the reference's `dfdy: &mut Matrix`.  One lane runs it,
   // writing straight into the warp's Jacobian slot (>= n^2 doubles); the warp then re-strides the rows in place to the odd
@@ -316,10 +355,15 @@ template <class Prob, int FEAT>
 struct RadauWarpTraj {
   static constexpr int NN = Prob::N;
   static constexpr int MATD = WMat<NN>::DOUBLES;
-  // per warp behind the layout's 2n: staged vectors b1, b2, b3 (3n), four matrices, two pivot arrays (n doubles)
+  static constexpr bool MASS = Prob::HAS_MASS;
+  static constexpr WarpImplShape SH = warp_impl_shape(NN, M_RADAU, MASS);
+  static constexpr bool GM = SH.gmats;      // iteration matrices in the global-memory slot (they do not fit shared memory)
+  // per warp behind the layout's 2n: staged vectors b1, b2, b3 (3n), three iteration matrices, two pivot arrays (n doubles)
   // (the Jacobian itself lives in a per-warp global-memory slot, KArgs::scratch: it is touched O(n^2) times per
   // trip against the O(n^3) of the factorisations, and leaving it out of shared memory doubles the resident warps)
-  static constexpr int EXTRA = 3 * NN + 3 * MATD + NN;
+  static constexpr int SMATS = GM ? 0 : 3 * MATD;
+  static constexpr int EXTRA = 3 * NN + SMATS + NN;
+  static_assert(2 * NN + EXTRA == SH.smem_doubles, "RadauWarpTraj layout != warp_impl_shape");
   using B = WarpImplBase<Prob, EXTRA>;
   using L = typename B::L;
   using LA = WarpLinAlg<NN>;
@@ -327,8 +371,7 @@ struct RadauWarpTraj {
   using Out = SolOutDev<Prob, M_RADAU, FEAT, L>;
   // M y' = f (Options.mass_storage = Full, radau.rs:283,358-386,525-539,626-634): the mass matrix sits next to the
   // Jacobian in the warp's global-memory slot (KArgs::scratch holds SLOT doubles per warp)
-  static constexpr bool MASS = Prob::HAS_MASS;
-  static constexpr int SLOT = MASS ? 2 * MATD : MATD;
+  static constexpr i64 SLOT = SH.scratch_doubles;
   double hhfac;
 
   i64 idx;
@@ -344,8 +387,13 @@ struct RadauWarpTraj {
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double* b2() const { return B::extra() + NN; }
   __device__ __forceinline__ double* b3() const { return B::extra() + 2 * NN; }
-  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + 3 * NN + (k - 1) * MATD; return m; }   // k = 1..3
-  __device__ __forceinline__ int* ip1() const { return (int*)(B::extra() + 3 * NN + 3 * MATD); }
+  __device__ __forceinline__ WMat<NN> mat(const KArgs& a, int k) const {      // k = 1..3: E1, E2re, E2im
+    WMat<NN> m;
+    if constexpr (GM) m.b = jacm(a).b + (i64)((MASS ? 2 : 1) + (k - 1)) * MATD;
+    else m.b = B::extra() + 3 * NN + (k - 1) * MATD;
+    return m;
+  }
+  __device__ __forceinline__ int* ip1() const { return (int*)(B::extra() + 3 * NN + SMATS); }
   __device__ __forceinline__ int* ip2() const { return ip1() + NN; }
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
@@ -369,6 +417,7 @@ struct RadauWarpTraj {
     h = fmin(fmax(h, -hmax), hmax);
     hhfac = h;
     if constexpr (MASS) B::eval_mass(p, massm(a));
+    B::zero_jac(a, jacm(a));
     nfev = 0; njev = 0; nlu = 0; nstep = 0; naccpt = 0; nrejct = 0;
     singular_count = 0; status = ST_SUCCESS;
     hold = h; h_acc = 0.0; err_acc = 0.0; faccon = 1.0; theta = 0.001; dynold = 0.0; thqold = 0.0;
@@ -389,7 +438,7 @@ struct RadauWarpTraj {
     return false;
   }
   __device__ __forceinline__ WMat<NN> jacm(const KArgs& a) const {
-    WMat<NN> m; m.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (i64)SLOT; return m;
+    WMat<NN> m; m.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SLOT; return m;
   }
   __device__ __forceinline__ WMat<NN> massm(const KArgs& a) const { WMat<NN> m = jacm(a); m.b += MATD; return m; }
 
@@ -427,9 +476,9 @@ struct RadauWarpTraj {
   }
 
   // real solve of one distributed vector through the staging row b1
-  __device__ __forceinline__ void solve_real(double (&v)[N]) {
+  __device__ __forceinline__ void solve_real(const KArgs& a, double (&v)[N]) {
     B::put(b1(), v);
-    LA::lin_solve(mat(1), b1(), ip1());
+    LA::lin_solve(mat(a, 1), b1(), ip1());
     B::get(b1(), v);
   }
 
@@ -444,7 +493,7 @@ struct RadauWarpTraj {
     const double hmin = a.has_min_step ? a.min_step : 0.0;
     const double newton_tol = a.newton_tol;
     const WMat<NN> jac = jacm(a), mm = massm(a);
-    const WMat<NN> e1 = mat(1), e2r = mat(2), e2i = mat(3);
+    const WMat<NN> e1 = mat(a, 1), e2r = mat(a, 2), e2i = mat(a, 3);
 
     if (call_jac) { B::eval_jac(a, x, y, p, jac); njev += 1; }
     if (call_decomp) {
@@ -590,7 +639,7 @@ struct RadauWarpTraj {
       if constexpr (!MASS) f2[i] = 0.0 + f1[i];
       w[i] = f2[i] + f0[i];
     }
-    solve_real(w);
+    solve_real(a, w);
     nlu += 1;
     double q[N];
 #pragma unroll
@@ -603,7 +652,7 @@ struct RadauWarpTraj {
       nfev += 1;
 #pragma unroll
       for (int i = 0; i < N; ++i) w[i] = f1[i] + f2[i];
-      solve_real(w);
+      solve_real(a, w);
 #pragma unroll
       for (int i = 0; i < N; ++i) q[i] = L::valid(i) ? w[i] / scal[i] : 0.0;
       err = fmax(sqrt(L::sumsq(q) / (double)NN), 1e-10);
@@ -677,8 +726,13 @@ struct BdfWarpTraj {
   static constexpr int NN = Prob::N;
   static constexpr int MATD = WMat<NN>::DOUBLES;
   static constexpr int ND = bdf_c::MAX_ORDER + 3, NS = bdf_c::MAX_ORDER + 1;
-  // per warp behind the layout's 2n: staging row b1 (n), D (8n), scratch (6n), two matrices, pivots (n/2 -> n)
-  static constexpr int EXTRA = NN + (ND + NS) * NN + 1 * MATD + NN;     // Jacobian in KArgs::scratch, see RadauWarpTraj
+  static constexpr WarpImplShape SH = warp_impl_shape(NN, M_BDF, false);
+  static constexpr bool GM = SH.gmats;      // the LU matrix in the global-memory slot, behind the Jacobian
+  static constexpr i64 SLOT = SH.scratch_doubles;
+  static constexpr int SMATS = GM ? 0 : MATD;
+  // per warp behind the layout's 2n: staging row b1 (n), D (8n), scratch (6n), the LU matrix, pivots (n/2 -> n)
+  static constexpr int EXTRA = NN + (ND + NS) * NN + SMATS + NN;     // Jacobian in KArgs::scratch, see RadauWarpTraj
+  static_assert(2 * NN + EXTRA == SH.smem_doubles, "BdfWarpTraj layout != warp_impl_shape");
   using B = WarpImplBase<Prob, EXTRA>;
   using L = typename B::L;
   using LA = WarpLinAlg<NN>;
@@ -698,8 +752,16 @@ struct BdfWarpTraj {
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double& D(int k, int i) const { return B::extra()[NN + k * NN + L::gi(i)]; }          // local slot i
   __device__ __forceinline__ double& S(int k, int i) const { return B::extra()[NN + (ND + k) * NN + L::gi(i)]; }
-  __device__ __forceinline__ WMat<NN> mat(int k) const { WMat<NN> m; m.b = B::extra() + NN + (ND + NS) * NN + (k - 1) * MATD; return m; }   // k = 1
-  __device__ __forceinline__ int* pivot() const { return (int*)(B::extra() + NN + (ND + NS) * NN + 1 * MATD); }
+  __device__ __forceinline__ WMat<NN> jacm(const KArgs& a) const {
+    WMat<NN> m; m.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SLOT; return m;
+  }
+  __device__ __forceinline__ WMat<NN> mat(const KArgs& a, int k) const {      // k = 1: the LU of I - cJ
+    WMat<NN> m;
+    if constexpr (GM) m.b = jacm(a).b + (i64)k * MATD;
+    else m.b = B::extra() + NN + (ND + NS) * NN + (k - 1) * MATD;
+    return m;
+  }
+  __device__ __forceinline__ int* pivot() const { return (int*)(B::extra() + NN + (ND + NS) * NN + SMATS); }
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
     x = tev;
@@ -762,6 +824,7 @@ struct BdfWarpTraj {
     }
     nfev = 0; njev = 0; nlu = 0; nstep = 0; naccpt = 0; nrejct = 0;
     status = ST_SUCCESS; order = 1; n_equal_steps = 0; lu_is_current = false; current_c = 0.0; pend = 1.0;
+    B::zero_jac(a, jacm(a));
     so.reset();
     const double direction = signum(a.tf - a.t0);
     const double hmax = fabs(a.has_max_step ? a.max_step : fabs(a.tf - a.t0));
@@ -834,8 +897,8 @@ struct BdfWarpTraj {
     const double hmin = fabs(a.has_min_step ? a.min_step : 0.0);
     const int newton_maxiter = 4;
     const double newton_tol = a.newton_tol;
-    WMat<NN> jac; jac.b = a.scratch + (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (i64)MATD;
-    const WMat<NN> lu = mat(1);
+    const WMat<NN> jac = jacm(a);
+    const WMat<NN> lu = mat(a, 1);
 
     if (jac_pending) { B::eval_jac(a, jx, jy, p, jac); jac_pending = false; }
     if ((u64)nstep >= a.max_steps) { status = ST_NMAX; return true; }
@@ -1028,12 +1091,12 @@ struct ImplicitWarpSel {
   using Traj = typename std_conditional<METHOD == M_RADAU, RadauWarpTraj<Prob, FEAT>, BdfWarpTraj<Prob, FEAT>>::type;
   static constexpr int DOUBLES_PER_WARP = 2 * Prob::N + Traj::EXTRA;
   static constexpr int BYTES_PER_WARP = DOUBLES_PER_WARP * 8;
-  // as many warps per block as fit ~200 KB, at most 4
-  static constexpr int WARPS = BYTES_PER_WARP * 4 <= 200 * 1024 ? 4 : (BYTES_PER_WARP * 2 <= 200 * 1024 ? 2 : 1);
+  // as many warps per block as fit ~200 KB, at most 4; one when the matrices live in global memory (warp_impl_shape)
+  static constexpr int WARPS = Traj::SH.warps;
   static constexpr int BLK = 32 * WARPS;
   static constexpr int SMEM_BYTES = BYTES_PER_WARP * WARPS;
   static constexpr bool FITS = BYTES_PER_WARP <= 227 * 1024;
-  static constexpr int SCRATCH_DOUBLES_PER_WARP = WMat<Prob::N>::DOUBLES;     // the Jacobian slot in KArgs::scratch
+  static constexpr long long SCRATCH_DOUBLES_PER_WARP = Traj::SH.scratch_doubles;     // the warp's slot in KArgs::scratch
 };
 
 template <class Prob, int METHOD, int FEAT>

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "ivpb_runtime.h"
+#include "ivpb_common.cuh"
 #include "embedded_headers.inc"
 
 namespace {
@@ -183,7 +185,8 @@ extern "C" long long ivpb_debug_nvrtc_compile(const char* src, int n, int p, int
 }
 
 int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms, int method, int feat, int strict,
-                      const void* kargs, size_t kargs_bytes, long long N, int static_sched, cudaStream_t stream) {
+                      const void* kargs, size_t kargs_bytes, long long N, int static_sched, long long max_warps,
+                      cudaStream_t stream) {
   Api& A = api();
   if (!A.ok) { ivpb_set_error(ctx, "NVRTC path unavailable: " + A.err); return IVPB_ERR_NVRTC; }
   if (!up.impl) up.impl = new Cache();
@@ -207,11 +210,10 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   long long units_per_block = 0;
   if (method >= 4 && up.n > 8) {
     // one trajectory per warp; must match ivpb::ImplicitWarpSel (ivpb_implicit_warp.cuh)
-    const size_t n = (size_t)up.n, matd = (n | 1) * n;
-    const size_t extra = method == 4 ? 3 * n + 3 * matd + n : n + 14 * n + 1 * matd + n;    // Jacobian: KArgs::scratch
-    const size_t bytes = (2 * n + extra) * 8;
-    if (bytes > 227 * 1024) { ivpb_set_error(ctx, "implicit methods: the per-warp matrices of this state size do not fit shared memory"); return IVPB_ERR_CONFIG; }
-    const int warps = bytes * 4 <= 200 * 1024 ? 4 : (bytes * 2 <= 200 * 1024 ? 2 : 1);
+    const ivpb::WarpImplShape sh = ivpb::warp_impl_shape(up.n, method, (up.has_jac & 2) != 0);
+    const size_t bytes = (size_t)sh.smem_doubles * 8;
+    if (bytes > 227 * 1024) { ivpb_set_error(ctx, "implicit methods: the per-warp vectors of this state size do not fit shared memory"); return IVPB_ERR_CONFIG; }
+    const int warps = sh.warps;
     block = 32 * warps; smem = bytes * warps; units_per_block = warps;
     CUresult ar = A.FuncSetAttribute(it->second.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
     if (ar != CUDA_SUCCESS) { ivpb_set_error(ctx, "cuFuncSetAttribute: " + drv_err(ar)); return IVPB_ERR_CUDA; }
@@ -245,6 +247,7 @@ int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms,
   long long grid = (long long)sms * occ;
   const long long need = (N + units_per_block - 1) / units_per_block;
   if (static_sched || need < grid) grid = need;
+  if (max_warps > 0 && method >= 4 && up.n > 8) grid = std::max<long long>(1, std::min<long long>(grid, max_warps / units_per_block));
   std::vector<char> copy((const char*)kargs, (const char*)kargs + kargs_bytes);
   void* params[] = {copy.data()};
   CUresult cr = A.LaunchKernel(it->second.fn, (unsigned)grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)stream, params, nullptr);

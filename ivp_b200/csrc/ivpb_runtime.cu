@@ -83,6 +83,7 @@ struct Device {
   int id = 0;
   int sms = 0;
   cudaStream_t stream = nullptr;
+  int sp_ngroups = 0;               // column groups of the staged jac_sparsity (stage_shared)
   cudaStream_t stream2 = nullptr;   // second lane of the chunked host-buffer pipeline (ivpb_solve_batch)
   cudaEvent_t ev_shared = nullptr;  // "t_eval / tolerance staging uploaded" (recorded on stream, awaited by stream2)
   u64* queue = nullptr;             // work-queue head(s) of the launches in flight on this device
@@ -95,7 +96,7 @@ struct Device {
   cudaEvent_t ev_last = nullptr;    // end of the most recent solve enqueued on this device: the per-device queue counter,
                                     // t_eval / tolerance staging and sort buffers are shared, so solves on one context are
                                     // serialised on the device even when the caller hands in different streams
-  Buf y0, params, t_eval, tol_ext, scratch, out[OUT_FIELDS];
+  Buf y0, params, t_eval, tol_ext, sparsity, scratch, out[OUT_FIELDS];
   Buf sort_keys, sort_vals, sort_tmp, sort_minmax;   // locality order of the shard (locality_order)
   Buf q_traj, q_ts, q_y, q_ok;      // ivpb_dense_eval query staging (grow-only)
   Buf dense_nseg, dense_segx, dense_segc;   // the retained dense log of this device's shard (never shared with dev.out[])
@@ -238,6 +239,15 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
     for (int i = 0; i < (o->n_atol == 1 ? 1 : pi.n); ++i)
       if (o->atol[i] < 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: negative absolute tolerance");
     if (o->has_first_step && o->first_step == 0.0) return fail(ctx, IVPB_ERR_CONFIG, "BDF: first_step is zero");
+  }
+  if (o->has_jac_sparsity) {       // SparsityStructure (src/python/sparsity.rs:13-84): compressed columns, rows in range
+    if (!o->jac_sparsity_colptr || !o->jac_sparsity_rows) return fail(ctx, IVPB_ERR_CONFIG, "has_jac_sparsity = 1 but the colptr / rows arrays are null");
+    if (o->jac_sparsity_colptr[0] != 0) return fail(ctx, IVPB_ERR_CONFIG, "jac_sparsity_colptr[0] must be 0");
+    for (int c = 0; c < pi.n; ++c) {
+      if (o->jac_sparsity_colptr[c + 1] < o->jac_sparsity_colptr[c]) return fail(ctx, IVPB_ERR_CONFIG, "jac_sparsity_colptr must be non-decreasing");
+      for (int k = o->jac_sparsity_colptr[c]; k < o->jac_sparsity_colptr[c + 1]; ++k)
+        if (o->jac_sparsity_rows[k] < 0 || o->jac_sparsity_rows[k] >= pi.n) return fail(ctx, IVPB_ERR_CONFIG, "jac_sparsity row index out of range");
+    }
   }
   if (o->jac_mode == 1 && !(pi.has_jac & 1) && (o->method == IVPB_RADAU || o->method == IVPB_BDF))
     return fail(ctx, IVPB_ERR_CONFIG, "jac_mode=1 but the problem has no analytic Jacobian");
@@ -488,6 +498,34 @@ static bool wants_tol_ext(const ProblemInfo& pi, const ivpb_options* o) {
   const bool implicit_m = o->method == IVPB_RADAU || o->method == IVPB_BDF;
   return (pi.n > ivpb::MAX_N || (implicit_m && pi.n > 8)) && (o->n_rtol > 1 || o->n_atol > 1);
 }
+// Column groups of a Jacobian structure: the reference's greedy first-fit rule (group_columns, src/python/sparsity.rs:109-154)
+// -- columns in index order, each into the first group none of whose columns shares a structural non-zero row with it.
+// One bitset of "rows taken" per group.
+static int group_columns(int n, const int32_t* colptr, const int32_t* rows, std::vector<int32_t>& group) {
+  const size_t words = ((size_t)n + 63) / 64;
+  std::vector<std::vector<uint64_t>> taken;
+  group.assign((size_t)n, 0);
+  for (int c = 0; c < n; ++c) {
+    size_t g = 0;
+    for (; g < taken.size(); ++g) {
+      bool clash = false;
+      for (int k = colptr[c]; k < colptr[c + 1] && !clash; ++k) clash = (taken[g][(size_t)rows[k] >> 6] >> (rows[k] & 63)) & 1u;
+      if (!clash) break;
+    }
+    if (g == taken.size()) taken.emplace_back(words, 0ull);
+    for (int k = colptr[c]; k < colptr[c + 1]; ++k) taken[g][(size_t)rows[k] >> 6] |= 1ull << (rows[k] & 63);
+    group[(size_t)c] = (int32_t)g;
+  }
+  return (int)taken.size();
+}
+// jac_sparsity is used by the warp-cooperative RADAU / BDF kernels (n > 8) with finite differences.  The thread-per-
+// trajectory kernels (n <= 8) keep dense differences: for a structure that covers the true dependencies both give the same
+// bits (a column's rows do not depend on the other columns of its group; entries outside the structure are (f - f) / h = 0),
+// and at n <= 8 there is nothing to save.
+static bool wants_sparsity(const ProblemInfo& pi, const ivpb_options* o) {
+  return o->has_jac_sparsity && (o->method == IVPB_RADAU || o->method == IVPB_BDF) && pi.n > 8 &&
+         !(o->jac_mode == 1 && (pi.has_jac & 1));
+}
 // Upload the small per-call arrays every launch of the call reads (t_eval, per-component tolerances) on `stream`.
 static int stage_shared(ivpb_ctx* ctx, Device& dev, const ProblemInfo& pi, const ivpb_options* o, cudaStream_t stream) {
   if (o->has_t_eval && o->n_t_eval > 0) {
@@ -509,7 +547,25 @@ static int stage_shared(ivpb_ctx* ctx, Device& dev, const ProblemInfo& pi, const
     CK(cudaMemcpyAsync(dev.tol_ext.p, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));      // `tol` is a stack-lifetime staging buffer
   }
+  if (wants_sparsity(pi, o)) {      // [colptr (n + 1) | group (n) | rows (nnz)] as int32
+    const int n = pi.n, nnz = o->jac_sparsity_colptr[n];
+    std::vector<int32_t> buf((size_t)2 * n + 1 + (size_t)std::max(nnz, 1)), group;
+    dev.sp_ngroups = group_columns(n, o->jac_sparsity_colptr, o->jac_sparsity_rows, group);
+    std::memcpy(buf.data(), o->jac_sparsity_colptr, sizeof(int32_t) * ((size_t)n + 1));
+    std::memcpy(buf.data() + n + 1, group.data(), sizeof(int32_t) * (size_t)n);
+    if (nnz > 0) std::memcpy(buf.data() + 2 * n + 1, o->jac_sparsity_rows, sizeof(int32_t) * (size_t)nnz);
+    CK(dev.sparsity.ensure(sizeof(int32_t) * buf.size()));
+    CK(cudaMemcpyAsync(dev.sparsity.p, buf.data(), sizeof(int32_t) * buf.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
   return 0;
+}
+
+// How many warps of a warp-cooperative implicit launch get a slot in KArgs::scratch: every warp the device can hold
+// (64 per SM), no more than there are trajectories, and no more than fit 16 GB (large n: 6.4 MB per warp at n = 400).
+static long long warp_pool_warps(const ivpb::WarpImplShape& sh, int sms, int64_t N) {
+  const long long by_device = (long long)sms * 64, by_bytes = (16ll << 30) / (8 * std::max<long long>(1, sh.scratch_doubles));
+  return std::max<long long>(1, std::min<long long>(std::min<long long>(by_device, by_bytes), std::max<int64_t>(N, 1)));
 }
 
 // `slot`: which of the device's work-queue heads this launch uses.  `upload_shared`: copy t_eval / per-component
@@ -550,6 +606,10 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     if (int rc = stage_shared(ctx, dev, pi, o, stream)) return rc;
   if (o->has_t_eval && o->n_t_eval > 0) a.t_eval = (const double*)dev.t_eval.p;
   if (wants_tol_ext(pi, o)) { a.rtol_ext = (const double*)dev.tol_ext.p; a.atol_ext = a.rtol_ext + pi.n; }
+  if (wants_sparsity(pi, o)) {
+    a.sp_colptr = (const int*)dev.sparsity.p; a.sp_group = a.sp_colptr + pi.n + 1; a.sp_rows = a.sp_group + pi.n;
+    a.sp_ngroups = dev.sp_ngroups;
+  }
   const bool implicit_method = o->method == IVPB_RADAU || o->method == IVPB_BDF;
   const int strict = ctx->fp_override >= 0 ? ctx->fp_override
                                            : ((o->flags & IVPB_FLAG_STRICT_FP) || (implicit_method && !(o->flags & IVPB_FLAG_FAST_FP))) ? 1 : 0;
@@ -592,16 +652,18 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaMemsetAsync(dev.queue + slot, 0, sizeof(u64), stream));
 
   if (pi.user) {
+    long long max_warps = 0;
     if (pi.n > 8 && (o->method == IVPB_RADAU || o->method == IVPB_BDF)) {
       // warp-cooperative implicit kernels keep one Jacobian per resident warp in global memory; the launch shape is
       // chosen inside ivpb_nvrtc_launch, so size the pool for the most warps an SM can hold (64 warps x SMs)
       // (+ the mass matrix next to it for RADAU problems that have one)
-      const size_t matd = (size_t)(pi.n | 1) * pi.n * ((o->method == IVPB_RADAU && (pi.has_jac & 2)) ? 2 : 1);
-      CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)dev.sms * 64));
+      const ivpb::WarpImplShape sh = ivpb::warp_impl_shape(pi.n, o->method, (pi.has_jac & 2) != 0);
+      max_warps = warp_pool_warps(sh, dev.sms, N);
+      CK(dev.scratch.ensure(sizeof(double) * (size_t)sh.scratch_doubles * (size_t)max_warps));
       a.scratch = (double*)dev.scratch.p;
     }
     int rc = ivpb_nvrtc_launch(ctx, ctx->user[pi.uidx], dev.id, dev.sms, o->method, feat, strict, &a, sizeof(a), N,
-                               a.static_sched, stream);
+                               a.static_sched, max_warps, stream);
     if (rc) return rc;
     ctx->launches += 1;
     return 0;
@@ -636,9 +698,11 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   const int64_t units_per_block = kunits > 0 ? kunits : (warp_mode ? kblock / 32 : kblock);
   const int64_t need = (N + units_per_block - 1) / units_per_block;
   if (a.static_sched || need < grid) grid = need;
-  if (impl_warp) {       // per-warp Jacobian slots in global memory (L2-resident: grid x warps x n (n|1) doubles)
-    const size_t matd = (size_t)(pi.n | 1) * pi.n * ((o->method == IVPB_RADAU && (pi.has_jac & 2)) ? 2 : 1);
-    CK(dev.scratch.ensure(sizeof(double) * matd * (size_t)grid * (size_t)(kblock / 32)));
+  if (impl_warp) {       // per-warp slots in global memory (L2-resident): Jacobian (+ mass, + the iteration matrices for large n)
+    const ivpb::WarpImplShape sh = ivpb::warp_impl_shape(pi.n, o->method, (pi.has_jac & 2) != 0);
+    const int64_t wpb = kblock / 32;
+    grid = std::min<int64_t>(grid, std::max<int64_t>(1, warp_pool_warps(sh, dev.sms, N) / wpb));
+    CK(dev.scratch.ensure(sizeof(double) * (size_t)sh.scratch_doubles * (size_t)grid * (size_t)wpb));
     a.scratch = (double*)dev.scratch.p;
   }
   void* kargs[] = {&a};
@@ -882,7 +946,7 @@ void ivpb_destroy(ivpb_ctx* ctx) {
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.id);
     if (d.stream) cudaStreamSynchronize(d.stream);
-    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.scratch.release();
+    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.sparsity.release(); d.scratch.release();
     d.q_traj.release(); d.q_ts.release(); d.q_y.release(); d.q_ok.release();
     d.sort_keys.release(); d.sort_vals.release(); d.sort_tmp.release(); d.sort_minmax.release();
     d.dense_nseg.release(); d.dense_segx.release(); d.dense_segc.release();
@@ -1346,6 +1410,15 @@ int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+// Debug hook (not part of include/ivpb.h): the runtime's column grouping of a jac_sparsity structure, so the CPU suite can
+// compare it with the reference's greedy rule without a GPU.  Returns the number of groups.
+extern "C" int ivpb_debug_group_columns(int n, const int32_t* colptr, const int32_t* rows, int32_t* groups) {
+  std::vector<int32_t> g;
+  const int ng = group_columns(n, colptr, rows, g);
+  for (int c = 0; c < n; ++c) groups[c] = g[(size_t)c];
+  return ng;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Debug hook (not part of include/ivpb.h): evaluates the fast-mode controller helpers of

@@ -24,6 +24,6 @@ struct ivpb_user_problem {
 };
 
 int ivpb_nvrtc_launch(ivpb_ctx* ctx, ivpb_user_problem& up, int device, int sms, int method, int feat, int strict,
-                      const void* kargs, size_t kargs_bytes, long long N, int static_sched, cudaStream_t stream);
+                      const void* kargs, size_t kargs_bytes, long long N, int static_sched, long long max_warps, cudaStream_t stream);
 void ivpb_nvrtc_release(ivpb_user_problem& up);
 void ivpb_set_error(ivpb_ctx* ctx, const std::string& msg);

@@ -100,7 +100,8 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
         problem = api.Problem.builtin(fun)
     t0, tf = float(t_span[0]), float(t_span[1])
     known = {"rtol", "atol", "max_step", "min_step", "first_step", "max_steps",          # solve.rs:290-340
-             "mass_storage", "nind1", "nind2", "nind3"}                                  # Options of the Rust crate (RADAU)
+             "mass_storage", "nind1", "nind2", "nind3",                                  # Options of the Rust crate (RADAU)
+             "jac_sparsity"}                                                             # solve.rs: sparse finite differences
     unknown = set(options) - known - {"max_events", "max_out", "max_segments", "strict_fp", "fast_fp"}
     if unknown:
         raise TypeError(f"unknown options: {sorted(unknown)}")
@@ -112,7 +113,7 @@ def solve_ivp(fun, t_span, y0, method=None, t_eval=None, dense_output=False, eve
                    dense_output=bool(dense_output), event_config=cfgs, max_events=int(options.get("max_events", 64)),
                    max_out=int(options.get("max_out", 4096)), max_segments=int(options.get("max_segments", 4096)) if dense_output else 0,
                    mass_storage=options.get("mass_storage", "Identity"), nind1=options.get("nind1"),
-                   nind2=options.get("nind2"), nind3=options.get("nind3"),
+                   nind2=options.get("nind2"), nind3=options.get("nind3"), jac_sparsity=options.get("jac_sparsity"),
                    jac_mode=1 if jac in (True, "analytic") or (isinstance(jac, str) and "ivp_jac" in jac) else 0,
                    flags=(api.IVPB_FLAG_STRICT_FP if options.get("strict_fp") else 0) |
                          (api.IVPB_FLAG_FAST_FP if options.get("fast_fp") else 0))

@@ -87,3 +87,43 @@ def ensemble(name: str, N: int, offset: int = 0):
         y0[:, 1::2] = 0.9 + 0.2 * u
         return "medakzo64", y0, None, 0.0, 20.0
     raise KeyError(name)
+
+
+def medakzo_sparsity(n_grid: int) -> np.ndarray:
+    """Structure of the MEDAKZO Jacobian on `n_grid` points (2 n_grid states) as a dense 0/1 array -- the pattern of the
+    reference's tests/test_helpers.py:81-112 (`medazko_sparsity`), for Options.jac_sparsity."""
+    n = 2 * n_grid
+    S = np.zeros((n, n), dtype=np.int8)
+    i = np.arange(n_grid) * 2            # u rows: f[i] reads y[i - 2], y[i], y[i + 1], y[i + 2]
+    S[i[1:], i[1:] - 2] = 1
+    S[i, i] = 1
+    S[i, i + 1] = 1
+    S[i[:-1], i[:-1] + 2] = 1
+    j = i + 1                            # v rows: f[j] reads y[j - 1], y[j]
+    S[j, j] = 1
+    S[j, j - 1] = 1
+    return S
+
+
+def medakzo_cuda_source(n_grid: int) -> str:
+    """MEDAKZO (reference tests/test_helpers.py:54-80, `fun_medazko`) on `n_grid` points as a user problem in CUDA C:
+    the per-component RHS `ivp_ode_i` the warp-per-trajectory kernels (n > 32) ask for.  n = 2 n_grid states."""
+    return f"""
+#define NG {int(n_grid)}
+__device__ __forceinline__ double medakzo_z(double t, const double* y, int m) {{   // hstack((phi, 0, y, y[-2]))
+  if (m == 0) return t <= 5.0 ? 2.0 : 0.0;
+  if (m == 1) return 0.0;
+  if (m == 2 * NG + 2) return y[2 * NG - 2];
+  return y[m - 2];
+}}
+__device__ double ivp_ode_i(double t, const double* y, const double* p, int i) {{
+  const double k = 100.0, c = 4.0, d = 1.0 / (double)NG;
+  const int j = i / 2 + 1;
+  const double u = medakzo_z(t, y, 2 * j), v = medakzo_z(t, y, 2 * j + 1);
+  if (i & 1) return -k * v * u;
+  const double w = (double)j * d - 1.0;
+  const double alpha = 2.0 * ((w * w) * w) / (c * c), beta = ((w * w) * (w * w)) / (c * c);
+  const double zp = medakzo_z(t, y, 2 * j + 2), zm = medakzo_z(t, y, 2 * j - 2);
+  return alpha * (zp - zm) / (2.0 * d) + beta * (zm - 2.0 * u + zp) / (d * d) - k * u * v;
+}}
+"""

@@ -119,6 +119,7 @@ class Options:
     max_events: int = 8          # capacity of t_events/y_events per event function per trajectory
     max_out: int = 0             # step-mode capacity of Solution.t/.y per trajectory (0 = final state only)
     jac_mode: int = 0            # 0 finite differences (ivp.rs:67-107), 1 analytic
+    jac_sparsity: object = None  # (n, n) structure of the Jacobian: finite differences per column GROUP (src/python/sparsity.rs)
     flags: int = 0
     user_solout: bool = False    # the problem's own SolOut hook replaces DefaultSolOut (src/solout.rs:55-63; include/ivpb.h)
     max_segments: int = 0        # dense_output: interpolant segments kept per trajectory (one per accepted step)

@@ -8,6 +8,7 @@
 // oracle::solve_ivp, the restatement of reference src/solve/solve_ivp.rs:99-313.
 #include <atomic>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "../include/ivpb.h"
@@ -95,6 +96,8 @@ int run_batch(const ivpb_options* o, int64_t N, double t0, double tf, const doub
       evc.push_back(c);
     }
   }
+  std::unique_ptr<Sparsity> sparsity;
+  if (o->has_jac_sparsity && o->jac_sparsity_colptr) sparsity.reset(new Sparsity((size_t)n, o->jac_sparsity_colptr, o->jac_sparsity_rows));
   if (nthreads < 1) nthreads = 1;
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
@@ -110,6 +113,7 @@ int run_batch(const ivpb_options* o, int64_t N, double t0, double tf, const doub
         prob.p = (p > 0 && params) ? params + (int64_t)p * i : nullptr;
         prob.ev_cfg = evc.empty() ? nullptr : evc.data();
         prob.jac_mode = o->jac_mode;
+        prob.sparsity = sparsity.get();
         std::vector<double> yy(y0 + (int64_t)n * i, y0 + (int64_t)n * (i + 1));
         try {
           Solution S = solve_ivp(prob, t0, tf, yy, O);
@@ -152,6 +156,13 @@ int dense_eval(const ivpb_options* o, double t0, double tf, const double* y0, co
 }  // namespace
 
 extern "C" {
+
+// Column groups of a sparsity structure (src/python/sparsity.rs:109-154), for tests of the runtime's own grouping.
+int oracle_group_columns(int n, const int32_t* colptr, const int32_t* rows, int32_t* groups) {
+  Sparsity sp((size_t)n, colptr, rows);
+  for (int c = 0; c < n; ++c) groups[c] = (int32_t)sp.groups[c];
+  return (int)sp.n_groups;
+}
 
 int oracle_problem_dims(int problem, int* n, int* p, int* ne) {
 #define DIMS(T) { *n = T::N; *p = T::P; *ne = T::NEV; return 0; }

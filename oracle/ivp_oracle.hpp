@@ -45,6 +45,39 @@ enum class Flag { Continue, Interrupt, ModifiedSolution };   // src/solout.rs:73
 
 struct ConfigError : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// src/python/sparsity.rs:13-154 -- SparsityStructure: per-column row lists and the greedy first-fit column groups
+// (two columns share a group iff they have no structural non-zero row in common).
+struct Sparsity {
+  size_t n = 0, n_groups = 0;
+  std::vector<std::vector<size_t>> col_to_rows;
+  std::vector<size_t> groups;
+  // from compressed columns (include/ivpb.h: jac_sparsity_colptr / jac_sparsity_rows)
+  Sparsity(size_t n_, const int* colptr, const int* rows) : n(n_), col_to_rows(n_), groups(n_, (size_t)-1) {
+    for (size_t c = 0; c < n; ++c)
+      for (int k = colptr[c]; k < colptr[c + 1]; ++k) col_to_rows[c].push_back((size_t)rows[k]);
+    std::vector<std::vector<bool>> group_rows;           // group_columns, sparsity.rs:109-154
+    for (size_t col = 0; col < n; ++col) {
+      const std::vector<size_t>& rs = col_to_rows[col];
+      bool assigned = false;
+      for (size_t g = 0; g < group_rows.size() && !assigned; ++g) {
+        bool can_use = true;
+        for (size_t r : rs) if (group_rows[g][r]) { can_use = false; break; }
+        if (can_use) {
+          groups[col] = g;
+          for (size_t r : rs) group_rows[g][r] = true;
+          assigned = true;
+        }
+      }
+      if (!assigned) {
+        groups[col] = n_groups++;
+        std::vector<bool> used(n, false);
+        for (size_t r : rs) used[r] = true;
+        group_rows.push_back(used);
+      }
+    }
+  }
+};
+
 // src/methods/mod.rs:104-214 -- scalar or per-component tolerance
 struct Tol {
   std::vector<double> v;

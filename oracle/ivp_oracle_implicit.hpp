@@ -128,6 +128,30 @@ inline void lin_solve_complex(const double* ar, const double* ai, size_t n, doub
   cdiv(0);
 }
 
+// ---- sparse finite differences with column grouping, src/python/sparsity.rs:160-202 (the Python front end's jac_fd,
+// src/python/ivp_wrapper.rs:194-209, when `jac_sparsity` is given).  One RHS call per group; only the structural
+// non-zeros are written -- every other entry of J keeps what it held (zero: the solvers allocate J zeroed).
+template <class F>
+void sparse_jacobian_fd(const F& f, double x, const std::vector<double>& y, const std::vector<double>& f0,
+                        const Sparsity& sp, std::vector<double>& J) {
+  const size_t n = sp.n;
+  const double eps = std::sqrt(std::numeric_limits<double>::epsilon());
+  for (size_t group = 0; group < sp.n_groups; ++group) {
+    std::vector<size_t> cols;                                   // columns_in_group, ascending (sparsity.rs:94-101)
+    for (size_t c = 0; c < n; ++c) if (sp.groups[c] == group) cols.push_back(c);
+    if (cols.empty()) continue;
+    std::vector<double> yp = y, h(n, 0.0), fp(n, 0.0);
+    for (size_t col : cols) {
+      const double pert = eps * std::fmax(std::fabs(y[col]), 1.0);
+      yp[col] = y[col] + pert;
+      h[col] = pert;
+    }
+    f.ode(x, yp.data(), fp.data());
+    for (size_t col : cols)
+      for (size_t row : sp.col_to_rows[col]) J[row * n + col] = (fp[row] - f0[row]) / h[col];
+  }
+}
+
 // ---- IVP::jac: user override (jac_mode 1) or the default forward differences, src/ivp.rs:67-107.
 // Row-major J[row * n + col]; the n + 1 RHS calls of the default are NOT counted in nfev.
 template <class F>
@@ -136,6 +160,7 @@ void eval_jac(const F& f, double x, const std::vector<double>& y, std::vector<do
   if (f.jac_mode == 1 && F::HAS_JAC) { f.jac(x, y.data(), J.data()); return; }
   std::vector<double> yp = y, fp(n), fo(n);
   f.ode(x, y.data(), fo.data());
+  if (f.sparsity) { sparse_jacobian_fd(f, x, y, fo, *f.sparsity, J); return; }
   const double eps = std::sqrt(std::numeric_limits<double>::epsilon());
   for (size_t col = 0; col < n; ++col) {
     const double yo = y[col];

@@ -12,6 +12,7 @@ struct ProblemBase {
   const double* p = nullptr;               // parameter row of this trajectory
   const EventConfig* ev_cfg = nullptr;     // override of event_config (from ivpb_options), or null
   int jac_mode = 0;                        // 0: default finite differences (ivp.rs:67-107); 1: analytic override
+  const Sparsity* sparsity = nullptr;      // jac_sparsity of the Python front end (src/python/sparsity.rs), or null
   int n_events() const { return NEV; }
   void events(double, const double*, double*) const {}
   EventConfig default_event_config(int) const { return EventConfig(); }

@@ -40,6 +40,9 @@ pub struct ivpb_options {
     pub mass_storage: i32,
     pub user_solout: i32,
     pub nind1: i32, pub nind2: i32, pub nind3: i32,
+    pub has_jac_sparsity: i32,
+    pub jac_sparsity_colptr: *const i32,
+    pub jac_sparsity_rows: *const i32,
 }
 
 #[repr(C)]

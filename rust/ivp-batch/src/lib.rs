@@ -70,6 +70,8 @@ pub struct Options {
     /// the problem's own SolOut hook replaces DefaultSolOut (ivp: `Method::solve(.., Some(&mut solout))`, src/solout.rs:55-63)
     pub user_solout: bool,
     pub mass_full: bool, pub nind1: Option<usize>, pub nind2: Option<usize>, pub nind3: Option<usize>,
+    /// `jac_sparsity` of ivp's Python front end (src/python/sparsity.rs): structural non-zeros as (row, col) pairs.
+    pub jac_sparsity: Option<Vec<(usize, usize)>>,
 }
 impl Options { pub fn builder() -> OptionsBuilder { OptionsBuilder(Options::default()) } }
 impl Default for Options {
@@ -77,7 +79,7 @@ impl Default for Options {
         Options { method: Method::DOPRI5, rtol: 1e-3.into(), atol: 1e-6.into(), max_steps: None, t_eval: None,
                   first_step: None, max_step: None, min_step: None, dense_output: false, event_config: None,
                   max_events: 8, max_out: 4096, analytic_jac: false, strict_fp: false, max_segments: 4096,
-                  user_solout: false, mass_full: false, nind1: None, nind2: None, nind3: None }
+                  user_solout: false, mass_full: false, nind1: None, nind2: None, nind3: None, jac_sparsity: None }
     }
 }
 pub struct OptionsBuilder(Options);
@@ -102,6 +104,8 @@ impl OptionsBuilder {
     pub fn nind1(mut self, k: usize) -> Self { self.0.nind1 = Some(k); self }
     pub fn nind2(mut self, k: usize) -> Self { self.0.nind2 = Some(k); self }
     pub fn nind3(mut self, k: usize) -> Self { self.0.nind3 = Some(k); self }
+    /// Sparse finite-difference Jacobian for RADAU / BDF: one RHS call per group of structurally orthogonal columns.
+    pub fn jac_sparsity(mut self, nz: Vec<(usize, usize)>) -> Self { self.0.jac_sparsity = Some(nz); self }
     /// The problem's own `SolOut` (`ivp_solout`) instead of `DefaultSolOut` (ivp: `Method::solve(.., Some(&mut solout))`).
     pub fn user_solout(mut self, b: bool) -> Self { self.0.user_solout = b; self }
     pub fn build(self) -> Options { self.0 }
@@ -177,6 +181,18 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         match e.direction { Direction::All => 0, Direction::Positive => 1, Direction::Negative => -1 },
         e.terminal_count.map(|k| k as i64).unwrap_or(-1))).unzip()).unwrap_or_default();
     let te = options.t_eval.as_deref();
+    // (row, col) pairs -> compressed columns (rows ascending, duplicates dropped)
+    let (sp_colptr, sp_rows): (Vec<i32>, Vec<i32>) = match &options.jac_sparsity {
+        None => (Vec::new(), Vec::new()),
+        Some(nz) => {
+            let mut cols: Vec<Vec<i32>> = vec![Vec::new(); n];
+            for &(r, c) in nz { assert!(r < n && c < n, "jac_sparsity entry out of range"); cols[c].push(r as i32); }
+            let mut colptr = vec![0i32]; let mut rows = Vec::new();
+            for c in cols.iter_mut() { c.sort_unstable(); c.dedup(); rows.extend_from_slice(c); colptr.push(rows.len() as i32); }
+            if rows.is_empty() { rows.push(0); }
+            (colptr, rows)
+        }
+    };
     let o = sys::ivpb_options {
         method: options.method as i32,
         n_rtol: options.rtol.as_slice().len() as i32, n_atol: options.atol.as_slice().len() as i32,
@@ -195,6 +211,9 @@ pub fn solve_ivp_batch(ctx: &Context, f: &Problem, t0: Float, tf: Float, y0: &[F
         mass_storage: options.mass_full as i32, user_solout: options.user_solout as i32,
         nind1: options.nind1.map_or(-1, |k| k as i32), nind2: options.nind2.map_or(-1, |k| k as i32),
         nind3: options.nind3.map_or(-1, |k| k as i32),
+        has_jac_sparsity: options.jac_sparsity.is_some() as i32,
+        jac_sparsity_colptr: if sp_colptr.is_empty() { ptr::null() } else { sp_colptr.as_ptr() },
+        jac_sparsity_rows: if sp_rows.is_empty() { ptr::null() } else { sp_rows.as_ptr() },
     };
     let cap = te.map_or(options.max_out, |t| t.len() + 1);
     let me = o.max_events as usize;

@@ -289,3 +289,60 @@ __device__ int ivp_solout(double xold, double& x, double* y, const double* p, do
             "__device__ void ivp_mass(const double* p, double* M) { for (int i = 0; i < 25; ++i) M[i] = (i % 6 == 0) ? 1.0 + i : 0.1; }")
     size, log = _nvrtc_compile(five, 5, 0, 0, 2, 4, 1, 1)   # n = 5: the mass matrix is the fifth shared-memory matrix
     assert size > 10000, log
+
+
+def _greedy_groups(S):
+    """Python restatement of group_columns (reference src/python/sparsity.rs:109-154)."""
+    n = S.shape[0]
+    groups, used = [-1] * n, []
+    for col in range(n):
+        rows = np.nonzero(S[:, col])[0]
+        for g, u in enumerate(used):
+            if not u[rows].any():
+                groups[col] = g
+                u[rows] = True
+                break
+        else:
+            u = np.zeros(n, dtype=bool)
+            u[rows] = True
+            used.append(u)
+            groups[col] = len(used) - 1
+    return groups, len(used)
+
+
+def test_jac_sparsity_marshalling_and_column_groups(oracle):
+    """Options.jac_sparsity -> compressed columns (include/ivpb.h), and the runtime's column grouping == the oracle's ==
+    a Python restatement of the reference's greedy first-fit rule, on the MEDAKZO structure and on random structures."""
+    lib = api.load_library()
+    olib = oracle.lib()
+    rng = np.random.default_rng(3)
+    cases = [synth.medakzo_sparsity(200), synth.medakzo_sparsity(5), np.eye(7, dtype=np.int8), np.ones((6, 6), dtype=np.int8),
+             np.zeros((4, 4), dtype=np.int8)] + [(rng.random((n, n)) < d).astype(np.int8) for n, d in ((40, 0.05), (64, 0.1), (9, 0.4))]
+    for S in cases:
+        n = S.shape[0]
+        mo = _abi.MarshalledOptions(Options(method=Method.RADAU, jac_sparsity=S), n, 0)
+        o = mo.struct
+        assert o.has_jac_sparsity == 1
+        colptr = np.ctypeslib.as_array(o.jac_sparsity_colptr, shape=(n + 1,))
+        assert colptr[0] == 0 and colptr[n] == int(S.sum())
+        rows = np.ctypeslib.as_array(o.jac_sparsity_rows, shape=(max(int(colptr[n]), 1),))
+        for c in range(n):
+            assert np.array_equal(rows[colptr[c]:colptr[c + 1]], np.nonzero(S[:, c])[0])
+        g_rt = np.zeros(n, dtype=np.int32)
+        g_or = np.zeros(n, dtype=np.int32)
+        ng_rt = lib.ivpb_debug_group_columns(n, _abi.ptr(mo.sp_colptr), _abi.ptr(mo.sp_rows), _abi.ptr(g_rt))
+        ng_or = olib.oracle_group_columns(n, _abi.ptr(mo.sp_colptr), _abi.ptr(mo.sp_rows), _abi.ptr(g_or))
+        g_py, ng_py = _greedy_groups(S)
+        assert ng_rt == ng_or == ng_py and list(g_rt) == list(g_or) == g_py
+    g, ng = _greedy_groups(synth.medakzo_sparsity(200))
+    assert ng <= 6          # 400 columns, a handful of RHS evaluations per Jacobian
+    assert _abi.MarshalledOptions(Options(), 3, 0).struct.has_jac_sparsity == 0
+    with pytest.raises(ValueError):
+        _abi.MarshalledOptions(Options(jac_sparsity=np.ones((2, 3))), 3, 0)
+
+
+def test_nvrtc_compiles_medakzo_400_for_the_warp_cooperative_kernels():
+    """n = 400 (the reference's own MEDAKZO size): the warp-cooperative RADAU kernel compiles for sm_100a with its iteration
+    matrices in global memory (warp_impl_shape says so; shared memory holds 6 n doubles per warp)."""
+    size, log = _nvrtc_compile(synth.medakzo_cuda_source(200), 400, 0, 0, 0, 4, 0, 1)
+    assert size > 10000, log

@@ -1142,3 +1142,73 @@ def test_analytic_jacobian_warp_cooperative_implicit(oracle, method):
         r = ib.solve_ivp_batch(user, 0.0, 1.5, Y0, None, Options(method=method, rtol=1e-8, atol=1e-10, jac_mode=jm))
         assert np.all(r.status == 0) and np.all(r.njev > 0)
         np.testing.assert_allclose(r.y_final, exact, rtol=2e-5, atol=2e-7)
+
+
+# ---- large state sizes and jac_sparsity on the warp-cooperative implicit kernels ------------------------------------
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_medakzo_400_on_the_device(oracle, method):
+    """The reference's own sparse-Jacobian test at its own size (tests/test_ivp.py:244-269: MEDAKZO on 200 grid points,
+    n = 400, `jac_sparsity=medazko_sparsity(n)`, default tolerances) on the device: the iteration matrices of a 400 x 400
+    system do not fit shared memory, so they live in the warp's global-memory slot (warp_impl_shape, gmats); the Jacobian
+    comes from one RHS evaluation per column GROUP (src/python/sparsity.rs:160-202).  Bit-exact with the oracle (problem
+    108 = the same RHS, same structure), and the golden values of the reference test hold."""
+    from ivp_b200 import api
+    ng = 200
+    user = api.Problem.from_cuda_source(synth.medakzo_cuda_source(ng), n=2 * ng)
+    y0 = np.zeros((2, 2 * ng))
+    y0[:, 1::2] = 1.0
+    y0[1, 1::2] = np.linspace(0.95, 1.05, ng)          # a second, different trajectory in the same launch
+    opts = Options(method=method, jac_sparsity=synth.medakzo_sparsity(ng))      # rtol 1e-3, atol 1e-6: the reference's defaults
+    g = ib.solve_ivp_batch(user, 0.0, 20.0, y0, None, opts)
+    o = oracle.solve_batch(108, 0.0, 20.0, y0, None, opts, nthreads=2)
+    assert np.array_equal(g.status, o.status) and np.all(g.status == 0)
+    assert np.array_equal(g.counters, o.counters)
+    assert np.array_equal(g.y_final, o.y_final)
+    y = g.y_final[0]
+    np.testing.assert_allclose(y[78], 0.233994e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[79], 0, atol=1e-3)
+    np.testing.assert_allclose(y[148], 0.359561e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[149], 0, atol=1e-3)
+    np.testing.assert_allclose(y[198], 0.117374129e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[199], 0.6190807e-5, atol=1e-3)
+    np.testing.assert_allclose(y[238], 0, atol=1e-3)
+    np.testing.assert_allclose(y[239], 0.9999997, rtol=1e-2)
+
+
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_sparse_fd_jacobian_groups(oracle, method):
+    """jac_sparsity on the built-in MEDAKZO (n = 64).  (a) With the true structure the grouped differences give the very
+    bits of the dense ones (a column's rows do not depend on the other columns of its group; entries outside the structure
+    are (f - f) / h = 0).  (b) With a deliberately INCOMPLETE structure (the coupling to the neighbouring grid points
+    removed) the Jacobian is a different matrix: the device must follow the reference's rule -- only structural entries are
+    written, the rest stays zero -- and agree with the oracle bit for bit, with different Newton statistics than (a)."""
+    N = 24
+    prob, y0, par, t0, tf = synth.ensemble("medakzo", N)
+    S = synth.medakzo_sparsity(32)
+    base = dict(method=method, rtol=1e-5, atol=1e-7, flags=IVPB_FLAG_STRICT_FP)
+    dense = ib.solve_ivp_batch(prob, t0, 3.0, y0, par, Options(**base))
+    full = ib.solve_ivp_batch(prob, t0, 3.0, y0, par, Options(jac_sparsity=S, **base))
+    assert np.array_equal(dense.counters, full.counters) and np.array_equal(dense.y_final, full.y_final)
+    S2 = S.copy()
+    i = np.arange(32) * 2
+    S2[i[1:], i[1:] - 2] = 0
+    S2[i[:-1], i[:-1] + 2] = 0
+    opts = Options(jac_sparsity=S2, **base)
+    g = ib.solve_ivp_batch(prob, t0, 3.0, y0, par, opts)
+    o = oracle.solve_batch(PROBLEMS[prob], t0, 3.0, y0, par, opts)
+    assert np.array_equal(g.status, o.status)
+    assert np.array_equal(g.counters, o.counters) and np.array_equal(g.y_final, o.y_final)
+    assert not np.array_equal(g.counters, dense.counters)
+
+
+def test_radau_n100_matrices_in_global_memory(oracle):
+    """RADAU at n = 100 (built-in linear100): three 100 x 101 iteration matrices are 242 KB -- over the 227 KB of shared
+    memory, refused until round 2 -- so they take the global-memory slot; bit-exact with the oracle."""
+    N = 6
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(0.5, 1.5, (N, 100))
+    opts = Options(method=Method.RADAU, rtol=1e-6, atol=1e-8, flags=IVPB_FLAG_STRICT_FP)
+    g = ib.solve_ivp_batch("linear100", 0.0, 2.0, y0, None, opts)
+    o = oracle.solve_batch(PROBLEMS["linear100"], 0.0, 2.0, y0, None, opts)
+    assert np.all(g.status == 0) and np.array_equal(g.counters, o.counters) and np.array_equal(g.y_final, o.y_final)
+    np.testing.assert_allclose(g.y_final, y0 * np.exp(-2.0), rtol=1e-5)

@@ -336,3 +336,27 @@ def test_medakzo_400_golden_values(oracle, method):
     np.testing.assert_allclose(y[199], 0.6190807e-5, atol=1e-3)
     np.testing.assert_allclose(y[238], 0, atol=1e-3)
     np.testing.assert_allclose(y[239], 0.9999997, rtol=1e-2)
+
+
+@pytest.mark.parametrize("method", [Method.RADAU, Method.BDF])
+def test_medakzo_400_with_jac_sparsity(oracle, method):
+    """tests/test_ivp.py:244-269 as the reference runs it: `jac_sparsity=medazko_sparsity(n)`.  The grouped differences
+    (src/python/sparsity.rs:160-202) reproduce the dense ones bit for bit on the true structure, and the golden values hold."""
+    from ivp_b200 import synth
+    n = 200
+    y0 = np.zeros(2 * n)
+    y0[1::2] = 1
+    d = oracle.solve_batch(108, 0.0, 20.0, [y0], None, Options(method=method))
+    s = oracle.solve_batch(108, 0.0, 20.0, [y0], None, Options(method=method, jac_sparsity=synth.medakzo_sparsity(n)))
+    assert s.status[0] == Status.Success
+    assert np.array_equal(s.counters, d.counters) and np.array_equal(s.y_final, d.y_final)
+    y = s.y_final[0]
+    np.testing.assert_allclose(y[78], 0.233994e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[148], 0.359561e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[198], 0.117374129e-3, rtol=1e-2)
+    np.testing.assert_allclose(y[239], 0.9999997, rtol=1e-2)
+    # an incomplete structure really changes the Jacobian (only structural entries are written)
+    S = synth.medakzo_sparsity(n)
+    S[np.arange(n) * 2, np.arange(n) * 2 + 1] = 0
+    w = oracle.solve_batch(108, 0.0, 20.0, [y0], None, Options(method=method, jac_sparsity=S))
+    assert not np.array_equal(w.counters, d.counters)
