@@ -95,7 +95,9 @@ typedef struct {
   int32_t user_solout;         /* 1: the problem's own SolOut hook (`solout` / `ivp_solout`, src/solout.rs:55-63) replaces
                                   DefaultSolOut -- the reference's low-level `Method::solve(.., Some(&mut solout))` call
                                   (e.g. src/methods/dop853.rs:114-127): no t_eval / events / dense log; samples the hook emits
-                                  go to t_out / y_out (capacity max_out).  All six methods; n <= 32 (RADAU / BDF: n <= 8). */
+                                  go to t_out / y_out (capacity max_out).  All six methods, every state size: in the
+                                  warp-per-trajectory kernels (n > 32; RADAU / BDF n > 8) the hook runs warp-uniformly on the
+                                  full state in shared memory and must take its eval() buffer from dense.buffer(). */
   int32_t nind1, nind2, nind3; /* Options.nind1..3: index-1/2/3 variable counts of a DAE, < 0 => None
                                   (partition rules and Error::Config of src/methods/radau.rs:210-245) */
   /* RADAU / BDF with jac_mode = 0: `jac_sparsity` of the reference's Python front end (src/python/solve.rs, SparsityStructure

@@ -524,6 +524,58 @@ struct SolOutDev {
 };
 
 // ---------------------------------------------------------------------------------------------
+// The problem's own SolOut (src/solout.rs:55-63) in the warp-per-trajectory kernels (n > 32; RADAU / BDF n > 8).  The
+// hook is executed by all 32 lanes with identical arguments (warp-uniform control flow): `y` is the FULL state in the
+// warp's shared-memory row (n doubles, writable); `dense.eval(t, yi)` fills a full vector that must be shared by the warp
+// -- `dense.buffer()` hands out n doubles for it (the thread-per-trajectory kernels offer the same call, so a hook
+// written with it runs in both) -- each lane evaluating its own components; `emit(t, yv)` takes a full vector and
+// every lane stores its slice.  Afterwards the lanes re-read their slices of y, so a moved state (ModifiedSolution, or the
+// point an Interrupt reports) is picked up.
+template <class Prob, int METHOD, class L, class Out>
+struct WarpHook {
+  static constexpr int N = L::NL, NG = Prob::N, NC = MethodTraits<METHOD>::NC;
+  struct Interp {
+    const double (&c)[NC][N]; double xold, h; bool ok;
+    __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ double* buffer() const { return L::row() + NG; }
+    __device__ __forceinline__ void eval(double t, double* yi) const {
+      double loc[N];
+      erk_interp<METHOD, N>(t, loc, c, xold, h);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < N; ++i) if (L::valid(i)) yi[L::gi(i)] = loc[i];
+      __syncwarp();
+    }
+  };
+  struct Emit {
+    Out& so; const KArgs& a; i64 idx;
+    __device__ __forceinline__ void operator()(double t, const double* yv) {
+      double loc[N];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < N; ++i) loc[i] = L::valid(i) ? yv[L::gi(i)] : 0.0;
+      so.push(a, idx, t, loc);
+    }
+  };
+  // returns the hook's flag: 0 Continue, 1 Interrupt, 2 ModifiedSolution
+  static __device__ __forceinline__ int run(const KArgs& a, i64 idx, Out& so, bool first, double xold, double& x, double (&y)[N],
+                                            const double* p, double* ustate, const double (&cont)[NC][N], double hstep, double ixold) {
+    double* ys = L::row();
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (L::valid(i)) ys[L::gi(i)] = y[i];
+    __syncwarp();
+    const Interp ip{cont, ixold, hstep, !first};
+    Emit em{so, a, idx};
+    const int fl = Prob::solout(xold, x, ys, p, ustate, ip, em);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = L::valid(i) ? ys[L::gi(i)] : 0.0;
+    __syncwarp();
+    return fl;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Per-thread trajectory state + the step loops.
 template <class Prob, int METHOD, int FEAT, class L = ThreadLayout<Prob>>
 struct ErkTraj {
@@ -560,7 +612,9 @@ struct ErkTraj {
   // What the user SolOut sees of the step (StepInterpolant, src/dense.rs:32-97) and of the output arrays
   struct UserInterp {
     const double (&c)[NC][N]; double xold, h; bool ok;
+    mutable double buf[N];
     __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ double* buffer() const { return buf; }      // n doubles for eval(), see WarpHook
     __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<METHOD, N>(t, yi, c, xold, h); }
   };
   struct UserEmit {
@@ -571,9 +625,13 @@ struct ErkTraj {
   // Returns 0 Continue, 1 Interrupt (status set, (x, y) at the point to report), 2 ModifiedSolution (k1 re-evaluated).
   __device__ __forceinline__ int callback(const KArgs& a, bool first, double xold, const double (&cont)[NC][N], double hstep) {
     if constexpr (USER) {
-      const UserInterp ip{cont, xold, hstep, !first};
-      UserEmit em{so, a, idx};
-      const int fl = Prob::solout(xold, x, y, p, ustate, ip, em);
+      int fl;
+      if constexpr (L::WARP) fl = WarpHook<Prob, METHOD, L, Out>::run(a, idx, so, first, xold, x, y, p, ustate, cont, hstep, xold);
+      else {
+        const UserInterp ip{cont, xold, hstep, !first};
+        UserEmit em{so, a, idx};
+        fl = Prob::solout(xold, x, y, p, ustate, ip, em);
+      }
       if (fl == 1) { status = ST_INTERRUPT; return 1; }
       if (fl == 2) { L::ode(x, y, p, k1); nfev += 1; return 2; }
       return 0;

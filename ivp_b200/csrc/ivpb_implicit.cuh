@@ -408,6 +408,8 @@ struct RadauTraj {
   double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
   struct UserInterp {                                  // StepInterpolant of the accepted step (src/dense.rs:32-97)
     const double (&c)[4][N]; double xold, h; bool ok;
+    mutable double buf[N];
+    __device__ __forceinline__ double* buffer() const { return buf; }      // n doubles for eval(), see WarpHook (ivpb_erk.cuh)
     __device__ __forceinline__ bool valid() const { return ok; }
     __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<M_RADAU, N>(t, yi, c, xold, h); }
   };
@@ -888,6 +890,8 @@ struct BdfTraj {
   double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
   struct UserInterp {                                  // StepInterpolant of the accepted step (bdf.rs:516-519)
     const double (&c)[7][N]; double xold, h; bool ok;
+    mutable double buf[N];
+    __device__ __forceinline__ double* buffer() const { return buf; }      // n doubles for eval(), see WarpHook (ivpb_erk.cuh)
     __device__ __forceinline__ bool valid() const { return ok; }
     __device__ __forceinline__ void eval(double t, double* yi) const { erk_interp<M_BDF, N>(t, yi, c, xold, h); }
   };

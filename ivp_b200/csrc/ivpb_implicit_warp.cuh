@@ -383,6 +383,22 @@ struct RadauWarpTraj {
   int singular_count, status;
   bool last, reject, first, call_jac, call_decomp;
   Out so;
+  static constexpr bool USER = (FEAT & K_USER) != 0;
+  double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
+  // The callback slot of radau.rs:336-356,712-740: DefaultSolOut, or the problem's own SolOut (WarpHook, ivpb_erk.cuh;
+  // ModifiedSolution re-evaluates f0, scal keeps the values of the unmodified state, like the reference).  1 = Interrupt.
+  __device__ __forceinline__ int callback(const KArgs& a, bool first_call, double xold, double hstep) {
+    if constexpr (USER) {
+      const int fl = WarpHook<Prob, M_RADAU, L, Out>::run(a, idx, so, first_call, xold, x, y, p, ustate, cont, hstep, xold);
+      if (fl == 1) { status = ST_INTERRUPT; return 1; }
+      if (fl == 2) { L::ode(x, y, p, f0); nfev += 1; return 2; }
+      return 0;
+    } else {
+      double tev, yev[N];
+      if (so.solout(a, idx, p, first_call, xold, x, y, cont, hstep, xold, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return 1; }
+      return 0;
+    }
+  }
 
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double* b2() const { return B::extra() + NN; }
@@ -430,8 +446,11 @@ struct RadauWarpTraj {
     L::ode(x, y, p, f0);
     nfev = 1;
     if constexpr (FEAT != 0) {
-      double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if constexpr (USER) {
+#pragma unroll
+        for (int q = 0; q < Prob::NSTATE; ++q) ustate[q] = 0.0;
+      }
+      if (callback(a, true, x, 0.0) == 1) return true;
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) scal[i] = L::atol(a, i) + L::rtol(a, i) * fabs(y[i]);
@@ -690,10 +709,7 @@ struct RadauWarpTraj {
 #pragma unroll
       for (int i = 0; i < N; ++i) scal[i] = L::atol(a, i) + L::rtol(a, i) * fabs(y[i]);
       if constexpr (FEAT != 0) {
-        double tev, yev[N];
-        if (so.solout(a, idx, p, false, xold, x, y, cont, h, xold, tev, yev)) {
-          status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-        }
+        if (callback(a, false, xold, h) == 1) return true;
       }
       if (last) { h = hnew; status = ST_SUCCESS; return true; }
       singular_count = 0;
@@ -748,6 +764,41 @@ struct BdfWarpTraj {
   int order, n_equal_steps, status;
   bool lu_is_current, jac_pending;
   Out so;
+  static constexpr bool USER = (FEAT & K_USER) != 0;
+  double ustate[USER ? Prob::NSTATE : 1];              // the user SolOut's own fields (Options.user_solout)
+  // The callback slot of bdf.rs:243-274,516-545: DefaultSolOut, or the problem's own SolOut (WarpHook, ivpb_erk.cuh).
+  // ModifiedSolution restarts the difference table at order 1 from the changed state and asks for a new Jacobian
+  // (bdf.rs:255-271,525-541), as in the thread-per-trajectory kernel.  Returns 1 on Interrupt.
+  __device__ __forceinline__ int callback(const KArgs& a, bool first_call, double xold, const double (&cont)[7][N],
+                                          double hstep, double ixold) {
+    if constexpr (USER) {
+      const int fl = WarpHook<Prob, M_BDF, L, Out>::run(a, idx, so, first_call, xold, x, y, p, ustate, cont, hstep, ixold);
+      if (fl == 1) { status = ST_INTERRUPT; return 1; }
+      if (fl == 2) {
+        double f0[N];
+        L::ode(x, y, p, f0);
+        nfev += 1;
+        const double direction = signum(a.tf - a.t0);
+        for (int k = 2; k < ND; ++k)
+#pragma unroll
+          for (int i = 0; i < N; ++i) if (L::valid(i)) D(k, i) = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (L::valid(i)) { D(0, i) = y[i]; D(1, i) = f0[i] * current_h * direction; }
+          jy[i] = y[i];
+        }
+        order = 1; n_equal_steps = 0;
+        jx = x; jac_pending = true; njev += 1;
+        lu_is_current = false;
+        return 2;
+      }
+      return 0;
+    } else {
+      double tev, yev[N];
+      if (so.solout(a, idx, p, first_call, xold, x, y, cont, hstep, ixold, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return 1; }
+      return 0;
+    }
+  }
 
   __device__ __forceinline__ double* b1() const { return B::extra(); }
   __device__ __forceinline__ double& D(int k, int i) const { return B::extra()[NN + k * NN + L::gi(i)]; }          // local slot i
@@ -856,8 +907,11 @@ struct BdfWarpTraj {
       for (int c = 0; c < 7; ++c)
 #pragma unroll
         for (int i = 0; i < N; ++i) cont[c][i] = 0.0;
-      double tev, yev[N];
-      if (so.solout(a, idx, p, true, x, x, y, cont, 0.0, x, tev, yev)) { status = ST_INTERRUPT; to_event_point(tev, yev); return true; }
+      if constexpr (USER) {
+#pragma unroll
+        for (int q = 0; q < Prob::NSTATE; ++q) ustate[q] = 0.0;
+      }
+      if (callback(a, true, x, cont, 0.0, x) == 1) return true;
     }
     return false;
   }
@@ -1037,10 +1091,7 @@ struct BdfWarpTraj {
         for (int k = 0; k < MAX_ORDER; ++k) cont[1 + k][i] = (k + 1 <= order && L::valid(i)) ? D(k + 1, i) : 0.0;
         cont[6][i] = (double)order;
       }
-      double tev, yev[N];
-      if (so.solout(a, idx, p, false, x - h_signed, x, y, cont, h_signed, x_start, tev, yev)) {
-        status = ST_INTERRUPT; to_event_point(tev, yev); return true;
-      }
+      if (callback(a, false, x - h_signed, cont, h_signed, x_start) == 1) return true;
     }
     if (direction * (x - xend) >= 0.0) { status = ST_SUCCESS; return true; }
     if (n_equal_steps >= order + 1) {

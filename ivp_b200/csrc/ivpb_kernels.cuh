@@ -75,6 +75,9 @@ __host__ inline const void* erk_lookup_feat_any(int feat) {
       case K_OUT | K_EVENTS:
         if constexpr (Prob::NEV > 0) return (const void*)&erk_warp_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
         else return nullptr;
+      case K_USER:                       // Options.user_solout: the problem's own SolOut (WarpHook, ivpb_erk.cuh)
+        if constexpr (Prob::HAS_SOLOUT) return (const void*)&erk_warp_kernel<Prob, METHOD, K_USER>;
+        else return nullptr;
       default: return nullptr;
     }
   }
@@ -139,6 +142,9 @@ __host__ inline const void* implicit_lookup_feat(int feat, int* block, int* smem
         case K_OUT: return (const void*)&implicit_warp_kernel<Prob, METHOD, K_OUT>;
         case K_OUT | K_EVENTS:
           if constexpr (Prob::NEV > 0) return (const void*)&implicit_warp_kernel<Prob, METHOD, K_OUT | K_EVENTS>;
+          else return nullptr;
+        case K_USER:                     // Options.user_solout: the problem's own SolOut (WarpHook, ivpb_erk.cuh)
+          if constexpr (Prob::HAS_SOLOUT) return (const void*)&implicit_warp_kernel<Prob, METHOD, K_USER>;
           else return nullptr;
         default: return nullptr;
       }

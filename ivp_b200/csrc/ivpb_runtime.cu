@@ -254,8 +254,6 @@ int validate(ivpb_ctx* ctx, const ProblemInfo& pi, const ivpb_options* o, int64_
   if (o->user_solout) {
     // Method::solve(.., Some(&mut user_solout)) (e.g. dop853.rs:114-127): DefaultSolOut's services do not exist on this path
     if (!(pi.has_jac & 4)) return fail(ctx, IVPB_ERR_CONFIG, "user_solout = 1, but the problem defines no SolOut hook (solout / ivp_solout)");
-    if (pi.n > ((o->method == IVPB_RADAU || o->method == IVPB_BDF) ? 8 : ivpb::MAX_N))
-      return fail(ctx, IVPB_ERR_CONFIG, "user SolOut hooks need the thread-per-trajectory kernels (n <= 32, RADAU / BDF: n <= 8)");
     if (o->has_t_eval || o->dense_output) return fail(ctx, IVPB_ERR_CONFIG, "user_solout = 1: t_eval / dense_output belong to DefaultSolOut; emit samples from the hook instead");
   }
   if (o->method == IVPB_RADAU) {

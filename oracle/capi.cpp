@@ -174,7 +174,7 @@ int oracle_problem_dims(int problem, int* n, int* p, int* ne) {
     case IVPB_P_LINEAR100: DIMS(Linear100) case IVPB_P_MEDAKZO64: DIMS(Medakzo64)
     case IVPB_P_ROBERTSON_DAE: DIMS(RobertsonDae) case IVPB_P_MASS_LINEAR3: DIMS(MassLinear3) case IVPB_P_BALL_BOUNCE: DIMS(BallBounce)
     case 100: DIMS(RationalEv) case 101: DIMS(Sys3) case 102: DIMS(Scale1) case 103: DIMS(Scale2)
-    case 104: DIMS(Radial) case 105: DIMS(ConstRates) case 106: DIMS(Linear2) case 107: DIMS(MassLinear4) case 108: DIMS(Medakzo400) case 109: DIMS(MassLinear12)
+    case 104: DIMS(Radial) case 105: DIMS(ConstRates) case 106: DIMS(Linear2) case 107: DIMS(MassLinear4) case 108: DIMS(Medakzo400) case 109: DIMS(MassLinear12) case 110: DIMS(DecayKick40)
     default: return 1;
   }
 }
@@ -191,7 +191,7 @@ int oracle_solve_batch(int problem, const ivpb_options* o, int64_t N, double t0,
     case IVPB_P_ROBERTSON_DAE: return RB(RobertsonDae); case IVPB_P_MASS_LINEAR3: return RB(MassLinear3);
     case IVPB_P_BALL_BOUNCE: return RB(BallBounce);
     case 100: return RB(RationalEv); case 101: return RB(Sys3); case 102: return RB(Scale1); case 103: return RB(Scale2);
-    case 104: return RB(Radial); case 105: return RB(ConstRates); case 106: return RB(Linear2); case 107: return RB(MassLinear4); case 108: return RB(Medakzo400); case 109: return RB(MassLinear12);
+    case 104: return RB(Radial); case 105: return RB(ConstRates); case 106: return RB(Linear2); case 107: return RB(MassLinear4); case 108: return RB(Medakzo400); case 109: return RB(MassLinear12); case 110: return RB(DecayKick40);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -210,7 +210,7 @@ int oracle_dense_eval(int problem, const ivpb_options* o, double t0, double tf, 
     case IVPB_P_ROBERTSON_DAE: return DE(RobertsonDae); case IVPB_P_MASS_LINEAR3: return DE(MassLinear3);
     case IVPB_P_BALL_BOUNCE: return DE(BallBounce);
     case 100: return DE(RationalEv); case 101: return DE(Sys3); case 102: return DE(Scale1); case 103: return DE(Scale2);
-    case 104: return DE(Radial); case 105: return DE(ConstRates); case 106: return DE(Linear2); case 107: return DE(MassLinear4); case 108: return DE(Medakzo400); case 109: return DE(MassLinear12);
+    case 104: return DE(Radial); case 105: return DE(ConstRates); case 106: return DE(Linear2); case 107: return DE(MassLinear4); case 108: return DE(Medakzo400); case 109: return DE(MassLinear12); case 110: return DE(DecayKick40);
     default: g_err = "unknown problem id"; return 1;
   }
 }
@@ -228,7 +228,7 @@ int oracle_dense_eval_extrapolate(int problem, const ivpb_options* o, double t0,
     case IVPB_P_ROBERTSON_DAE: return DX(RobertsonDae); case IVPB_P_MASS_LINEAR3: return DX(MassLinear3);
     case IVPB_P_BALL_BOUNCE: return DX(BallBounce);
     case 100: return DX(RationalEv); case 101: return DX(Sys3); case 102: return DX(Scale1); case 103: return DX(Scale2);
-    case 104: return DX(Radial); case 105: return DX(ConstRates); case 106: return DX(Linear2); case 107: return DX(MassLinear4); case 108: return DX(Medakzo400); case 109: return DX(MassLinear12);
+    case 104: return DX(Radial); case 105: return DX(ConstRates); case 106: return DX(Linear2); case 107: return DX(MassLinear4); case 108: return DX(Medakzo400); case 109: return DX(MassLinear12); case 110: return DX(DecayKick40);
     default: g_err = "unknown problem id"; return 1;
   }
 }

@@ -715,6 +715,8 @@ struct UserSolOut {
   UserSolOut(const F& f_, size_t n_) : f(f_), n(n_), state(F::NSTATE, 0.0) {}
   struct Interp {
     const StepInterp* ip; size_t n;
+    mutable std::vector<double> buf;
+    double* buffer() const { buf.resize(n); return buf.data(); }      // n doubles for eval() (device: WarpHook, ivpb_erk.cuh)
     bool valid() const { return ip != nullptr; }
     void eval(double tt, double* yi) const { ip->interpolate(tt, yi, n); }
   };
@@ -723,7 +725,7 @@ struct UserSolOut {
     void operator()(double tt, const double* yy) { self->t.push_back(tt); self->y.insert(self->y.end(), yy, yy + self->n); }
   };
   Flag solout(double xold, double& x, std::vector<double>& yv, const StepInterp* ip) {
-    Interp in{ip, n};
+    Interp in{ip, n, {}};
     Emit em{this};
     const int fl = f.solout(xold, x, yv.data(), state.data(), in, em);
     x_last = x; y_last = yv;

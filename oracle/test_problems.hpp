@@ -131,4 +131,34 @@ struct Medakzo400 : ProblemBase<Medakzo400, 400, 0, 0> {
   }
 };
 
+// Test infrastructure for SolOut hooks in the warp-per-trajectory kernels (n > 32 explicit, n > 8 RADAU / BDF): 40 decaying
+// components y_i' = -(0.5 + 0.05 i) y_i; the hook finds the point where y[0] falls below 0.5 on the step interpolant
+// (bisection), restarts there with the whole state doubled (ModifiedSolution), records the point, and stops the
+// integration at the third kick (Interrupt).  tests/test_solout_hook.py holds the same hook in CUDA C.
+struct DecayKick40 : ProblemBase<DecayKick40, 40, 0, 0> {
+  void ode(double, const double* y, double* d) const {
+    for (int i = 0; i < 40; ++i) d[i] = -(0.5 + 0.05 * (double)i) * y[i];
+  }
+  static constexpr bool HAS_SOLOUT = true;
+  template <class Interp, class Emit>
+  int solout(double xold, double& x, double* y, double* state, const Interp& dense, Emit& emit) const {
+    if (!dense.valid()) { emit(x, y); return 0; }
+    if (!(y[0] < 0.5)) return 0;
+    double lo = xold, hi = x;
+    double* yi = dense.buffer();
+    for (int it = 0; it < 40; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      dense.eval(mid, yi);
+      if (yi[0] < 0.5) hi = mid; else lo = mid;
+    }
+    dense.eval(hi, yi);
+    x = hi;
+    for (int i = 0; i < 40; ++i) y[i] = 2.0 * yi[i];
+    state[0] += 1.0;
+    emit(x, y);
+    if (state[0] >= 3.0) return 1;
+    return 2;
+  }
+};
+
 }  // namespace oracle

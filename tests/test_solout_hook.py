@@ -143,3 +143,83 @@ def test_user_solout_config_errors():
     # without user_solout the same problem is an ordinary ODE under DefaultSolOut: the ball falls through the floor
     g = ib.solve_ivp_batch("ball_bounce", 0.0, 3.0, np.array([[10.0, 0.0]]), par, Options(rtol=1e-8, atol=1e-10))
     assert g.status[0] == Status.Success and g.y_final[0, 0] < 0.0
+
+
+# ---- hooks in the warp-per-trajectory kernels (n > 32 explicit, n > 8 RADAU / BDF) -------------------------------------
+# The device twin of oracle/test_problems.hpp DecayKick40 (problem 110): 40 decaying components; the hook bisects the point
+# where y[0] falls below 0.5 on the step interpolant, restarts there with the whole state doubled, records it, and stops at
+# the third kick.  `dense.buffer()` provides the n doubles eval() fills -- shared by the warp in these kernels.
+KICK40_SRC = r"""
+__device__ double ivp_ode_i(double t, const double* y, const double* p, int i) { return -(0.5 + 0.05 * (double)i) * y[i]; }
+template <class Interp, class Emit>
+__device__ int ivp_solout(double xold, double& x, double* y, const double* p, double* state, const Interp& dense, Emit& emit) {
+  if (!dense.valid()) { emit(x, y); return 0; }
+  if (!(y[0] < 0.5)) return 0;
+  double lo = xold, hi = x;
+  double* yi = dense.buffer();
+  for (int it = 0; it < 40; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    dense.eval(mid, yi);
+    if (yi[0] < 0.5) hi = mid; else lo = mid;
+  }
+  dense.eval(hi, yi);
+  x = hi;
+  for (int i = 0; i < 40; ++i) y[i] = 2.0 * yi[i];
+  state[0] += 1.0;
+  emit(x, y);
+  if (state[0] >= 3.0) return 1;
+  return 2;
+}
+"""
+
+
+def kick40_y0(N):
+    rng = np.random.default_rng(40)
+    y0 = rng.uniform(0.8, 1.2, (N, 40))
+    y0[:, 0] = np.linspace(0.9, 1.1, N)
+    return y0
+
+
+@pytest.mark.parametrize("method", HOOKED)
+def test_oracle_kick40_hook(oracle, method):
+    """The oracle side of the warp-kernel hook test: three kicks, each where y[0] crosses 0.5 (y[0] = y0 e^{-t/2})."""
+    y0 = kick40_y0(3)
+    o = oracle.solve_batch(110, 0.0, 20.0, y0, None, opts_for(method))
+    assert np.all(o.status == Status.UserInterrupt) and np.all(o.n_out == 4)
+    t1 = 2.0 * np.log(y0[:, 0] / 0.5)                                 # first crossing; afterwards y[0] restarts from 1.0
+    tol = 5e-3 if method == Method.RK4 else 1e-5
+    np.testing.assert_allclose(o.t_out[:, 1], t1, rtol=tol)
+    np.testing.assert_allclose(o.t_out[:, 3] - o.t_out[:, 2], 2.0 * np.log(2.0), rtol=tol)
+    np.testing.assert_allclose(o.y_out[:, 1:4, 0], 1.0, rtol=tol)
+    assert np.array_equal(o.t_final, o.t_out[:, 3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", HOOKED)
+def test_hook_in_warp_per_trajectory_kernels(oracle, method):
+    """Options.user_solout on a problem with n = 40: explicit methods run one trajectory per warp (n > 32), RADAU / BDF the
+    warp-cooperative kernels (n > 8).  The hook sees the full state in shared memory, evaluates the step interpolant into
+    dense.buffer(), moves (x, y) and returns ModifiedSolution / Interrupt; strict build bit-identical to the oracle."""
+    from ivp_b200 import api
+    N = 37
+    y0 = kick40_y0(N)
+    user = api.Problem.from_cuda_source(KICK40_SRC, n=40, has_solout=True)
+    opts = opts_for(method, flags=IVPB_FLAG_STRICT_FP)
+    g = ib.solve_ivp_batch(user, 0.0, 20.0, y0, None, opts)
+    o = oracle.solve_batch(110, 0.0, 20.0, y0, None, opts)
+    assert np.array_equal(g.status, o.status) and np.all(g.status == Status.UserInterrupt)
+    assert np.array_equal(g.n_out, o.n_out) and np.array_equal(g.counters, o.counters)
+    assert np.array_equal(g.t_out, o.t_out) and np.array_equal(g.y_out, o.y_out)
+    assert np.array_equal(g.t_final, o.t_final) and np.array_equal(g.y_final, o.y_final)
+
+
+@pytest.mark.parametrize("method", HOOKED)
+def test_nvrtc_compiles_the_hook_for_the_warp_kernels(method):
+    """No GPU needed: the K_USER instances of erk_warp_kernel / implicit_warp_kernel compile for sm_100a (strict build)."""
+    import ctypes
+    from ivp_b200 import api
+    lib = api.load_library()
+    lib.ivpb_debug_nvrtc_compile.restype = ctypes.c_longlong
+    log = ctypes.create_string_buffer(1 << 16)
+    size = lib.ivpb_debug_nvrtc_compile(KICK40_SRC.encode(), 40, 0, 0, 4, int(method), 4, 1, log, 1 << 16)
+    assert size > 10000, log.value.decode()
