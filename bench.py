@@ -441,6 +441,8 @@ def main():
         dist.all_reduce(t)
         e2e_rank_ms = [round(float(x), 3) for x in t.tolist()]
     fp_mode = ctx.last_fp_mode() if hasattr(ctx, "last_fp_mode") else None
+    if isinstance(fp_mode, dict) and fp_mode.get("mode") == "strict":
+        fp_mode["second_pass_trajectories"] = ctx.last_reruns()      # strictd kernels: deferred division guards (ivpb_exact.cuh)
 
     # ---- N > 1: the other scaling flavour, same JSON line ----
     other = None

@@ -203,6 +203,12 @@ class Context:
                      out_of_tolerance=int(info[5]))
         return d
 
+    def last_reruns(self) -> int:
+        """Debug: trajectories the last strict solve on device 0 handed to its guarded second pass (-1: none has run)."""
+        self.lib.ivpb_debug_last_reruns.restype = C.c_longlong
+        self.lib.ivpb_debug_last_reruns.argtypes = [C.c_void_p]
+        return int(self.lib.ivpb_debug_last_reruns(self.ptr))
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self.check(self.lib.ivpb_measure_fp64_peak(self.ptr, C.byref(v)))

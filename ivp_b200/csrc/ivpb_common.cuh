@@ -14,6 +14,7 @@ typedef unsigned long long u64;
 enum { M_RK23 = 0, M_DOPRI5 = 1, M_DOP853 = 2, M_RK4 = 3, M_RADAU = 4, M_BDF = 5 };
 // Status codes == reference enum Status (src/status.rs:4-19)
 enum { ST_SUCCESS = 0, ST_INTERRUPT = 1, ST_NMAX = 2, ST_SMALL = 3, ST_STIFF = 4, ST_SINGULAR = 5, ST_POOR = 6 };
+enum { ST_RERUN = 100 };   // internal, never written out: a strictd trajectory abandoned for the guarded re-run (ivpb_exact.cuh)
 // Output-handler features a kernel instance is specialised for (what DefaultSolOut has to do,
 // reference src/solve/solout.rs:128-431).  FEAT == 0: final state + counters only, and the dense-output
 // coefficients nobody would read are not computed.
@@ -43,6 +44,12 @@ struct KArgs {
   const int* sp_rows;    // [sp_colptr[n]]
   const int* sp_group;   // [n] group of each column
   int sp_ngroups;
+  // strictd kernels (deferred division / square-root guards, ivpb_exact.cuh): trajectories that have to be repeated by
+  // the guarded twin are appended here; the twin's launch gets perm = rerun_list and n_dev = rerun_count
+  unsigned* rerun_list;      // [N]
+  unsigned* rerun_count;     // zeroed before the first pass
+  const unsigned* n_dev;     // second pass: number of trajectories, read on the device (null: KArgs::N)
+  int debug_rerun_mod;       // > 0: the strictd kernel lists every k-th trajectory as if a guard had failed (tests)
   double first_step, max_step, min_step;
   int has_first_step, has_max_step, has_min_step, static_sched;
   u64 max_steps;         // usize::MAX when Options.max_steps is None

@@ -65,24 +65,24 @@ template <int METHOD, int N>
 __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (&c)[MethodTraits<METHOD>::NC][N],
                                            double xold, double h) {
   if constexpr (METHOD == M_DOP853) {          // dop853.rs:659-670
-    const double s = ex::div(xi - xold, h), s1 = 1.0 - s;
+    const double s = ex::gdiv(xi - xold, h), s1 = 1.0 - s;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const double conpar = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, c[7][i], c[6][i]), c[5][i]), c[4][i]);
       yi[i] = IVPB_MA(s, IVPB_MA(s1, IVPB_MA(s, IVPB_MA(s1, conpar, c[3][i]), c[2][i]), c[1][i]), c[0][i]);
     }
   } else if constexpr (METHOD == M_DOPRI5) {   // dopri5.rs:467-478
-    const double th = ex::div(xi - xold, h), th1 = 1.0 - th;
+    const double th = ex::gdiv(xi - xold, h), th1 = 1.0 - th;
 #pragma unroll
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(th, IVPB_MA(th1, IVPB_MA(th, IVPB_MA(th1, c[4][i], c[3][i]), c[2][i]), c[1][i]), c[0][i]);
   } else if constexpr (METHOD == M_RK23) {     // rk23.rs:313-321
-    const double xc = ex::div(xi - xold, h), x2 = xc * xc, x3 = x2 * xc;
+    const double xc = ex::gdiv(xi - xold, h), x2 = xc * xc, x3 = x2 * xc;
 #pragma unroll
     for (int i = 0; i < N; ++i)
       yi[i] = IVPB_MA(h, IVPB_MA(c[3][i], x3, IVPB_MA(c[2][i], x2, c[1][i] * xc)), c[0][i]);
   } else if constexpr (METHOD == M_RADAU) {    // radau.rs:798-809
-    const double s = ex::div(xi - (xold + h), h);
+    const double s = ex::gdiv(xi - (xold + h), h);
     const double C1M1 = -0.8449489742783178, C2M1 = -0.3550510257216822;
 #pragma unroll
     for (int i = 0; i < N; ++i) yi[i] = c[0][i] + s * (c[1][i] + (s - C2M1) * (c[2][i] + (s - C1M1) * c[3][i]));
@@ -108,7 +108,7 @@ __device__ __forceinline__ void erk_interp(double xi, double* yi, const double (
       yi[i] = sum;
     }
   } else {                                      // rk4.rs:229-244 (cubic Hermite, cont = [y_old, k4 stage, f_new, y_new])
-    const double t = ex::div(xi - xold, h), t2 = t * t, t3 = t2 * t;
+    const double t = ex::gdiv(xi - xold, h), t2 = t * t, t3 = t2 * t;
     const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
     const double h01 = -2.0 * t3 + 3.0 * t2, h11 = t3 - t2;
 #pragma unroll
@@ -147,7 +147,23 @@ struct ThreadLayout {
     for (int i = 0; i < NL; ++i) acc += t[i];
     return acc;
   }
-  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) { Prob::ode(t, y, p, d); }
+  // IVPB_NOINLINE_ODE: ONE out-of-line copy of the right-hand side per kernel instead of one per stage (DOP853: 12-15
+  // sites).  The operands cross in local memory (2 n + p doubles per call, L1-resident); what it buys is code size: the
+  // strict CR3BP DOP853 kernel is 140 KB of SASS against a 32 KB instruction cache.
+  static __device__ __noinline__ void ode_call(double t, const double* y, const double* p, double* d) { Prob::ode(t, y, p, d); }
+  static __device__ __forceinline__ void ode(double t, const double* y, const double* p, double* d) {
+#ifdef IVPB_NOINLINE_ODE
+    if constexpr (N >= IVPB_NOINLINE_ODE) {
+      double yy[N], dd[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) yy[i] = y[i];
+      ode_call(t, yy, p, dd);
+#pragma unroll
+      for (int i = 0; i < N; ++i) d[i] = dd[i];
+    } else
+#endif
+    Prob::ode(t, y, p, d);
+  }
   static __device__ __forceinline__ void events(double t, const double* y, const double* p, double* g) { Prob::events(t, y, p, g); }
 };
 
@@ -245,19 +261,19 @@ struct WarpLayout {
 // min(|h|, 100|h|, h1, hmax) keeps the reference's extra |h| term, mod.rs:279)
 template <class Prob, int IORD, class L = ThreadLayout<Prob>>
 __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const double* y, const double* f0,
-                                            const double* p, double posneg, double hmax) {
+                                            const double* p, double posneg, double hmax, bool& gbad) {
   constexpr int N = L::NL;
   double qf[N], qy[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
     const ex::Recip rsk = ex::recip(sk);       // ex::div == `/` bit for bit (ivpb_exact.cuh), one reciprocal for both
-    qf[i] = L::valid(i) ? ex::div(f0[i], rsk) : 0.0;
-    qy[i] = L::valid(i) ? ex::div(y[i], rsk) : 0.0;
+    qf[i] = L::valid(i) ? ex::div(f0[i], rsk, gbad) : 0.0;
+    qy[i] = L::valid(i) ? ex::div(y[i], rsk, gbad) : 0.0;
   }
   // interleaved in the reference (dnf, dny in one loop); the two sums are independent
   const double dnf = L::sumsq(qf), dny = L::sumsq(qy);
-  double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : ex::sqrt(ex::div(dny, dnf)) * 0.01;
+  double hh = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : ex::sqrt(ex::div(dny, dnf, gbad), gbad) * 0.01;
   if (hh > fabs(hmax)) hh = fabs(hmax);
   hh = fabs(hh) * signum(posneg);
   double y1[N], f1[N];
@@ -267,12 +283,12 @@ __device__ __forceinline__ double hinit_dev(const KArgs& a, double x, const doub
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double sk = IVPB_MA(L::rtol(a, i), fabs(y[i]), L::atol(a, i));
-    qf[i] = L::valid(i) ? ex::div(f1[i] - f0[i], sk) : 0.0;
+    qf[i] = L::valid(i) ? ex::div(f1[i] - f0[i], sk, gbad) : 0.0;
   }
   double der2 = L::sumsq(qf);
-  der2 = ex::div(ex::sqrt(der2), fabs(hh));
-  const double der12 = fmax(fabs(der2), ex::sqrt(dnf));
-  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(ex::div(0.01, der12), 1.0 / (double)IORD);
+  der2 = ex::div(ex::sqrt(der2, gbad), fabs(hh), gbad);
+  const double der12 = fmax(fabs(der2), ex::sqrt(dnf, gbad));
+  const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(hh) * 1.0e-3) : ivpb_libm_pow(ex::div(0.01, der12, gbad), 1.0 / (double)IORD);
   const double hf = fmin(fmin(fmin(fabs(hh), 100.0 * fabs(hh)), h1), fabs(hmax));
   return fabs(hf) * signum(posneg);
 }
@@ -585,7 +601,9 @@ struct ErkTraj {
   static constexpr bool BATCH_HEAVY = false;     // see run_schedule
   // Block-synchronous trips (run_schedule) for the kernels whose step code is far larger than the 32 KB instruction cache
   // and fetch-bound: the strict build (two instructions per multiply-add) of the wide tableaux / larger systems.
-#ifdef IVPB_STRICT
+#if defined(IVPB_FORCE_BLOCK_SYNC)
+  static constexpr bool BLOCK_SYNC = !L::WARP && (IVPB_FORCE_BLOCK_SYNC != 0);      // A/B builds (tools/build_variant.sh)
+#elif defined(IVPB_STRICT)
   static constexpr bool BLOCK_SYNC = !L::WARP && (METHOD == M_DOP853 ? NG >= 3 : NG >= 5);
 #else
   static constexpr bool BLOCK_SYNC = false;
@@ -603,6 +621,7 @@ struct ErkTraj {
   Out so;
   static constexpr bool USER = (FEAT & K_USER) != 0;
   double ustate[USER ? Prob::NSTATE : 1];      // the user SolOut's own fields (Options.user_solout)
+  bool gbad;      // deferred-guard flag of this trajectory (ivpb_exact.cuh); only the strictd kernels ever raise it
 
   __device__ __forceinline__ void to_event_point(double tev, const double* yev) {
     x = tev;
@@ -624,6 +643,7 @@ struct ErkTraj {
   // The solver's callback slot (e.g. dop853.rs:246-268,596-624): DefaultSolOut, or the problem's own SolOut.
   // Returns 0 Continue, 1 Interrupt (status set, (x, y) at the point to report), 2 ModifiedSolution (k1 re-evaluated).
   __device__ __forceinline__ int callback(const KArgs& a, bool first, double xold, const double (&cont)[NC][N], double hstep) {
+    if (gbad) { status = ST_RERUN; return 1; }      // strictd kernels: abandon before emitting (ivpb_exact.cuh)
     if constexpr (USER) {
       int fl;
       if constexpr (L::WARP) fl = WarpHook<Prob, METHOD, L, Out>::run(a, idx, so, first, xold, x, y, p, ustate, cont, hstep, xold);
@@ -645,7 +665,7 @@ struct ErkTraj {
   __device__ __forceinline__ double at(const KArgs& a, int i) const { return L::atol(a, i); }
 
   __device__ __forceinline__ double hinit(const KArgs& a, double posneg, double hmax) {
-    return hinit_dev<Prob, MethodTraits<METHOD>::IORD, L>(a, x, y, k1, p, posneg, hmax);
+    return hinit_dev<Prob, MethodTraits<METHOD>::IORD, L>(a, x, y, k1, p, posneg, hmax, gbad);
   }
 
   __device__ __forceinline__ double hmax_of(const KArgs& a) const {
@@ -657,6 +677,7 @@ struct ErkTraj {
   // Everything the reference does before its main loop; returns true if the trajectory is already done.
   __device__ __forceinline__ bool init(const KArgs& a, i64 index) {
     idx = index;
+    gbad = false;
     x = a.t0;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = 0.0;
@@ -824,7 +845,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       IVPB_LINCOMB(e8, LIN_LEN[1], LIN_SLOT[1], D853_LIN_COEF[1], k, i)
 #ifdef IVPB_STRICT
       const ex::Recip rsk = ex::recip(sk);               // dop853.rs:412,423: two correctly rounded quotients, one reciprocal
-      const double q2 = ex::div(erri, rsk), q1 = ex::div(e8, rsk);
+      const double q2 = ex::div(erri, rsk, gbad), q1 = ex::div(e8, rsk, gbad);
 #else
       const double rsk = fm::rcp(sk);                      // one reciprocal shared by both norms
       const double q2 = erri * rsk, q1 = e8 * rsk;
@@ -836,15 +857,15 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     double deno = IVPB_MA(0.01, err2, err);
     if (deno <= 0.0) deno = 1.0;
 #ifdef IVPB_STRICT
-    err = fabs(h) * err * ex::sqrt(ex::div(1.0, (double)NG * deno));
+    err = fabs(h) * err * ex::sqrt(ex::div(1.0, (double)NG * deno, gbad), gbad);
     const double fac11 = ivpb_libm_pow(err, 0.125);                     // expo1 = 1/8 - beta*0.2, beta = 0
     // facold^beta == 1 exactly (beta = 0), so fac = fac11 (dop853.rs:434)
-    const double fmin1 = fmin(facc1, ex::div(fac11, safe));
+    const double fmin1 = fmin(facc1, ex::div(fac11, safe, gbad));
     const double fac = fmax(facc2, fmin1);
-    double hnew = ex::div(h, fac);
+    double hnew = ex::div(h, fac, gbad);
     // dop853.rs:645: the rejected step is h / min(facc1, fac11 / safe).  Same quotient whenever the lower clamp is idle
     // (always after a rejection: err > 1 => fac11 >= 1 > facc2 * safe), so the second division is almost never executed.
-    const double hrej = (fac == fmin1) ? hnew : ex::div(h, fmin1);
+    const double hrej = (fac == fmin1) ? hnew : ex::div(h, fmin1, gbad);
 #else
     // Same controller written with the reciprocal step factor 1/fac = safe * err^(-1/8), which needs
     // multiplications only (see ivpb_fastmath.cuh): hnew = h * clamp(safe/fac11, 1/facc1, 1/facc2).
@@ -865,7 +886,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
 #pragma unroll
         for (int i = 0; i < N; ++i) { sd1[i] = k[3][i] - k[2][i]; sd2[i] = k[4][i] - y1[i]; }
         const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
-        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden));
+        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden, gbad), gbad);
         if (hlamb > 6.1) {
           nonstiff = 0; iasti += 1;
           if (iasti == 15) { status = ST_STIFF; return true; }
@@ -998,7 +1019,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       k[3][i] = acc * h;
 #ifdef IVPB_STRICT
       const double sk = at(a, i) + rt(a, i) * fmax(fabs(y[i]), fabs(y1[i]));
-      const double q = ex::div(k[3][i], sk);
+      const double q = ex::div(k[3][i], sk, gbad);
 #else
       const double sk = fma(rt(a, i), fm::maxsel(fabs(y[i]), fabs(y1[i])), at(a, i));
       const double q = k[3][i] * fm::rcp(sk);
@@ -1007,11 +1028,11 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     }
     double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = ex::sqrt(ex::div(err, (double)NG));
+    err = ex::sqrt(ex::div(err, (double)NG, gbad), gbad);
     const double fac11 = ivpb_libm_pow(err, expo1);
-    double fac = ex::div(fac11, ivpb_libm_pow(facold, beta));
-    fac = fmax(facc2, fmin(facc1, ex::div(fac, safe)));
-    double hnew = ex::div(h, fac);
+    double fac = ex::div(fac11, ivpb_libm_pow(facold, beta), gbad);
+    fac = fmax(facc2, fmin(facc1, ex::div(fac, safe, gbad)));
+    double hnew = ex::div(h, fac, gbad);
     const bool accept = err <= 1.0;
 #else
     // Same PI controller in log2 space: err = sqrt(e2), so log2(err) = log2(e2)/2 needs no square root, and
@@ -1042,7 +1063,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
           sd2[i] = y1[i] - ysti;
         }
         const double stnum = L::sumsq(sd1), stden = L::sumsq(sd2);
-        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden));
+        if (stden > 0.0) hlamb = fabs(h) * ex::sqrt(ex::div(stnum, stden, gbad), gbad);
         if (hlamb > 3.25) {
           nonstiff = 0; iasti += 1;
           if (iasti == 15) { status = ST_STIFF; return true; }
@@ -1074,7 +1095,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       if (reject) { hnew = posneg * fmin(fabs(hnew), fabs(h)); reject = false; }
     } else {
 #ifdef IVPB_STRICT
-      hnew = ex::div(h, fmin(facc1, ex::div(fac11, safe)));
+      hnew = ex::div(h, fmin(facc1, ex::div(fac11, safe, gbad)), gbad);
 #else
       hnew = h * fm::maxsel(safe * fm::exp2_fast(-expo1 * lerr), 0.2);
 #endif
@@ -1112,7 +1133,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
       const double ye = h * IVPB_MA(e4, k4[i], IVPB_MA(e3, k3[i], IVPB_MA(e2, k2[i], e1 * k1[i])));
       const double tol = IVPB_MA(rt(a, i), fmax(fabs(yt[i]), fabs(y[i])), at(a, i));
 #ifdef IVPB_STRICT
-      const double q = ex::div(ye, tol);
+      const double q = ex::div(ye, tol, gbad);
 #else
       const double q = ye * fm::rcp(tol);
 #endif
@@ -1120,7 +1141,7 @@ __device__ __forceinline__ bool ErkTraj<Prob, METHOD, FEAT, L>::step(const KArgs
     }
     double err = L::sumsq(qe);
 #ifdef IVPB_STRICT
-    err = ex::sqrt(ex::div(err, (double)NG));
+    err = ex::sqrt(ex::div(err, (double)NG, gbad), gbad);
     const double sfac = safe * ivpb_libm_pow(err, expo);                 // 0.9 * err^(-1/3), rk23.rs:289,303
     const bool accept = err <= 1.0;
 #else
@@ -1276,6 +1297,22 @@ __device__ __forceinline__ void chunk_signal_warp(const KArgs& a, i64 idx) {
 // PIPE = false compiles the arrival / completion flags out altogether: the device-resident entry point
 // (ivpb_solve_batch_device) never uses them, and even the uniform early-outs cost the north-star kernel 3 % (15.0 -> 15.46 ms
 // per 2^20 trajectories, measured A/B on one box).
+// A trajectory has ended: write its results -- or, in a strictd kernel, put it on the re-run list if one of its divisions /
+// square roots left the fast-path range (ivpb_exact.cuh).  Returns true when the results were written.
+template <class Traj>
+__device__ __forceinline__ bool retire(const KArgs& a, Traj& T) {
+#ifdef IVPB_DEFER_GUARDS
+  // a.debug_rerun_mod > 0 (IVPB_DEBUG_RERUN=k): hand every k-th trajectory to the second pass, to test it
+  if (T.status == ST_RERUN || T.gbad || (a.debug_rerun_mod > 0 && T.idx % a.debug_rerun_mod == 0)) {
+    const unsigned k = atomicAdd(a.rerun_count, 1u);
+    a.rerun_list[k] = (unsigned)T.idx;
+    return false;
+  }
+#endif
+  T.finish(a);
+  return true;
+}
+
 template <class Traj, bool PIPE = true>
 __device__ __forceinline__ void run_schedule(const KArgs& a) {
   Traj T;
@@ -1283,6 +1320,14 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
   const int lane = threadIdx.x & 31;
   constexpr bool bsync = Traj::BLOCK_SYNC;
   bool active = false, exhausted = false;
+  // Second pass of a strictd launch (guarded strict build only): the trajectories are the ones on the first pass's re-run
+  // list (KArgs::n_dev, perm).  Every other build reads N straight from the constant bank -- a register for it costs the
+  // north-star kernel, which sits at its 72-register cap, 17 % (15.0 -> 17.5 ms).
+#if defined(IVPB_STRICT) && !defined(IVPB_DEFER_GUARDS)
+  const i64 NQ = a.n_dev ? (i64)*a.n_dev : a.N;
+#else
+#define NQ a.N
+#endif
   for (;;) {
     // ---- refill: lanes without a trajectory pull the next index from the global queue (one atomic per warp).
     // The static schedule is the same loop with a "queue" that hands every thread exactly its own index, so
@@ -1299,14 +1344,14 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         if (lane == leader) base = atomicAdd(a.queue, (u64)__popc(need));
         base = __shfl_sync(FULL, base, leader);
         idx = (i64)base + __popc(need & ((1u << lane) - 1u));
-        if ((i64)base + __popc(need) >= a.N) exhausted = true;
+        if ((i64)base + __popc(need) >= NQ) exhausted = true;
       }
       bool fin0 = false;
-      if (!active && idx < a.N) {
+      if (!active && idx < NQ) {
         active = true;
         const i64 tidx = a.perm ? (i64)a.perm[idx] : idx;
         if constexpr (PIPE) wait_input(a, tidx);
-        if (T.init(a, tidx)) { T.finish(a); active = false; fin0 = true; }
+        if (T.init(a, tidx)) { fin0 = retire(a, T); active = false; }
       }
       if constexpr (PIPE) chunk_signal(a, fin0, T.idx);
     }
@@ -1337,10 +1382,17 @@ __device__ __forceinline__ void run_schedule(const KArgs& a) {
         run = active && (!hv || nh * IVPB_BATCH_DEN >= na * IVPB_BATCH_NUM);
       }
       if (run) done = T.step(a);
+#ifdef IVPB_DEFER_GUARDS
+      if (run && T.gbad) done = true;      // abandon at once: garbage must not keep a trajectory stepping
+#endif
     } while (!(bsync ? (__syncthreads_or(done ? 1 : 0) != 0) : (__any_sync(FULL, done) != 0)));
-    if (done) { T.finish(a); active = false; }
-    if constexpr (PIPE) chunk_signal(a, done, T.idx);
+    bool fin = false;
+    if (done) { fin = retire(a, T); active = false; }
+    if constexpr (PIPE) chunk_signal(a, fin, T.idx);
   }
+#ifdef NQ
+#undef NQ
+#endif
 }
 
 template <class Prob, int METHOD, int FEAT, bool PIPE = true>

@@ -889,7 +889,8 @@ struct BdfWarpTraj {
     if (a.has_first_step) {
       h_abs = fabs(a.first_step);
     } else {
-      double guess = hinit_dev<Prob, 1, L>(a, x, y, f0, p, direction, hmax);
+      bool gunused = false;      // the warp kernels keep the guarded divisions (ivpb_exact.cuh)
+      double guess = hinit_dev<Prob, 1, L>(a, x, y, f0, p, direction, hmax, gunused);
       const double max_h = fabs(a.tf - x);
       if (fabs(guess) > max_h) guess = max_h * direction;
       h_abs = fabs(guess);

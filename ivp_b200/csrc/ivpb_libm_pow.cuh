@@ -23,6 +23,13 @@
 
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 #define IVPB_LIBM_TABLE static __device__ const
+// The polynomial / reduction constants (compile-time indices only) come from the constant bank: as `__device__ const` the
+// compiler folds them into immediates, and every 64-bit immediate costs two moves per use (IVPB_PLAIN_POW_HEAD: A/B switch)
+#ifdef IVPB_PLAIN_POW_HEAD
+#define IVPB_LIBM_HEAD static __device__ const
+#else
+#define IVPB_LIBM_HEAD static __constant__
+#endif
 #define IVPB_LIBM_FN __device__ __forceinline__
 #define IVPB_LIBM_FMA(a, b, c) fma((a), (b), (c))
 #define IVPB_LIBM_MUL(a, b) __dmul_rn((a), (b))
@@ -34,6 +41,7 @@
 #include <cmath>
 #include <cstring>
 #define IVPB_LIBM_TABLE static const
+#define IVPB_LIBM_HEAD static const
 #define IVPB_LIBM_FN static inline
 #define IVPB_LIBM_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #define IVPB_LIBM_MUL(a, b) ((a) * (b))

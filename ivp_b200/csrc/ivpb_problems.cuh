@@ -136,13 +136,25 @@ struct PCr3bp : ProblemDefaults<6, 1, 0> {      // reference examples/cr3bp.rs:2
     d[0] = s[3]; d[1] = s[4]; d[2] = s[5];
 #ifdef IVPB_STRICT
     // the reference's 2 sqrt + 6 divisions, correctly rounded (ivpb_exact.cuh): the six quotients have two distinct
-    // denominators, so two refined reciprocals serve all of them
-    const double r1 = ex::sqrt((x + mu) * (x + mu) + y * y + z * z);
-    const double r2 = ex::sqrt((x - 1.0 + mu) * (x - 1.0 + mu) + y * y + z * z);
-    const ex::Recip r13 = ex::recip((r1 * r1) * r1), r23 = ex::recip((r2 * r2) * r2);   // powi(3)
-    d[3] = x + 2.0 * s[4] - ex::div((1.0 - mu) * (x + mu), r13) - ex::div(mu * (x - 1.0 + mu), r23);
-    d[4] = y - 2.0 * s[3] - ex::div((1.0 - mu) * y, r13) - ex::div(mu * y, r23);
-    d[5] = ex::div(-(1.0 - mu) * z, r13) - ex::div(mu * z, r23);
+    // denominators, so two refined reciprocals serve all of them.  All eight run branch-free with ONE test of their
+    // guards at the end; the guarded forms repeat the group if an operand left the fast-path range (never on an orbit).
+    bool ok = true;
+    {
+      const double r1 = ex::sqrt_fast((x + mu) * (x + mu) + y * y + z * z, ok);
+      const double r2 = ex::sqrt_fast((x - 1.0 + mu) * (x - 1.0 + mu) + y * y + z * z, ok);
+      const ex::Recip r13 = ex::recip((r1 * r1) * r1), r23 = ex::recip((r2 * r2) * r2);   // powi(3)
+      d[3] = x + 2.0 * s[4] - ex::div_fast((1.0 - mu) * (x + mu), r13, ok) - ex::div_fast(mu * (x - 1.0 + mu), r23, ok);
+      d[4] = y - 2.0 * s[3] - ex::div_fast((1.0 - mu) * y, r13, ok) - ex::div_fast(mu * y, r23, ok);
+      d[5] = ex::div_fast(-(1.0 - mu) * z, r13, ok) - ex::div_fast(mu * z, r23, ok);
+    }
+    if (!ok) {
+      const double r1 = ex::sqrt((x + mu) * (x + mu) + y * y + z * z);
+      const double r2 = ex::sqrt((x - 1.0 + mu) * (x - 1.0 + mu) + y * y + z * z);
+      const ex::Recip r13 = ex::recip((r1 * r1) * r1), r23 = ex::recip((r2 * r2) * r2);
+      d[3] = x + 2.0 * s[4] - ex::div((1.0 - mu) * (x + mu), r13) - ex::div(mu * (x - 1.0 + mu), r23);
+      d[4] = y - 2.0 * s[3] - ex::div((1.0 - mu) * y, r13) - ex::div(mu * y, r23);
+      d[5] = ex::div(-(1.0 - mu) * z, r13) - ex::div(mu * z, r23);
+    }
 #else
     // fast build: 1/r^3 = rsqrt(r^2)^3 -- two slow-path-free reciprocal square roots (ivpb_fastmath.cuh)
     // replace the reference's 2 sqrt + 6 divisions (a few ulp apart, like every other fast-mode operation)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -30,13 +31,16 @@ typedef const void* (*lookup_impl_fn)(int method, int feat, int* block, int* sme
 #define DECL(tag)                                                                  \
   extern "C" const void* ivpb_lookup_##tag(int, int, ivpb_pinfo*);                 \
   extern "C" const void* ivpb_lookup_strict_##tag(int, int, ivpb_pinfo*);          \
+  extern "C" const void* ivpb_lookup_strictd_##tag(int, int, ivpb_pinfo*);         \
+  extern "C" const void* ivpb_lookup_impl_strictd_##tag(int, int, int*, int*, int*); \
   extern "C" const void* ivpb_lookup_impl_##tag(int, int, int*, int*, int*);       \
   extern "C" const void* ivpb_lookup_impl_strict_##tag(int, int, int*, int*, int*);
 DECL(decay) DECL(vdp_eps) DECL(vdp_mu) DECL(lorenz) DECL(cr3bp) DECL(ball) DECL(robertson) DECL(sho)
 DECL(zero3) DECL(exp2) DECL(rational) DECL(cannon) DECL(linear100) DECL(medakzo64) DECL(robertson_dae) DECL(mass_linear3) DECL(ball_bounce)
 #undef DECL
-#define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag}
-static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][2] = {
+// [0] FMA build, [1] strict build, [2] strict build with deferred guards (first pass of a strict solve, ivpb_exact.cuh)
+#define ROW(tag) {ivpb_lookup_##tag, ivpb_lookup_strict_##tag, ivpb_lookup_strictd_##tag}
+static const lookup_fn BUILTIN[IVPB_P_BUILTIN_COUNT][3] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
     ROW(robertson_dae), ROW(mass_linear3), ROW(ball_bounce)};
@@ -49,8 +53,8 @@ extern "C" cudaError_t ivpb_launch_dense_eval(int method, int n, int n_cont, int
 extern "C" cudaError_t ivpb_launch_dense_span(int cap, const int* seg_n, const double* seg_x, long long first, long long count,
                                               double* t_start, double* t_end, int* n_out, cudaStream_t stream);
 // RADAU / BDF kernels (ivpb_inst_implicit.cu)
-#define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag}
-static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][2] = {
+#define ROW(tag) {ivpb_lookup_impl_##tag, ivpb_lookup_impl_strict_##tag, ivpb_lookup_impl_strictd_##tag}
+static const lookup_impl_fn BUILTIN_IMPL[IVPB_P_BUILTIN_COUNT][3] = {
     ROW(decay), ROW(vdp_eps), ROW(vdp_mu), ROW(lorenz), ROW(cr3bp), ROW(ball),
     ROW(robertson), ROW(sho), ROW(zero3), ROW(exp2), ROW(rational), ROW(cannon), ROW(linear100), ROW(medakzo64),
     ROW(robertson_dae), ROW(mass_linear3), ROW(ball_bounce)};
@@ -96,7 +100,7 @@ struct Device {
   cudaEvent_t ev_last = nullptr;    // end of the most recent solve enqueued on this device: the per-device queue counter,
                                     // t_eval / tolerance staging and sort buffers are shared, so solves on one context are
                                     // serialised on the device even when the caller hands in different streams
-  Buf y0, params, t_eval, tol_ext, sparsity, scratch, out[OUT_FIELDS];
+  Buf y0, params, t_eval, tol_ext, sparsity, scratch, rerun, out[OUT_FIELDS];
   Buf sort_keys, sort_vals, sort_tmp, sort_minmax;   // locality order of the shard (locality_order)
   Buf q_traj, q_ts, q_y, q_ok;      // ivpb_dense_eval query staging (grow-only)
   Buf dense_nseg, dense_segx, dense_segc;   // the retained dense log of this device's shard (never shared with dev.out[])
@@ -667,11 +671,14 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     return 0;
   }
 
+  // flavour: 0 FMA build, 1 strict build, 2 strict build with deferred guards.  `probe`: only report whether the kernel exists.
+  auto launch_flavour = [&](int flavour, KArgs& a, bool probe) -> int {
   const void* kern = nullptr;
   int kblock = block, ksmem = 0, kunits = 0;
   if (o->method == IVPB_RADAU || o->method == IVPB_BDF) {
-    kern = BUILTIN_IMPL[problem][strict](o->method, feat, &kblock, &ksmem, &kunits);
-    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: the per-warp matrices of this state size do not fit shared memory");
+    kern = BUILTIN_IMPL[problem][flavour](o->method, feat, &kblock, &ksmem, &kunits);
+    if (probe) return kern ? 0 : 1;
+    if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "implicit methods: the per-warp vectors of this state size do not fit shared memory");
     if (ksmem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksmem));
   } else {
     ivpb_pinfo kinfo;
@@ -679,7 +686,8 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
     // no arrival / completion flags in this launch (device-resident entry point, or a host-buffer solve too small to
     // pipeline): take the twin compiled without them (K_NOPIPE, ivpb_kernels.cuh)
     const int nopipe = (a.chunk_size <= 0 && a.in_chunk <= 0 && !(feat & 4)) ? 0x100 : 0;
-    kern = BUILTIN[problem][strict](o->method, feat | nopipe, &kinfo);
+    kern = BUILTIN[problem][flavour](o->method, feat | nopipe, &kinfo);
+    if (probe) return kern ? 0 : 1;
     if (!kern) return fail(ctx, IVPB_ERR_CONFIG, "no kernel for this problem/method/feature combination");
     kblock = kinfo.block;
     if (warp_mode) {
@@ -707,6 +715,26 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kblock), kargs, ksmem, stream));
   ctx->launches += 1;
   return 0;
+  };
+  // A strict solve takes two launches when the problem has a `strictd` kernel (thread-per-trajectory kernels of the
+  // built-in problems, ivpb_exact.cuh): the first runs every division / square root on its fast path and lists the
+  // trajectories in which a guard failed; the second -- the guarded build, one persistent grid that reads the count on
+  // the device and normally finds it zero -- integrates those from the start.  No host synchronisation in between.
+  static const bool no_defer = std::getenv("IVPB_NO_DEFER") != nullptr;      // A/B measurements
+  if (strict == 1 && !no_defer && N < ((int64_t)1 << 32) && launch_flavour(2, a, true) == 0) {
+    CK(dev.rerun.ensure(sizeof(unsigned) * ((size_t)N + 1)));
+    unsigned* count = (unsigned*)dev.rerun.p;
+    CK(cudaMemsetAsync(count, 0, sizeof(unsigned), stream));
+    KArgs a1 = a;
+    a1.rerun_count = count; a1.rerun_list = count + 1;
+    if (const char* dbg = std::getenv("IVPB_DEBUG_RERUN")) a1.debug_rerun_mod = std::atoi(dbg);
+    if (int rc = launch_flavour(2, a1, false)) return rc;
+    KArgs a2 = a;
+    a2.perm = count + 1; a2.n_dev = count; a2.static_sched = 0;
+    CK(cudaMemsetAsync(dev.queue + slot, 0, sizeof(u64), stream));
+    return launch_flavour(1, a2, false);
+  }
+  return launch_flavour(strict, a, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -944,7 +972,7 @@ void ivpb_destroy(ivpb_ctx* ctx) {
   for (auto& d : ctx->devs) {
     cudaSetDevice(d.id);
     if (d.stream) cudaStreamSynchronize(d.stream);
-    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.sparsity.release(); d.scratch.release();
+    d.y0.release(); d.params.release(); d.t_eval.release(); d.tol_ext.release(); d.sparsity.release(); d.scratch.release(); d.rerun.release();
     d.q_traj.release(); d.q_ts.release(); d.q_y.release(); d.q_ok.release();
     d.sort_keys.release(); d.sort_vals.release(); d.sort_tmp.release(); d.sort_minmax.release();
     d.dense_nseg.release(); d.dense_segx.release(); d.dense_segc.release();
@@ -1408,6 +1436,17 @@ int ivpb_measure_fp64_peak(ivpb_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+// Debug hook (not part of include/ivpb.h): how many trajectories the last strict solve on device 0 handed to the guarded
+// second pass (ivpb_exact.cuh, "deferred guards").  Synchronises the device.  -1: no two-pass solve has run.
+extern "C" long long ivpb_debug_last_reruns(ivpb_ctx* ctx) {
+  if (!ctx || ctx->devs.empty() || !ctx->devs[0].rerun.p) return -1;
+  unsigned n = 0;
+  cudaSetDevice(ctx->devs[0].id);
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpy(&n, ctx->devs[0].rerun.p, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return (long long)n;
+}
 
 // Debug hook (not part of include/ivpb.h): the runtime's column grouping of a jac_sparsity structure, so the CPU suite can
 // compare it with the reference's greedy rule without a GPU.  Returns the number of groups.

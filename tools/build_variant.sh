@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../ivp_b200/csrc"
 NAME=$1; EXTRA=$2; shift 2
 MAIN=../../build/ivpb; VAR=../../build/var_$NAME
 mkdir -p $VAR
-NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177 $EXTRA"
+NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177 -Xfatbin -compress-all $EXTRA"
 struct_of() { grep -o "$1:[A-Za-z0-9]*" Makefile | head -1 | cut -d: -f2; }
 REPL=""
 for o in "$@"; do
