@@ -768,6 +768,9 @@ struct PilotTol { double rtol[ivpb::MAX_N], atol[ivpb::MAX_N]; };
 
 // res[0] status mismatches, res[1] accepted / rejected step-count mismatches, res[2] trajectories outside
 // max(10 rtol |y|, 10 atol) (final state, elementwise; final time likewise with the first component's tolerances)
+// The sample has to stay inside HALF the north-star tolerance max(10 rtol |y|, 10 atol): the margin is for the trajectories
+// the pilot does not see (VdP DOPRI5 at 1e-6: all 8192 sampled trajectories inside the full tolerance, 2 of 32768 outside).
+#define PILOT_TOL_FACTOR 5.0
 __global__ void pilot_compare_kernel(int S, int n, PilotTol tol, const int* st_a, const unsigned* cn_a, const double* tf_a,
                                      const double* yf_a, const int* st_b, const unsigned* cn_b, const double* tf_b,
                                      const double* yf_b, unsigned* res) {
@@ -779,9 +782,9 @@ __global__ void pilot_compare_kernel(int S, int n, PilotTol tol, const int* st_a
   for (int c = 0; c < n; ++c) {
     const int tc = c < ivpb::MAX_N ? c : 0;
     const double ref = yf_a[(long long)k * n + c], d = fabs(yf_b[(long long)k * n + c] - ref);
-    if (!(d <= fmax(10.0 * tol.rtol[tc] * fabs(ref), 10.0 * tol.atol[tc]))) bad = true;
+    if (!(d <= fmax(PILOT_TOL_FACTOR * tol.rtol[tc] * fabs(ref), PILOT_TOL_FACTOR * tol.atol[tc]))) bad = true;
   }
-  if (!(fabs(tf_b[k] - tf_a[k]) <= fmax(10.0 * tol.rtol[0] * fabs(tf_a[k]), 10.0 * tol.atol[0]))) bad = true;
+  if (!(fabs(tf_b[k] - tf_a[k]) <= fmax(PILOT_TOL_FACTOR * tol.rtol[0] * fabs(tf_a[k]), PILOT_TOL_FACTOR * tol.atol[0]))) bad = true;
   if (bad) atomicAdd(res + 2, 1u);
 }
 
