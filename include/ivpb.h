@@ -247,8 +247,8 @@ uint64_t ivpb_launch_count(const ivpb_ctx* ctx);
  * 1 the method's default (RADAU / BDF: strict), 2 a cached verdict of the parity pilot, 3 the parity pilot just ran.
  * The pilot (explicit methods without either flag): the first solve of a configuration integrates `sample` evenly
  * strided trajectories of the ensemble with BOTH builds and picks the FMA build only if all of them end with the same
- * status and inside max(10 rtol |y|, 10 atol) of the strict result, and >= 99 % with the same accepted / rejected step
- * counts (ivpb_runtime.cu resolve_fp). */
+ * status and inside HALF of max(10 rtol |y|, 10 atol) of the strict result (the margin is for the trajectories the pilot
+ * does not see), and >= 99 % with the same accepted / rejected step counts (ivpb_runtime.cu resolve_fp). */
 int ivpb_last_fp_mode(const ivpb_ctx* ctx, int32_t info[6]);
 
 /* FP64 FMA-pipe peak of the first device measured with a dependent-chain DFMA microbenchmark
