@@ -234,6 +234,8 @@ __device__ __forceinline__ void swap_rt(double (&b)[N], int k, int m) {
 }
 
 // ---- SOL: reference src/matrix/linear.rs:55-96 ---------------------------------------------------
+// (NZ divisions: a right-hand side is exactly zero only once Newton has converged to the last bit -- Robertson BDF's tiny first
+// steps do that, and those trajectories take the guarded second pass; accepting zeros here costs VdP mu=1000 BDF 10 %)
 template <int N, class Mat>
 __device__ __forceinline__ void lin_solve(const Mat& A, double (&b)[N], const int (&ip)[N], const double (&dy)[N], bool& gbad) {
   if constexpr (N == 1) {

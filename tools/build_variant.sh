@@ -13,6 +13,8 @@ REPL=""
 for o in "$@"; do
   (
   case $o in
+    inst_strictd_*) t=${o#inst_strictd_}; $NV -fmad=false -DIVPB_STRICT -DIVPB_DEFER_GUARDS -DIVPB_PROBLEM=$(struct_of $t) -DIVPB_TAG=$t -c ivpb_inst.cu -o $VAR/$o.o ;;
+    impl_strictd_*) t=${o#impl_strictd_}; $NV -fmad=false -DIVPB_STRICT -DIVPB_DEFER_GUARDS -DIVPB_PROBLEM=$(struct_of $t) -DIVPB_TAG=$t -c ivpb_inst_implicit.cu -o $VAR/$o.o ;;
     inst_strict_*) t=${o#inst_strict_}; $NV -fmad=false -DIVPB_STRICT -DIVPB_PROBLEM=$(struct_of $t) -DIVPB_TAG=$t -c ivpb_inst.cu -o $VAR/$o.o ;;
     inst_*) t=${o#inst_}; $NV -DIVPB_PROBLEM=$(struct_of $t) -DIVPB_TAG=$t -c ivpb_inst.cu -o $VAR/$o.o ;;
     impl_strict_*) t=${o#impl_strict_}; $NV -fmad=false -DIVPB_STRICT -DIVPB_PROBLEM=$(struct_of $t) -DIVPB_TAG=$t -c ivpb_inst_implicit.cu -o $VAR/$o.o ;;
