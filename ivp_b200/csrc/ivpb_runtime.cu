@@ -698,6 +698,16 @@ static int launch_shard(ivpb_ctx* ctx, Device& dev, int problem, const ProblemIn
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kblock, ksmem));
   if (occ < 1) occ = 1;
+  static const int occ_cap = std::getenv("IVPB_GRID_OCC") ? std::atoi(std::getenv("IVPB_GRID_OCC")) : 0;      // A/B measurements
+  if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
+  // Small shards (strong scaling): when the full grid holds a thread for every trajectory the queue has nothing to refill
+  // and every warp runs as long as its slowest lane.  Two resident blocks fewer per SM give each thread >= 1.35
+  // trajectories, so refill evens the step counts out again.  Measured on the north star at 131072 trajectories (one of
+  // eight shards of the 2^20 ensemble): 7 / 6 / 5 / 4 / 3 blocks per SM -> 2.036 / 2.078 / 1.976 / 2.136 / 2.369 ms;
+  // at 262144 and above the full grid wins (4.12 vs 4.19 ms, 7.47 vs 7.72 ms).  Only the kernels that keep >= 7 blocks.
+  if (occ_cap == 0 && occ >= 7 && !a.static_sched && !warp_mode && kunits == 0 && N <= (int64_t)dev.sms * occ * kblock &&
+      (double)N >= 1.35 * (double)((int64_t)dev.sms * (occ - 2) * kblock))
+    occ -= 2;
   int64_t grid = (int64_t)dev.sms * occ;
   const bool impl_warp = kunits < 0;
   if (impl_warp) kunits = -kunits;

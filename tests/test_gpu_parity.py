@@ -316,6 +316,30 @@ def test_full_size_properties():
     assert np.all(np.abs(g.y_final[:, 0]) < 2.1) and np.all(np.abs(g.y_final[:, 1]) < 2.8)
 
 
+def test_full_size_random_subset_against_oracle(oracle):
+    """BASELINE full size (2^20 VdP trajectories, DOP853, rtol = atol = 1e-8, the default build the bench times): a seeded
+    random 65536-subset of the FULL-SIZE run -- rows produced by the work-queue schedule of the big launch, not a small
+    launch of their own -- compared with the oracle: status bit-exact, every value inside max(10 rtol |y|, 10 atol),
+    accepted / rejected / attempted step counts equal for >= 99 % (north_star), nfev equal wherever the counts are."""
+    N, S = 1 << 20, 1 << 16
+    prob, y0, par, t0, tf = synth.ensemble("vdp", N)
+    opts = Options(method=Method.DOP853, rtol=1e-8, atol=1e-8)
+    g = ib.solve_ivp_batch(prob, t0, tf, y0, par, opts)
+    rows = np.sort(np.random.default_rng(20261019).choice(N, S, replace=False))
+    o = oracle.solve_batch(PROBLEMS[prob], t0, tf, np.ascontiguousarray(y0[rows]), np.ascontiguousarray(par[rows]), opts,
+                           nthreads=oracle.hardware_threads())
+    assert np.array_equal(g.status[rows], o.status)
+    assert np.array_equal(g.t_final[rows], o.t_final)
+    assert np.all(close(g.y_final[rows], o.y_final, 1e-8, 1e-8))
+    same = (g.naccpt[rows] == o.naccpt) & (g.nrejct[rows] == o.nrejct) & (g.nstep[rows] == o.nstep)
+    assert same.mean() >= 0.99, f"step-count parity {same.mean():.5f} on the full-size subset"
+    assert np.array_equal(g.nfev[rows][same], o.nfev[same])
+    # the strict build of the same full-size launch is bit-identical on a smaller subset (it runs at half the speed)
+    gs = ib.solve_ivp_batch(prob, t0, tf, y0, par, Options(method=Method.DOP853, rtol=1e-8, atol=1e-8, flags=IVPB_FLAG_STRICT_FP))
+    assert np.array_equal(gs.y_final[rows], o.y_final) and np.array_equal(gs.counters[rows], o.counters)
+    assert np.array_equal(gs.h_next[rows], o.h_next)
+
+
 def test_fastmath_helpers_accuracy():
     """ivpb_fastmath.cuh (fast-mode controller arithmetic): a few ulp inside the range, exact fallbacks and
     controller-safe limits outside it."""
