@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, session 4: BDF / RADAU after the decision-only pow shortcut, the exact-convergence exit, the triangular change_d
+cd "$GRAFT_REPO_ROOT"
+O=gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -x -k "stiff or implicit or golden or hook or mass or medakzo or vdp_eps or dense_output or locality or nvrtc" > $O/r2z3_pytest.log 2>&1; tail -3 $O/r2z3_pytest.log
+t() { tag=$1; shift; timeout 200 "$@" > $O/r2z3_$tag.json 2> $O/r2z3_$tag.err; rc=$?
+  python -c "
+import json;d=json.load(open('$O/r2z3_$tag.json'));c=d.get('cpu_baseline') or {}
+fp=d['config']['fp']
+print('$tag', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'parity', c.get('step_count_parity_on_sample'), 'bits', c.get('bit_identical_y_final_on_sample'), 'reruns', fp.get('second_pass_trajectories') if isinstance(fp,dict) else None)" 2>/dev/null || echo "$tag rc=$rc $(tail -c 300 $O/r2z3_$tag.err | tr '\n' ' ')"; }
+for wl in vdpstiff_bdf robertson_bdf vdpstiff_radau robertson_radau robertson_dae_radau; do t $wl python bench.py --workload $wl --steps 5 --cpu-sample 4096; done
