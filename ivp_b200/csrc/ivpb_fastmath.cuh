@@ -76,6 +76,16 @@ __device__ __forceinline__ double rcp_nc(double x) {
   return fma(r, fma(e, e, e), r);
 }
 
+// Polynomial coefficients live in the constant bank: a literal double costs two UMOVs (one issue slot per 32-bit half) on
+// sm_100a, a constant-bank entry one LDCU.64 -- or half of an LDCU.128 -- and the DOPRI5 / RK23 kernels are issue-bound
+// (Lorenz DOPRI5 hot loop: 682 instructions, 304 of them on the fp64 pipe, 95 UMOVs before this change).
+static __constant__ double LOG2_C[12] = {0.12545174268599682, 0.1373995277037108, 0.15186263588304877, 0.16972882833987804,
+                                         0.19235933878519512, 0.22195308321368667, 0.2623081892525388, 0.3205988979753252,
+                                         0.4121985831111324, 0.5770780163555853, 0.9617966939259756, 2.8853900817779268};
+static __constant__ double EXP2_C[14] = {1.3691488853904128e-12, 2.5678435993488206e-11, 4.4455382718708116e-10,
+                                         7.054911620801123e-09, 1.01780860092397e-07, 1.321548679014431e-06,
+                                         1.5252733804059841e-05, 0.0001540353039338161, 0.0013333558146428443,
+                                         0.009618129107628477, 0.05550410866482158, 0.24022650695910072, 0.6931471805599453, 1.0};
 static __device__ __noinline__ double log2_slow(double x) { return ::log2(x); }
 static __device__ __noinline__ double exp2_slow(double x) { return ::exp2(x); }
 
@@ -91,18 +101,9 @@ __device__ __forceinline__ double log2_fast(double x) {
   double m = __hiloint2double(hi, lo);
   if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
   const double s = (m - 1.0) * rcp_nc(m + 1.0), s2 = s * s;
-  double p = 0.12545174268599682;
-  p = fma(p, s2, 0.1373995277037108);
-  p = fma(p, s2, 0.15186263588304877);
-  p = fma(p, s2, 0.16972882833987804);
-  p = fma(p, s2, 0.19235933878519512);
-  p = fma(p, s2, 0.22195308321368667);
-  p = fma(p, s2, 0.2623081892525388);
-  p = fma(p, s2, 0.3205988979753252);
-  p = fma(p, s2, 0.4121985831111324);
-  p = fma(p, s2, 0.5770780163555853);
-  p = fma(p, s2, 0.9617966939259756);
-  p = fma(p, s2, 2.8853900817779268);
+  double p = LOG2_C[0];
+#pragma unroll
+  for (int j = 1; j < 12; ++j) p = fma(p, s2, LOG2_C[j]);
   return fma(p, s, (double)e);
 }
 
@@ -113,20 +114,9 @@ __device__ __forceinline__ double exp2_fast(double t) {
   const double kd0 = t + 6755399441055744.0;          // 1.5 * 2^52: the low word now holds rint(t)
   const int k = __double2loint(kd0);
   const double f = t - (kd0 - 6755399441055744.0);
-  double p = 1.3691488853904128e-12;
-  p = fma(p, f, 2.5678435993488206e-11);
-  p = fma(p, f, 4.4455382718708116e-10);
-  p = fma(p, f, 7.054911620801123e-09);
-  p = fma(p, f, 1.01780860092397e-07);
-  p = fma(p, f, 1.321548679014431e-06);
-  p = fma(p, f, 1.5252733804059841e-05);
-  p = fma(p, f, 0.0001540353039338161);
-  p = fma(p, f, 0.0013333558146428443);
-  p = fma(p, f, 0.009618129107628477);
-  p = fma(p, f, 0.05550410866482158);
-  p = fma(p, f, 0.24022650695910072);
-  p = fma(p, f, 0.6931471805599453);
-  p = fma(p, f, 1.0);
+  double p = EXP2_C[0];
+#pragma unroll
+  for (int j = 1; j < 14; ++j) p = fma(p, f, EXP2_C[j]);
   return p * __hiloint2double((k + 1023) << 20, 0);
 }
 
