@@ -131,6 +131,7 @@ class ClockSampler:
         self.idx, self.rows, self.proc, self.nv, self.h = gpu_index, [], None, None, None
         self.stop_flag = False
         self.mx = None
+        self.period = float(os.environ.get("IVPB_BENCH_POLL_MS", "2")) * 1e-3
 
     def start(self):
         try:
@@ -164,7 +165,7 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, [k for k, b in bits.items() if r & b]))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
