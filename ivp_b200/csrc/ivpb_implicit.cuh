@@ -371,7 +371,9 @@ constexpr int implicit_min_blocks() {
   // re-measured after round 2 moved J / cont to shared memory and cached the reciprocals (ms per 2^18 trajectories at
   // 3 / 4 / 5 / 6 blocks): VdP mu=1000 RADAU 49.2 / 46.0 / 56.6 / 57.8, BDF 89.8 / 81.3 / 88.4 / 94.4 (n = 2);
   // Robertson RADAU 9.3 / 12.8 / - / 13.6, BDF 22.3 / 24.9 / - / 34.9 (n = 3)
-  return N <= 2 ? 4 : 3;
+  // re-measured once more after the decision shortcuts / triangular change_d (n = 2, 3 / 4 / 5 blocks): VdP mu=1000 RADAU
+  // 23.0 / 23.6 / 27.9 ms, BDF 53.3 / 53.3 / 53.1 ms -- RADAU's three-stage state likes the wider register budget
+  return (N <= 2 && METHOD != M_RADAU) ? 4 : 3;
 #endif
 }
 
